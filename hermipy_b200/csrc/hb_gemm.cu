@@ -1,0 +1,104 @@
+// Host launcher for the DMMA/TMA GEMM: builds the TMA tensor maps (cuTensorMapEncodeTiled obtained
+// through cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda) and picks
+// a tile configuration.
+#include "hb_gemm.cuh"
+#include "hb_internal.h"
+
+#include <cstdio>
+#include <mutex>
+
+namespace hb {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// rank-3 FP64 map: dims {d0 (contiguous), d1 (pitch ld elements), d2 (batch, stride elements)}
+static int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                    uint64_t ld, uint64_t stride, uint32_t b0, uint32_t b1) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return HB_ERR_CUDA;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {ld * 8, stride * 8};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[hermite_b200] cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu ld %llu\n",
+                (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                (unsigned long long)ld);
+        return HB_ERR_CUDA;
+    }
+    return HB_OK;
+}
+
+template <int BM, int BN, int WMc, int WNc, int ST, bool AM>
+static int launch_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    const uint64_t strideA = a.batch > 1 ? (uint64_t)a.strideA : (uint64_t)a.lda * (AM ? a.K : a.M);
+    const uint64_t strideB = a.batch > 1 ? (uint64_t)a.strideB : (uint64_t)a.ldb * a.K;
+    int rc;
+    if (AM)
+        rc = make_map(&tmA, a.A, a.M, a.K, a.batch, a.lda, strideA ? strideA : 2, 16, GEMM_BK);
+    else
+        rc = make_map(&tmA, a.A, a.K, a.M, a.batch, a.lda, strideA ? strideA : 2, GEMM_BK, BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, a.B, a.N, a.K, a.batch, a.ldb, strideB ? strideB : 2, 16, GEMM_BK);
+    if (rc) return rc;
+    auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM>;
+    constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return HB_ERR_CUDA;
+        attr_set = true;
+    }
+    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch);
+    kern<<<grid, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
+    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+}
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return HB_OK;
+    if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
+        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1))))
+        return HB_ERR_ALIGN;
+    GemmParams p;
+    p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
+    p.C = a.C; p.ldc = a.ldc; p.strideC = a.strideC;
+    p.epi = a.epi; p.lut = a.lut; p.P = a.P;
+    p.row_begin = a.row_begin; p.row_end = a.row_end; p.tri_degree = a.tri_degree;
+    p.alpha = a.alpha;
+    const long long tiles128 = (long long)((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;
+    int cfg = a.cfg;
+    if (cfg < 0) cfg = (tiles128 >= 148) ? 0 : 1;
+    if (a.a_mmajor) {
+        switch (cfg) {
+            case 0: return launch_cfg<128, 128, 4, 2, 4, true>(a, p, stream);
+            default: return launch_cfg<64, 64, 2, 2, 6, true>(a, p, stream);
+        }
+    } else {
+        switch (cfg) {
+            case 0: return launch_cfg<128, 128, 4, 2, 4, false>(a, p, stream);
+            default: return launch_cfg<64, 64, 2, 2, 6, false>(a, p, stream);
+        }
+    }
+}
+
+}  // namespace hb

@@ -1,0 +1,29 @@
+// Internal (non-ABI) declarations shared by the translation units of libhermite_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+
+#include "../../include/hermite_b200.h"
+
+namespace hb {
+
+struct GemmArgs {
+    int M = 0, N = 0, K = 0, batch = 1;
+    const double* A = nullptr;  // a_mmajor ? [K][M] : [M][K]
+    long long lda = 0, strideA = 0;
+    bool a_mmajor = false;
+    const double* B = nullptr;  // [K][N]
+    long long ldb = 0, strideB = 0;
+    double* C = nullptr;
+    long long ldc = 0, strideC = 0;
+    int epi = 0;
+    const int* lut = nullptr;
+    int P = 0, row_begin = 0, row_end = 0, tri_degree = -1;
+    double alpha = 1.0;
+    int cfg = -1;  // -1 auto, 0 = 128x128 tiles, 1 = 64x64 tiles
+};
+
+int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace hb
