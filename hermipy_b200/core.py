@@ -1,0 +1,264 @@
+"""Drop-in counterpart of the reference's hermipy/core.py (hermipy/core.py:125-348): the same function
+names, argument meaning and return types, but every numerical call goes through the C ABI of
+libhermite_b200.so (hand-written sm_100a CUDA) instead of the Boost.Python module `hermite_cpp`.
+
+NumPy arrays cross the boundary as contiguous float64 buffers (no per-element boxing as in
+core.py:29-66 of the reference).  Invalid input raises an exception where the reference would
+print a message and exit() the interpreter.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as ss
+
+from . import _lib
+from ._lib import c_dp, c_ip, c_up, check, lib
+
+VARF_MODE = {"reference": _lib.VARF_REFERENCE, "gram": _lib.VARF_GRAM}
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def _grid(nodes, weights):
+    nodes = [_d(n).ravel() for n in nodes]
+    weights = [_d(w).ravel() for w in weights]
+    n_pts = _i([len(n) for n in nodes])
+    return n_pts, _d(np.concatenate(nodes)), _d(np.concatenate(weights))
+
+
+def _fourier(do_fourier, dim):
+    return _i([0] * dim if do_fourier is None else do_fourier)
+
+
+# ---- iterator functions (hermipy/core.py:283-346) --------------------------------------------------
+
+_SETS = ("triangle", "cross", "cross_nc", "cube", "rectangle")
+
+
+def _check_set(index_set):
+    if index_set not in _SETS:
+        raise ValueError("Unknown index set")
+
+
+def iterator_get_degree(dim, n_polys, index_set="triangle"):
+    _check_set(index_set)
+    out = C.c_int(0)
+    check(lib().hb_index_get_degree(index_set.encode(), int(dim), int(n_polys), C.byref(out)))
+    return out.value
+
+
+def iterator_index(mult_ind, index_set="triangle"):
+    m = np.ascontiguousarray(mult_ind, dtype=np.uint32)
+    fn = {"triangle": lib().hb_triangle_index, "cube": lib().hb_cube_index}
+    if index_set not in fn:
+        raise ValueError("Unknown index set")
+    out = C.c_uint32(0)
+    check(fn[index_set](m.ctypes.data_as(c_up), len(m), C.byref(out)))
+    return int(out.value)
+
+
+def iterator_size(dim, degree, index_set="triangle"):
+    _check_set(index_set)
+    out = C.c_longlong(0)
+    check(lib().hb_index_size(index_set.encode(), int(dim), int(degree), C.byref(out)))
+    return int(out.value)
+
+
+def iterator_list_indices(dim, degree, index_set="triangle"):
+    n = iterator_size(dim, degree, index_set)
+    out = np.zeros((n, dim), dtype=np.uint32)
+    check(lib().hb_index_list(index_set.encode(), int(dim), int(degree), out.ctypes.data_as(c_up), out.size))
+    return np.asarray(out, dtype=int)
+
+
+# ---- wrapper functions (hermipy/core.py:125-281) ---------------------------------------------------
+
+def hermite_eval(x, degree):
+    """Normalised Hermite polynomials He_k(x)/sqrt(k!) for k <= degree at every x (hermite.cpp:29-41)."""
+    x = _d(np.atleast_1d(x))
+    out = np.zeros((len(x), degree + 1))
+    check(lib().hb_hermite_eval(_dp(x), len(x), int(degree), _dp(out)))
+    return out
+
+
+def integrate(fgrid, nodes, weights, do_fourier=None):
+    n_pts, nd, wt = _grid(nodes, weights)
+    f = _d(fgrid).ravel()
+    out = C.c_double(0)
+    check(lib().hb_integrate(len(n_pts), _ip(n_pts), _dp(f), _dp(nd), _dp(wt), _ip(_fourier(do_fourier, len(n_pts))),
+                             C.byref(out)))
+    return out.value
+
+
+def transform(degree, fgrid, nodes, weights, forward, do_fourier=None, index_set="triangle"):
+    n_pts, nd, wt = _grid(nodes, weights)
+    dim = len(n_pts)
+    degree = int(degree)
+    f = _d(fgrid).ravel()
+    n_grid = int(np.prod(n_pts))
+    n_polys = iterator_size(dim, degree, index_set)
+    n_in, n_out = (n_grid, n_polys) if forward else (n_polys, n_grid)
+    if len(f) != n_in:
+        raise ValueError("transform: input has %d entries, expected %d" % (len(f), n_in))
+    out = np.zeros(n_out)
+    check(lib().hb_transform(dim, _ip(n_pts), degree, _dp(f), _dp(nd), _dp(wt), _ip(_fourier(do_fourier, dim)),
+                             int(bool(forward)), index_set.encode(), _dp(out), n_out))
+    return out
+
+
+def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, index_set="triangle"):
+    """`batch` independent transforms in one call; fgrids has shape (batch, n_in).  No reference equivalent
+    (the reference loops over hm.Quad.transform in Python)."""
+    n_pts, nd, wt = _grid(nodes, weights)
+    dim = len(n_pts)
+    f = _d(fgrids)
+    batch = f.shape[0]
+    f = f.reshape(batch, -1)
+    n_grid = int(np.prod(n_pts))
+    n_polys = iterator_size(dim, int(degree), index_set)
+    n_in, n_out = (n_grid, n_polys) if forward else (n_polys, n_grid)
+    if f.shape[1] != n_in:
+        raise ValueError("transform_batch: rows have %d entries, expected %d" % (f.shape[1], n_in))
+    out = np.zeros((batch, n_out))
+    check(lib().hb_transform_batch(dim, _ip(n_pts), int(degree), batch, _dp(f), _dp(nd), _dp(wt),
+                                   _ip(_fourier(do_fourier, dim)), int(bool(forward)), index_set.encode(),
+                                   _dp(out), n_out))
+    return out
+
+
+def triple_products(degree):
+    out = np.zeros((2 * degree + 1, degree + 1, degree + 1))
+    check(lib().hb_triple_products(int(degree), _dp(out)))
+    return out
+
+
+def triple_products_fourier(degree):
+    out = np.zeros((2 * degree + 1, degree + 1, degree + 1))
+    check(lib().hb_triple_products_fourier(int(degree), _dp(out)))
+    return out
+
+
+def varf(degree, fgrid, nodes, weights, sparse=False, do_fourier=None, index_set="triangle", mode="reference"):
+    n_pts, nd, wt = _grid(nodes, weights)
+    dim = len(n_pts)
+    degree = int(degree)
+    f = _d(fgrid).ravel()
+    if len(f) != int(np.prod(n_pts)):
+        raise ValueError("varf: input has %d entries, expected %d" % (len(f), int(np.prod(n_pts))))
+    n = iterator_size(dim, degree, index_set)
+    four = _fourier(do_fourier, dim)
+    if not sparse:
+        out = np.zeros((n, n))
+        check(lib().hb_varf(dim, _ip(n_pts), degree, _dp(f), _dp(nd), _dp(wt), _ip(four), index_set.encode(),
+                            VARF_MODE[mode], _dp(out), n))
+        return out
+    nnz = C.c_longlong(0)
+    check(lib().hb_varf_sp(dim, _ip(n_pts), degree, _dp(f), _dp(nd), _dp(wt), _ip(four), index_set.encode(),
+                           VARF_MODE[mode], C.byref(nnz)))
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    indices = np.zeros(max(nnz.value, 1), dtype=np.int32)
+    data = np.zeros(max(nnz.value, 1))
+    check(lib().hb_sparse_fetch(indptr.ctypes.data_as(_lib.c_llp), _ip(indices), _dp(data)))
+    return ss.csr_matrix((data[:nnz.value], indices[:nnz.value], indptr), shape=(n, n))
+
+
+def varfd(dim, degree, direction, var, do_fourier=0, index_set="triangle"):
+    sparse = isinstance(var, ss.csr_matrix)
+    v = _d(var.toarray() if sparse else var)
+    out = np.zeros_like(v)
+    check(lib().hb_varfd(int(dim), int(degree), int(direction), _dp(v), v.shape[0], int(do_fourier),
+                         index_set.encode(), _dp(out)))
+    return ss.csr_matrix(out) if sparse else out
+
+
+def _tensorize_call(arrays, dirs_list, index_set, sparse):
+    arrays = [_d(a.toarray() if isinstance(a, ss.csr_matrix) else a) for a in arrays]
+    k = len(arrays)
+    matrices = arrays[0].ndim == 2
+    lens = _i([a.shape[0] for a in arrays])
+    dflat = _i(np.concatenate([np.asarray(d, dtype=np.int32) for d in dirs_list]))
+    dlens = _i([len(d) for d in dirs_list])
+    dim = int(dlens.sum())
+    degree = iterator_get_degree(len(dirs_list[0]), arrays[0].shape[0], index_set)
+    n = iterator_size(dim, degree, index_set)
+    ptrs = (c_dp * k)(*[_dp(a) for a in arrays])
+    if matrices:
+        out = np.zeros((n, n))
+        check(lib().hb_tensorize_mats(k, ptrs, _ip(lens), _ip(dflat), _ip(dlens), index_set.encode(), _dp(out), n))
+        return ss.csr_matrix(out) if sparse else out
+    out = np.zeros(n)
+    check(lib().hb_tensorize_vecs(k, ptrs, _ip(lens), _ip(dflat), _ip(dlens), index_set.encode(), _dp(out), n))
+    return out
+
+
+def tensorize(inp, dim=None, direction=None, sparse=False, index_set="triangle"):
+    """hermipy/core.py:201-253: `inp` is a dict {frozenset(dirs): array}, a list (one factor per axis), or a
+    single array with (dim, direction) (tensorised with identities on the other axes)."""
+    if isinstance(inp, dict):
+        any_elem = list(inp.values())[0]
+        if isinstance(any_elem, (float, int)):
+            return np.prod([inp[k] for k in inp])
+        assert isinstance(any_elem, (np.ndarray, ss.csr_matrix))
+        assert len(any_elem.shape) in (1, 2)
+        dirs_list = [sorted(dirs) for dirs in inp.keys()]
+        return _tensorize_call(list(inp.values()), dirs_list, index_set, sparse)
+    if isinstance(inp, list):
+        assert dim is None and direction is None
+        if isinstance(inp[0], (float, int)):
+            return np.prod(inp)
+        return _tensorize_call(inp, [[i] for i in range(len(inp))], index_set, sparse)
+    assert dim is not None and direction is not None
+    a = _d(inp.toarray() if isinstance(inp, ss.csr_matrix) else inp)
+    # tensorize_vec_id / tensorize_mat_id (tensorize.cpp:145-152, 373-381): identity factors elsewhere
+    if a.ndim == 1:
+        unit = np.zeros(len(a))
+        unit[0] = 1.0
+    else:
+        unit = np.eye(a.shape[0])
+    factors = [unit] * dim
+    factors[direction] = a
+    return _tensorize_call(factors, [[i] for i in range(dim)], index_set, sparse)
+
+
+def project(inp, dim, directions, index_set="triangle"):
+    if isinstance(directions, int):
+        directions = [directions]
+    sparse = isinstance(inp, ss.csr_matrix)
+    if isinstance(inp, list):
+        inp = np.asarray(inp, dtype=float)
+    a = _d(inp.toarray() if sparse else inp)
+    dirs = _i(directions)
+    degree = iterator_get_degree(dim, a.shape[0], index_set)
+    n = iterator_size(len(dirs), degree, index_set)
+    if a.ndim == 1:
+        out = np.zeros(n)
+        check(lib().hb_project_vec(_dp(a), len(a), int(dim), _ip(dirs), len(dirs), index_set.encode(), _dp(out), n))
+        return out
+    out = np.zeros((n, n))
+    check(lib().hb_project_mat(_dp(a), a.shape[0], int(dim), _ip(dirs), len(dirs), index_set.encode(), _dp(out), n))
+    return ss.csr_matrix(out) if sparse else out
+
+
+def inner(s1, s2, d1, d2, index_set="triangle"):
+    s1, s2, d1, d2 = _d(s1), _d(s2), _i(d1), _i(d2)
+    degree = iterator_get_degree(len(d1), len(s1), index_set)
+    n_res = len(set(d1.tolist()) ^ set(d2.tolist()))
+    n = iterator_size(n_res, degree, index_set) if n_res > 0 else 1
+    out = np.zeros(n)
+    check(lib().hb_inner(_dp(s1), len(s1), _dp(s2), len(s2), _ip(d1), len(d1), _ip(d2), len(d2),
+                         index_set.encode(), _dp(out), n))
+    return out

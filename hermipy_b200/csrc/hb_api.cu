@@ -1,0 +1,531 @@
+// C ABI of libhermite_b200.so (declared in include/hermite_b200.h).  Host-pointer entry points mirror
+// the functions of the reference's `hermite_cpp` module (cpp/src/hermite/python/module.cpp:85-167):
+// they look up (or build) a cached plan, stage the operands to the device, run the CUDA path and copy
+// the result back.  There is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <list>
+#include <mutex>
+#include <vector>
+
+#include "hb_kernels.h"
+#include "hb_plan.h"
+
+namespace hb {
+const char* last_error();
+long long launch_count(int reset);
+
+namespace {
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+struct PlanKey {
+    uint64_t hash;
+    int dim, degree, set;
+    std::vector<int> n_pts, fourier;
+    std::vector<double> nodes, weights;
+    bool operator==(const PlanKey& o) const {
+        return hash == o.hash && dim == o.dim && degree == o.degree && set == o.set && n_pts == o.n_pts &&
+               fourier == o.fourier && nodes == o.nodes && weights == o.weights;
+    }
+};
+
+struct CacheEntry { PlanKey key; hb_plan* plan; };
+std::mutex g_plan_mutex;
+std::list<CacheEntry> g_plans;  // most recently used first
+const size_t kMaxPlans = 12;
+
+int check_device() {
+    static int state = -1;
+    if (state < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            set_error("no usable CUDA device (%s); libhermite_b200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+            return HB_ERR_CUDA;
+        }
+        state = 1;
+    }
+    return HB_OK;
+}
+
+int cached_plan(hb_plan** out, int dim, const int* n_pts, int degree, const double* nodes, const double* weights,
+                const int* do_fourier, const char* index_set) {
+    HB_TRY(check_device());
+    const int set = index_set_from_name(index_set);
+    if (set < 0) { set_error("Invalid index set!"); return HB_ERR_INDEX_SET; }
+    if (dim < 1 || dim > HB_MAX_DIM || !n_pts) return HB_ERR_INVALID;
+    PlanKey key;
+    key.dim = dim; key.degree = degree; key.set = set;
+    key.n_pts.assign(n_pts, n_pts + dim);
+    key.fourier.assign(dim, 0);
+    if (do_fourier) key.fourier.assign(do_fourier, do_fourier + dim);
+    size_t tot = 0;
+    for (int a = 0; a < dim; a++) { if (n_pts[a] < 1) return HB_ERR_INVALID; tot += n_pts[a]; }
+    key.nodes.assign(nodes, nodes + tot);
+    key.weights.assign(weights, weights + tot);
+    uint64_t h = 1469598103934665603ull;
+    h = fnv1a(key.n_pts.data(), dim * 4, h);
+    h = fnv1a(key.fourier.data(), dim * 4, h);
+    h = fnv1a(key.nodes.data(), tot * 8, h);
+    h = fnv1a(key.weights.data(), tot * 8, h);
+    h = fnv1a(&degree, 4, h);
+    h = fnv1a(&set, 4, h);
+    key.hash = h;
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    for (auto it = g_plans.begin(); it != g_plans.end(); ++it)
+        if (it->key == key) {
+            g_plans.splice(g_plans.begin(), g_plans, it);
+            *out = g_plans.front().plan;
+            return HB_OK;
+        }
+    hb_plan* pl = nullptr;
+    HB_TRY(plan_create(&pl, dim, n_pts, degree, nodes, weights, key.fourier.data(), set));
+    g_plans.push_front(CacheEntry{std::move(key), pl});
+    while (g_plans.size() > kMaxPlans) {
+        delete g_plans.back().plan;
+        g_plans.pop_back();
+    }
+    *out = pl;
+    return HB_OK;
+}
+
+// staging buffers shared by the host-pointer entry points (one call at a time per process)
+std::mutex g_call_mutex;
+DevBuf g_in, g_out, g_aux[HB_MAX_FACTORS], g_auxi[HB_MAX_FACTORS];
+
+// last sparse result
+DevBuf g_sp_indptr, g_sp_indices, g_sp_data, g_sp_rownnz;
+long long g_sp_rows = 0, g_sp_nnz = 0;
+std::vector<long long> g_sp_indptr_host;
+
+int upload_grid(const hb_plan* pl, const double* f, int batch, double* dst) {
+    const Axis& L = pl->ax[pl->dim - 1];
+    HB_CUDA(cudaMemcpy2DAsync(dst, (size_t)L.np * 8, f, (size_t)L.n * 8, (size_t)L.n * 8,
+                              (size_t)pl->grid_rows * batch, cudaMemcpyHostToDevice, 0));
+    return HB_OK;
+}
+
+int set_or_err(const char* index_set) {
+    const int set = index_set_from_name(index_set);
+    if (set < 0) set_error("Invalid index set!");
+    return set;
+}
+
+// position LUT: for every multi-index of `full` restricted to `dirs` -> position in `sub` (or -1)
+std::vector<int> restriction_map(const IndexSet& full, const std::vector<int>& dirs, const IndexSet& sub) {
+    std::vector<int> map(full.size);
+    std::vector<uint32_t> m(dirs.size());
+    for (uint32_t i = 0; i < full.size; i++) {
+        for (size_t j = 0; j < dirs.size(); j++) m[j] = full.list[(size_t)i * full.dim + dirs[j]];
+        map[i] = sub.position(m.data());
+    }
+    return map;
+}
+
+}  // namespace
+}  // namespace hb
+
+using namespace hb;
+
+extern "C" {
+
+const char* hb_last_error(void) { return hb::last_error(); }
+const char* hb_version(void) { return "hermite_b200 0.1 (sm_100a)"; }
+long long hb_launch_count(int reset) { return hb::launch_count(reset); }
+
+int hb_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); if (count) *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    if (count) *count = n;
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int hb_index_size(const char* index_set, int dim, int degree, long long* size) {
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    const long long s = index_size(set, dim, degree);
+    if (s < 0) { set_error("index_size: invalid (dim %d, degree %d)", dim, degree); return HB_ERR_INVALID; }
+    *size = s;
+    return HB_OK;
+}
+
+int hb_index_get_degree(const char* index_set, int dim, long long n_polys, int* degree) {
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    if (index_get_degree(set, dim, n_polys, degree)) {
+        set_error("Can't find a degree with %lld polynomials in dimension %d", n_polys, dim);
+        return HB_ERR_DEGREE;
+    }
+    return HB_OK;
+}
+
+int hb_index_list(const char* index_set, int dim, int degree, uint32_t* out, size_t cap) {
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    auto s = get_index_set(set, dim, degree);
+    if (!s) { set_error("index_list: invalid (dim %d, degree %d)", dim, degree); return HB_ERR_INVALID; }
+    if (cap < s->list.size()) return HB_ERR_NOMEM;
+    memcpy(out, s->list.data(), s->list.size() * sizeof(uint32_t));
+    return HB_OK;
+}
+
+int hb_triangle_index(const uint32_t* m, int dim, uint32_t* index) {
+    if (!m || dim < 1) return HB_ERR_INVALID;
+    *index = triangle_index(m, dim);
+    return HB_OK;
+}
+int hb_cube_index(const uint32_t* m, int dim, uint32_t* index) {
+    if (!m || dim < 1) return HB_ERR_INVALID;
+    *index = cube_index(m, dim);
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int hb_hermite_eval(const double* x, int n, int degree, double* out) {
+    HB_TRY(check_device());
+    if (n < 0 || degree < 0) return HB_ERR_INVALID;
+    if (n == 0) return HB_OK;
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    const int P = degree + 1;
+    HB_TRY(g_in.ensure((size_t)n * 8));
+    HB_TRY(g_out.ensure((size_t)n * P * 8));
+    HB_CUDA(cudaMemcpyAsync(g_in.p, x, (size_t)n * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(launch_basis_tables(g_in.d(), nullptr, n, P, 0, g_out.d(), nullptr, P, nullptr, nullptr, 0, 0));
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, (size_t)n * P * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const double* f, const double* nodes,
+                       const double* weights, const int* do_fourier, int forward, const char* index_set,
+                       double* out, size_t out_len_each) {
+    hb_plan* pl = nullptr;
+    HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
+    if (batch < 1) return HB_OK;
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    const Axis& L = pl->ax[dim - 1];
+    const long long n_grid = pl->grid_rows * L.n;
+    const long long cstride = even_up(pl->n_polys);
+    if (forward) {
+        if (out_len_each != (size_t)pl->n_polys) { set_error("transform: out_len %zu != n_polys %lld", out_len_each, pl->n_polys); return HB_ERR_INVALID; }
+        HB_TRY(g_in.ensure((size_t)batch * pl->grid_size * 8));
+        HB_TRY(g_out.ensure((size_t)batch * cstride * 8));
+        HB_TRY(upload_grid(pl, f, batch, g_in.d()));
+        HB_TRY(plan_forward(pl, g_in.d(), pl->grid_size, batch, g_out.d(), cstride, 0));
+        HB_CUDA(cudaMemcpy2DAsync(out, (size_t)pl->n_polys * 8, g_out.p, (size_t)cstride * 8, (size_t)pl->n_polys * 8,
+                                  batch, cudaMemcpyDeviceToHost, 0));
+    } else {
+        if (out_len_each != (size_t)n_grid) { set_error("transform: out_len %zu != grid size %lld", out_len_each, n_grid); return HB_ERR_INVALID; }
+        HB_TRY(g_in.ensure((size_t)batch * cstride * 8));
+        HB_TRY(g_out.ensure((size_t)batch * pl->grid_size * 8));
+        HB_CUDA(cudaMemcpy2DAsync(g_in.p, (size_t)cstride * 8, f, (size_t)pl->n_polys * 8, (size_t)pl->n_polys * 8,
+                                  batch, cudaMemcpyHostToDevice, 0));
+        HB_TRY(plan_backward(pl, g_in.d(), cstride, batch, g_out.d(), pl->grid_size, 0));
+        HB_CUDA(cudaMemcpy2DAsync(out, (size_t)L.n * 8, g_out.p, (size_t)L.np * 8, (size_t)L.n * 8,
+                                  (size_t)pl->grid_rows * batch, cudaMemcpyDeviceToHost, 0));
+    }
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+int hb_transform(int dim, const int* n_pts, int degree, const double* f, const double* nodes,
+                 const double* weights, const int* do_fourier, int forward, const char* index_set, double* out,
+                 size_t out_len) {
+    return hb_transform_batch(dim, n_pts, degree, 1, f, nodes, weights, do_fourier, forward, index_set, out, out_len);
+}
+
+int hb_integrate(int dim, const int* n_pts, const double* f, const double* nodes, const double* weights,
+                 const int* do_fourier, double* result) {
+    // transform.cpp:170-181: degree-0 triangle transform, times sqrt(2 pi) per Fourier axis
+    double c0 = 0;
+    HB_TRY(hb_transform(dim, n_pts, 0, f, nodes, weights, do_fourier, 1, "triangle", &c0, 1));
+    double factor = 1;
+    for (int a = 0; a < dim; a++)
+        if (do_fourier && do_fourier[a] == 1) factor *= std::sqrt(2 * M_PI);
+    *result = factor * c0;
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int triple_products_impl(int degree, bool fourier, double* out) {
+    HB_TRY(check_device());
+    if (degree < 0) return HB_ERR_INVALID;
+    if (fourier && (degree % 2 == 1)) { set_error("Use even degree for Fourier"); return HB_ERR_FOURIER_DEGREE; }
+    const int P = degree + 1, Pp = (int)even_up(P), K = 2 * degree + 1;
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(g_out.ensure((size_t)K * P * Pp * 8));
+    if (fourier) {
+        std::vector<double> h;
+        fourier_triple_products_host(degree, Pp, h);
+        for (int k = 0; k < K; k++)
+            for (int i = 0; i < P; i++) memcpy(out + ((size_t)k * P + i) * P, &h[((size_t)k * P + i) * Pp], P * 8);
+        return HB_OK;
+    }
+    HB_TRY(launch_triple_products(degree, Pp, g_out.d(), 0));
+    HB_CUDA(cudaMemcpy2DAsync(out, (size_t)P * 8, g_out.p, (size_t)Pp * 8, (size_t)P * 8, (size_t)K * P,
+                              cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+int hb_triple_products(int degree, double* out) { return triple_products_impl(degree, false, out); }
+int hb_triple_products_fourier(int degree, double* out) { return triple_products_impl(degree, true, out); }
+
+static int varf_to_device(hb_plan** plp, int dim, const int* n_pts, int degree, const double* f, const double* nodes,
+                          const double* weights, const int* do_fourier, const char* index_set, int mode) {
+    hb_plan* pl = nullptr;
+    HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
+    *plp = pl;
+    HB_TRY(g_in.ensure((size_t)pl->grid_size * 8));
+    HB_TRY(g_out.ensure((size_t)pl->n_polys * pl->n_polys * 8));
+    HB_TRY(upload_grid(pl, f, 1, g_in.d()));
+    return plan_varf(pl, g_in.d(), mode, g_out.d(), pl->n_polys, 0, pl->n_polys, 0);
+}
+
+int hb_varf(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
+            const int* do_fourier, const char* index_set, int mode, double* out, size_t n_polys) {
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    hb_plan* pl = nullptr;
+    HB_TRY(varf_to_device(&pl, dim, n_pts, degree, f, nodes, weights, do_fourier, index_set, mode));
+    if (n_polys != (size_t)pl->n_polys) { set_error("varf: n_polys %zu != %lld", n_polys, pl->n_polys); return HB_ERR_INVALID; }
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, n_polys * n_polys * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+int hb_varf_sp(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
+               const int* do_fourier, const char* index_set, int mode, long long* nnz) {
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    hb_plan* pl = nullptr;
+    HB_TRY(varf_to_device(&pl, dim, n_pts, degree, f, nodes, weights, do_fourier, index_set, mode));
+    const int n = (int)pl->n_polys;
+    HB_TRY(g_sp_rownnz.ensure((size_t)n * 8));
+    HB_TRY(launch_count_nnz(g_out.d(), n, n, n, static_cast<long long*>(g_sp_rownnz.p), 0));
+    std::vector<long long> rn(n);
+    HB_CUDA(cudaMemcpyAsync(rn.data(), g_sp_rownnz.p, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    g_sp_indptr_host.assign(n + 1, 0);
+    for (int i = 0; i < n; i++) g_sp_indptr_host[i + 1] = g_sp_indptr_host[i] + rn[i];
+    g_sp_rows = n;
+    g_sp_nnz = g_sp_indptr_host[n];
+    HB_TRY(g_sp_indptr.ensure((size_t)(n + 1) * 8));
+    HB_TRY(g_sp_indices.ensure(std::max<size_t>(g_sp_nnz, 1) * 4));
+    HB_TRY(g_sp_data.ensure(std::max<size_t>(g_sp_nnz, 1) * 8));
+    HB_CUDA(cudaMemcpyAsync(g_sp_indptr.p, g_sp_indptr_host.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(launch_fill_csr(g_out.d(), n, n, n, static_cast<long long*>(g_sp_indptr.p), g_sp_indices.i(),
+                           g_sp_data.d(), 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    *nnz = g_sp_nnz;
+    return HB_OK;
+}
+
+int hb_sparse_fetch(long long* indptr, int* indices, double* data) {
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    if (g_sp_rows <= 0) { set_error("hb_sparse_fetch: no sparse result"); return HB_ERR_INVALID; }
+    memcpy(indptr, g_sp_indptr_host.data(), (size_t)(g_sp_rows + 1) * 8);
+    if (g_sp_nnz) {
+        HB_CUDA(cudaMemcpy(indices, g_sp_indices.p, (size_t)g_sp_nnz * 4, cudaMemcpyDeviceToHost));
+        HB_CUDA(cudaMemcpy(data, g_sp_data.p, (size_t)g_sp_nnz * 8, cudaMemcpyDeviceToHost));
+    }
+    return HB_OK;
+}
+
+int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_polys, int do_fourier,
+             const char* index_set, double* out) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    auto s = get_index_set(set, dim, degree);
+    if (!s || direction < 0 || direction >= dim) return HB_ERR_INVALID;
+    if (n_polys != s->size) { set_error("varfd: matrix size %zu != n_polys %u", n_polys, s->size); return HB_ERR_INVALID; }
+    const int n = (int)n_polys;
+    // column map (varf.cpp:423-453): entry (i, j) = factor(m_j) * var[i][index(m_j -/+ e_dir)]
+    std::vector<int> src(n, -1);
+    std::vector<double> fac(n, 0.0);
+    std::vector<uint32_t> m(dim);
+    for (int j = 0; j < n; j++) {
+        for (int a = 0; a < dim; a++) m[a] = s->list[(size_t)j * dim + a];
+        const uint32_t md = m[direction];
+        if (md == 0) continue;
+        if (do_fourier == 0) {
+            m[direction] = md - 1;
+            fac[j] = std::sqrt((double)md);
+        } else {
+            const bool is_cos = (md % 2) == 0;
+            m[direction] = is_cos ? md - 1 : md + 1;
+            const double wave = (double)((md + (is_cos ? 0 : 1)) / 2);
+            fac[j] = is_cos ? -wave : wave;
+        }
+        src[j] = s->position(m.data());
+    }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(g_in.ensure(n_polys * n_polys * 8));
+    HB_TRY(g_out.ensure(n_polys * n_polys * 8));
+    HB_TRY(g_auxi[0].ensure((size_t)n * 4));
+    HB_TRY(g_aux[0].ensure((size_t)n * 8));
+    HB_CUDA(cudaMemcpyAsync(g_in.p, var, n_polys * n_polys * 8, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_auxi[0].p, src.data(), (size_t)n * 4, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_aux[0].p, fac.data(), (size_t)n * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(launch_varfd(g_in.d(), g_auxi[0].i(), g_aux[0].d(), g_out.d(), n, 0));
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, n_polys * n_polys * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int tensorize_impl(int k, const double* const* inputs, const int* lens, const int* dirs_flat,
+                          const int* dir_lens, const char* index_set, bool matrices, double* out, size_t out_n) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    if (k < 1 || k > HB_MAX_FACTORS) { set_error("tensorize: between 1 and %d factors supported", HB_MAX_FACTORS); return HB_ERR_INVALID; }
+    int dim = 0;
+    std::vector<std::vector<int>> dirs(k);
+    for (int j = 0, off = 0; j < k; j++) {
+        dirs[j].assign(dirs_flat + off, dirs_flat + off + dir_lens[j]);
+        off += dir_lens[j];
+        dim += dir_lens[j];
+    }
+    std::vector<char> seen(dim, 0);
+    for (auto& dj : dirs)
+        for (int v : dj) {
+            if (v < 0 || v >= dim) { set_error("Missing direction, exiting ..."); return HB_ERR_INVALID; }
+            if (seen[v]) { set_error("The same direction appears twice, exiting ..."); return HB_ERR_INVALID; }
+            seen[v] = 1;
+        }
+    int degree = 0;
+    if (index_get_degree(set, dir_lens[0], lens[0], &degree)) {
+        set_error("Can't find a degree with %d polynomials in dimension %d", lens[0], dir_lens[0]);
+        return HB_ERR_DEGREE;
+    }
+    auto full = get_index_set(set, dim, degree);
+    if (!full) return HB_ERR_INVALID;
+    if (out_n != full->size) { set_error("tensorize: output size %zu != %u", out_n, full->size); return HB_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    TensorizeArgs a;
+    a.k = k;
+    for (int j = 0; j < k; j++) {
+        auto sub = get_index_set(set, dir_lens[j], degree);
+        if (!sub || (int)sub->size != lens[j]) {
+            set_error("Size of input does not match dimension! Expected dimension: %u Actual dimension: %d",
+                      sub ? sub->size : 0u, lens[j]);
+            return HB_ERR_INVALID;
+        }
+        std::vector<int> map = restriction_map(*full, dirs[j], *sub);
+        const size_t in_elems = matrices ? (size_t)lens[j] * lens[j] : (size_t)lens[j];
+        HB_TRY(g_aux[j].ensure(in_elems * 8));
+        HB_TRY(g_auxi[j].ensure(map.size() * 4));
+        HB_CUDA(cudaMemcpyAsync(g_aux[j].p, inputs[j], in_elems * 8, cudaMemcpyHostToDevice, 0));
+        HB_CUDA(cudaMemcpyAsync(g_auxi[j].p, map.data(), map.size() * 4, cudaMemcpyHostToDevice, 0));
+        HB_CUDA(cudaStreamSynchronize(0));  // `map` is a temporary
+        a.in[j] = g_aux[j].d();
+        a.map[j] = g_auxi[j].i();
+        a.size[j] = lens[j];
+    }
+    const size_t out_elems = matrices ? out_n * out_n : out_n;
+    HB_TRY(g_out.ensure(out_elems * 8));
+    HB_TRY(launch_tensorize(a, matrices, g_out.d(), (int)out_n, 0));
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, out_elems * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+int hb_tensorize_vecs(int k, const double* const* inputs, const int* lens, const int* dirs_flat,
+                      const int* dir_lens, const char* index_set, double* out, size_t out_len) {
+    return tensorize_impl(k, inputs, lens, dirs_flat, dir_lens, index_set, false, out, out_len);
+}
+int hb_tensorize_mats(int k, const double* const* inputs, const int* sizes, const int* dirs_flat,
+                      const int* dir_lens, const char* index_set, double* out, size_t n_out) {
+    return tensorize_impl(k, inputs, sizes, dirs_flat, dir_lens, index_set, true, out, n_out);
+}
+
+static int project_impl(const double* input, size_t n_in, int dim, const int* dirs, int n_dirs, const char* index_set,
+                        bool matrix, double* out, size_t n_out) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    if (n_dirs < 1 || n_dirs > dim) return HB_ERR_INVALID;
+    int degree = 0;
+    if (index_get_degree(set, dim, (long long)n_in, &degree)) {
+        set_error("Can't find a degree with %zu polynomials in dimension %d", n_in, dim);
+        return HB_ERR_DEGREE;
+    }
+    auto full = get_index_set(set, dim, degree);
+    auto sub = get_index_set(set, n_dirs, degree);
+    if (!full || !sub) return HB_ERR_INVALID;
+    if (n_out != sub->size) { set_error("project: output size %zu != %u", n_out, sub->size); return HB_ERR_INVALID; }
+    // sel[i] = position in the full set of sub-index i embedded on dirs (zeros elsewhere); project.cpp:48-56
+    // scans the full set and writes aligned entries, which visits each sub-index at most once.
+    std::vector<int> sel(n_out, -1);
+    std::vector<uint32_t> m(dim);
+    for (uint32_t i = 0; i < sub->size; i++) {
+        std::fill(m.begin(), m.end(), 0u);
+        for (int j = 0; j < n_dirs; j++) {
+            if (dirs[j] < 0 || dirs[j] >= dim) return HB_ERR_INVALID;
+            m[dirs[j]] = sub->list[(size_t)i * n_dirs + j];
+        }
+        sel[i] = full->position(m.data());
+    }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    const size_t in_elems = matrix ? n_in * n_in : n_in, out_elems = matrix ? n_out * n_out : n_out;
+    HB_TRY(g_in.ensure(in_elems * 8));
+    HB_TRY(g_out.ensure(out_elems * 8));
+    HB_TRY(g_auxi[0].ensure(n_out * 4));
+    HB_CUDA(cudaMemcpyAsync(g_in.p, input, in_elems * 8, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_auxi[0].p, sel.data(), n_out * 4, cudaMemcpyHostToDevice, 0));
+    HB_TRY(launch_project(g_in.d(), (int)n_in, g_auxi[0].i(), matrix, g_out.d(), (int)n_out, 0));
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, out_elems * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+int hb_project_vec(const double* input, size_t len, int dim, const int* dirs, int n_dirs, const char* index_set,
+                   double* out, size_t out_len) {
+    return project_impl(input, len, dim, dirs, n_dirs, index_set, false, out, out_len);
+}
+int hb_project_mat(const double* input, size_t n, int dim, const int* dirs, int n_dirs, const char* index_set,
+                   double* out, size_t n_out) {
+    return project_impl(input, n, dim, dirs, n_dirs, index_set, true, out, n_out);
+}
+
+int hb_inner(const double*, size_t, const double*, size_t, const int*, int, const int*, int, const char*, double*,
+             size_t) {
+    set_error("hb_inner: not implemented yet (SURVEY.md section 8f, rank 3)");
+    return HB_ERR_INVALID;
+}
+
+// ---------------------------------------------------------------------------------------------
+int hb_plan_create(hb_plan** plan, int dim, const int* n_pts, int degree, const double* nodes,
+                   const double* weights, const int* do_fourier, const char* index_set) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    return plan_create(plan, dim, n_pts, degree, nodes, weights, do_fourier, set);
+}
+void hb_plan_destroy(hb_plan* plan) { delete plan; }
+long long hb_plan_n_polys(const hb_plan* plan) { return plan->n_polys; }
+long long hb_plan_grid_pitch(const hb_plan* plan) { return plan->ax[plan->dim - 1].np; }
+long long hb_plan_grid_size(const hb_plan* plan) { return plan->grid_size; }
+int hb_plan_forward(hb_plan* plan, const double* d_f, long long f_stride, int batch, double* d_coef,
+                    long long coef_stride, void* stream) {
+    return plan_forward(plan, d_f, f_stride, batch, d_coef, coef_stride, static_cast<cudaStream_t>(stream));
+}
+int hb_plan_backward(hb_plan* plan, const double* d_coef, long long coef_stride, int batch, double* d_f,
+                     long long f_stride, void* stream) {
+    return plan_backward(plan, d_coef, coef_stride, batch, d_f, f_stride, static_cast<cudaStream_t>(stream));
+}
+int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
+                 long long row_end, void* stream) {
+    return plan_varf(plan, d_f, mode, d_out, ldo, row_begin, row_end, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

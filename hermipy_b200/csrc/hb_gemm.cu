@@ -3,6 +3,7 @@
 // a tile configuration.
 #include "hb_gemm.cuh"
 #include "hb_internal.h"
+#include "hb_plan.h"
 
 #include <cstdio>
 #include <mutex>
@@ -49,18 +50,28 @@ static int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1
 }
 
 template <int BM, int BN, int WMc, int WNc, int ST, bool AM>
-static int launch_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
-    const uint64_t strideA = a.batch > 1 ? (uint64_t)a.strideA : (uint64_t)a.lda * (AM ? a.K : a.M);
-    const uint64_t strideB = a.batch > 1 ? (uint64_t)a.strideB : (uint64_t)a.ldb * a.K;
+    // A batch stride of 0 means "shared operand": the map gets a batch extent of 1 and the kernel
+    // multiplies the batch coordinate by a_bmul/b_bmul = 0.
+    const bool a_batched = a.batch > 1 && a.strideA != 0, b_batched = a.batch > 1 && a.strideB != 0;
+    const uint64_t strideA = a_batched ? (uint64_t)a.strideA : (uint64_t)a.lda * (AM ? a.K : a.M);
+    const uint64_t strideB = b_batched ? (uint64_t)a.strideB : (uint64_t)a.ldb * a.K;
     int rc;
     if (AM)
-        rc = make_map(&tmA, a.A, a.M, a.K, a.batch, a.lda, strideA ? strideA : 2, 16, GEMM_BK);
+        rc = make_map(&tmA, a.A, a.M, a.K, a_batched ? a.batch : 1, a.lda, strideA, 16, GEMM_BK);
     else
-        rc = make_map(&tmA, a.A, a.K, a.M, a.batch, a.lda, strideA ? strideA : 2, GEMM_BK, BM);
+        rc = make_map(&tmA, a.A, a.K, a.M, a_batched ? a.batch : 1, a.lda, strideA, GEMM_BK, BM);
     if (rc) return rc;
-    rc = make_map(&tmB, a.B, a.N, a.K, a.batch, a.ldb, strideB ? strideB : 2, 16, GEMM_BK);
+    rc = make_map(&tmB, a.B, a.N, a.K, b_batched ? a.batch : 1, a.ldb, strideB, 16, GEMM_BK);
     if (rc) return rc;
+    GemmParams p = p_in;
+    p.tiles_m = (a.M + BM - 1) / BM;
+    p.tiles_n = (a.N + BN - 1) / BN;
+    p.a_bmul = a_batched ? 1 : 0;
+    p.b_bmul = b_batched ? 1 : 0;
+    const long long n_cta = (long long)p.tiles_m * p.tiles_n * a.batch;
+    if (n_cta > 0x7fffffffLL) return HB_ERR_INVALID;
     auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM>;
     constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
     static bool attr_set = false;
@@ -69,20 +80,20 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t strea
             return HB_ERR_CUDA;
         attr_set = true;
     }
-    dim3 grid((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, a.batch);
-    kern<<<grid, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
-    return cudaGetLastError() == cudaSuccess ? HB_OK : HB_ERR_CUDA;
+    kern<<<(unsigned)n_cta, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
+    return launch_status();
 }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return HB_OK;
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
-        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1))))
+        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1))) || a.K <= 0)
         return HB_ERR_ALIGN;
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
     p.C = a.C; p.ldc = a.ldc; p.strideC = a.strideC;
-    p.epi = a.epi; p.lut = a.lut; p.P = a.P;
+    p.epi = a.epi; p.lut = a.lut;
+    p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.row_begin = a.row_begin; p.row_end = a.row_end; p.tri_degree = a.tri_degree;
     p.alpha = a.alpha;
     const long long tiles128 = (long long)((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;

@@ -35,11 +35,14 @@ struct GemmParams {
     long long ldc;      // row pitch of C (EPI_STORE) / of the output matrix (EPI_VARF2D)
     long long strideC;  // batch stride of C / of the scattered output (EPI_LUT)
     int epi;
-    const int* lut;     // EPI_LUT: M*N entries; EPI_VARF2D: P*P entries
-    int P;              // EPI_VARF2D: per-axis basis count
+    const int* lut;     // EPI_LUT: M*N entries; EPI_VARF2D: P0*P1 entries (lex (m0,m1) -> position or -1)
+    int P0, Pp0;        // EPI_VARF2D: GEMM row = m0*Pp0 + n0 (axis-0 pair, n0 < P0 valid)
+    int P1, Pp1;        // EPI_VARF2D: GEMM col = m1*Pp1 + n1 (axis-1 pair, n1 < P1 valid)
     int row_begin, row_end;  // EPI_VARF2D: owned output rows [row_begin,row_end) (row sharding)
     int tri_degree;     // EPI_VARF2D: >=0 -> skip tiles with m0+m1 > tri_degree (triangle-like sets)
     double alpha;       // result scale
+    int tiles_m, tiles_n;    // grid is linear: blockIdx.x = (b*tiles_m + tile_m)*tiles_n + tile_n
+    int a_bmul, b_bmul;      // 0: operand shared by all batch entries, 1: batched
 };
 
 constexpr int GEMM_BK = 16;  // doubles per k-tile = one 128-byte swizzle span
@@ -65,13 +68,15 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES]
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    const int tile_n = blockIdx.x, tile_m = blockIdx.y, b = blockIdx.z;
+    const int tile_n = blockIdx.x % p.tiles_n;
+    const int tile_m = (blockIdx.x / p.tiles_n) % p.tiles_m;
+    const int b = blockIdx.x / (p.tiles_n * p.tiles_m);
     const int m_base = tile_m * BM, n_base = tile_n * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (p.epi == EPI_VARF2D && p.tri_degree >= 0) {
         // Triangle-like index sets keep only m0+m1 <= degree; the smallest m0 and m1 in this tile decide.
-        const int m0_min = m_base / p.P, m1_min = n_base / p.P;
+        const int m0_min = m_base / p.Pp0, m1_min = n_base / p.Pp1;
         if (m0_min + m1_min > p.tri_degree) return;
     }
 
@@ -102,13 +107,13 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
                 if (A_MMAJOR) {
 #pragma unroll
                     for (int g = 0; g < BM / 16; g++)
-                        tma_load_3d(sA + g * 2048, &tmA, full, m_base + 16 * g, k0, b);
+                        tma_load_3d(sA + g * 2048, &tmA, full, m_base + 16 * g, k0, b * p.a_bmul);
                 } else {
-                    tma_load_3d(sA, &tmA, full, k0, m_base, b);
+                    tma_load_3d(sA, &tmA, full, k0, m_base, b * p.a_bmul);
                 }
 #pragma unroll
                 for (int g = 0; g < BN / 16; g++)
-                    tma_load_3d(sB + g * 2048, &tmB, full, n_base + 16 * g, k0, b);
+                    tma_load_3d(sB + g * 2048, &tmB, full, n_base + 16 * g, k0, b * p.b_bmul);
             }
         }
         return;
@@ -207,14 +212,16 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
                     if (i1 >= 0) out[i1] = v1;
                 }
             } else {  // EPI_VARF2D
-                const int m0 = row / p.P, n0 = row - m0 * p.P;
+                const int m0 = row / p.Pp0, n0 = row - m0 * p.Pp0;
+                if (n0 >= p.P0) continue;
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     if (e == 1 && !has1) break;
                     const int c = col + e;
-                    const int m1 = c / p.P, n1 = c - m1 * p.P;
-                    const int r_out = p.lut[m0 * p.P + m1];
-                    const int c_out = p.lut[n0 * p.P + n1];
+                    const int m1 = c / p.Pp1, n1 = c - m1 * p.Pp1;
+                    if (n1 >= p.P1) continue;
+                    const int r_out = p.lut[m0 * p.P1 + m1];
+                    const int c_out = p.lut[n0 * p.P1 + n1];
                     if (r_out >= p.row_begin && r_out < p.row_end && c_out >= 0)
                         p.C[(long long)(r_out - p.row_begin) * p.ldc + c_out] = (e == 0 ? v0 : v1);
                 }

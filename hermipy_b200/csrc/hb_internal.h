@@ -11,7 +11,7 @@ namespace hb {
 struct GemmArgs {
     int M = 0, N = 0, K = 0, batch = 1;
     const double* A = nullptr;  // a_mmajor ? [K][M] : [M][K]
-    long long lda = 0, strideA = 0;
+    long long lda = 0, strideA = 0;  // stride 0 with batch > 1: operand shared by the batch
     bool a_mmajor = false;
     const double* B = nullptr;  // [K][N]
     long long ldb = 0, strideB = 0;
@@ -19,7 +19,7 @@ struct GemmArgs {
     long long ldc = 0, strideC = 0;
     int epi = 0;
     const int* lut = nullptr;
-    int P = 0, row_begin = 0, row_end = 0, tri_degree = -1;
+    int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, tri_degree = -1;
     double alpha = 1.0;
     int cfg = -1;  // -1 auto, 0 = 128x128 tiles, 1 = 64x64 tiles
 };

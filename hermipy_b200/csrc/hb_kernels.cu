@@ -1,0 +1,341 @@
+// HBM-bound helper kernels of the hot path: basis tables by three-term recurrence, exact triple
+// products, pitch repacking, index-map gathers (tensorize / project / varfd), and the "few retained
+// alpha" varf assembly.  All FP64; products and sums that decide reference parity are written with
+// explicit __dmul_rn/__dadd_rn so that nvcc does not contract them into FMAs the reference (compiled
+// for baseline x86-64, no FMA) does not have.
+#include "hb_kernels.h"
+#include "hb_plan.h"
+
+#include <cmath>
+
+namespace hb {
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// Basis tables.  Reference: hermite_eval (cpp/src/hermite/hermite.cpp:29-41, REC_A/REC_B
+// hermite.hpp:27-28) called per node from _transform (transform.cpp:77-111), Fourier branch :90-109.
+//   plain[i][k] = phi_k(x_i)              (inverse transform / eval)
+//   wgt  [i][k] = w_i * phi_k(x_i)        (forward transform: the reference forms f*w*phi, :121-139)
+// and their transposes [k][i].  One thread per node; the k-recurrence runs in registers in exactly the
+// reference's operation order ((A*x)*v_k - B*v_{k-1}); rows are written coalesced for the [k][i]
+// copies.  w_i == 0 gives wgt = 0 even where phi overflowed (the reference would produce 0*inf = NaN).
+__global__ void basis_tables_kernel(const double* __restrict__ x, const double* __restrict__ w, int n, int P,
+                                    int fourier, double* plain, double* wgt, long long ld_ik, double* plainT,
+                                    double* wgtT, long long ld_ki) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double xi = x[i];
+    const double wi = w ? w[i] : 1.0;
+    auto put = [&](int k, double v) {
+        const double vw = (wi == 0.0) ? 0.0 : __dmul_rn(wi, v);
+        if (plain) plain[(long long)i * ld_ik + k] = v;
+        if (wgt) wgt[(long long)i * ld_ik + k] = vw;
+        if (plainT) plainT[(long long)k * ld_ki + i] = v;
+        if (wgtT) wgtT[(long long)k * ld_ki + i] = vw;
+    };
+    if (fourier) {
+        // transform.cpp:98-109 ; COS(k)=2k, SIN(k)=2k-1 (transform.hpp:55-56)
+        put(0, 1.0 / sqrt(2 * M_PI));
+        for (int k = 1; 2 * k < P; k++) {
+            put(2 * k, cos(k * xi) / sqrt(M_PI));
+            put(2 * k - 1, sin(k * xi) / sqrt(M_PI));
+        }
+        return;
+    }
+    double vm = 1.0, v = xi;
+    put(0, vm);
+    if (P > 1) put(1, v);
+    for (int k = 1; k + 1 < P; k++) {
+        const double sk1 = sqrt((double)(k + 1));
+        const double a = __ddiv_rn(1.0, sk1);               // REC_A(k) = 1/sqrt(k+1)
+        const double b = __ddiv_rn(sqrt((double)k), sk1);   // REC_B(k) = sqrt(k)/sqrt(k+1)
+        const double nv = __dsub_rn(__dmul_rn(__dmul_rn(a, xi), v), __dmul_rn(b, vm));
+        vm = v;
+        v = nv;
+        put(k + 1, v);
+    }
+}
+
+int launch_basis_tables(const double* x, const double* w, int n, int P, int fourier, double* plain, double* wgt,
+                        long long ld_ik, double* plainT, double* wgtT, long long ld_ki, cudaStream_t s) {
+    basis_tables_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, n, P, fourier, plain, wgt, ld_ik, plainT, wgtT, ld_ki);
+    return launch_status();
+}
+
+// Products of pairs of basis functions on the nodes, the operand of the Gram-form varf:
+//   psi2[x][m*Pp + n] = scale_x * phi_m(x) * phi_n(x),  scale_x = w_x (left/outer table) or 1.
+__global__ void pair_table_kernel(const double* __restrict__ plain, long long ld_ik, const double* __restrict__ w,
+                                  int n, int P, int Pp, double* out) {
+    const int x = blockIdx.y;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)P * Pp) return;
+    const int m = (int)(idx / Pp), nn = (int)(idx - (long long)m * Pp);
+    double v = 0.0;
+    if (nn < P) {
+        v = plain[(long long)x * ld_ik + m] * plain[(long long)x * ld_ik + nn];
+        if (w) v = (w[x] == 0.0) ? 0.0 : v * w[x];
+    }
+    out[(long long)x * P * Pp + idx] = v;
+}
+
+int launch_pair_table(const double* plain, long long ld_ik, const double* w, int n, int P, int Pp, double* out,
+                      cudaStream_t s) {
+    dim3 grid(cdiv((long long)P * Pp, 256), n);
+    pair_table_kernel<<<grid, 256, 0, s>>>(plain, ld_ik, w, n, P, Pp, out);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact Hermite triple products T[k][i][j] = <phi_i phi_j, phi_k>, k <= 2N, i,j <= N.
+// Reference: triple_products_1d, cpp/src/hermite/varf.cpp:49-94.  The recursion raises i at fixed j
+// (three k-ranges :77-84, then symmetrisation :88-91), so columns j are independent: one CTA per j,
+// threads over k, levels i in sequence with the two previous levels kept in shared memory.  Each
+// entry is accumulated in the reference's order (term1, then term2, then term3) without FMA
+// contraction.  Output layout [k][i][Pp] with Pp >= P even (pad columns are zero).
+__global__ void triple_products_kernel(int N, int Pp, double* __restrict__ T) {
+    extern __shared__ double sh[];
+    const int K = 2 * N + 1;
+    double* lev0 = sh;            // level i-2
+    double* lev1 = sh + (K + 2);  // level i-1   (one guard cell on each side)
+    double* lev2 = sh + 2 * (K + 2);
+    const int j = blockIdx.x;
+    const long long plane = (long long)(N + 1) * Pp;
+    for (int k = threadIdx.x; k < K + 2; k += blockDim.x) lev0[k] = lev1[k] = lev2[k] = 0.0;
+    __syncthreads();
+    // level 0: T[j][0][j] = 1
+    if (threadIdx.x == 0) {
+        lev1[1 + j] = 1.0;
+        T[(long long)j * plane + 0 * Pp + j] = 1.0;
+        T[(long long)j * plane + (long long)j * Pp + 0] = 1.0;
+    }
+    __syncthreads();
+    for (int i = 1; i <= j; i++) {
+        const double ai = __ddiv_rn(1.0, sqrt((double)i));                    // a[i-1]
+        const double bi = __ddiv_rn(sqrt((double)(i - 1)), sqrt((double)i));  // b[i-1]
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            double v = 0.0;
+            if (k >= j - i && k <= j + i) {
+                const double sk1 = sqrt((double)(k + 1));
+                const double ak = __ddiv_rn(1.0, sk1);
+                const double r = __ddiv_rn(ai, ak);
+                if (k <= j + i - 2) v = __dadd_rn(v, __dmul_rn(r, lev1[1 + k + 1]));
+                if (k >= j - i + 2 && k <= j + i - 2) v = __dadd_rn(v, __dmul_rn(-bi, lev0[1 + k]));
+                if (k >= j - i + 2 && k >= 1) {
+                    const double bk = __ddiv_rn(sqrt((double)k), sk1);
+                    v = __dadd_rn(v, __dmul_rn(__dmul_rn(r, bk), lev1[1 + k - 1]));
+                }
+                T[(long long)k * plane + (long long)i * Pp + j] = v;
+                T[(long long)k * plane + (long long)j * Pp + i] = v;
+            }
+            lev2[1 + k] = v;
+        }
+        __syncthreads();
+        double* t = lev0; lev0 = lev1; lev1 = lev2; lev2 = t;
+    }
+}
+
+int launch_triple_products(int N, int Pp, double* T, cudaStream_t s) {
+    const size_t bytes = (size_t)(2 * N + 1) * (N + 1) * Pp * 8;
+    if (cudaMemsetAsync(T, 0, bytes, s) != cudaSuccess) return HB_ERR_CUDA;
+    const int smem = 3 * (2 * N + 3) * 8;
+    triple_products_kernel<<<N + 1, 256, smem, s>>>(N, Pp, T);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pitch repack / gather helpers.
+__global__ void repack_rows_kernel(const double* __restrict__ src, long long src_ld, double* __restrict__ dst,
+                                   long long dst_ld, long long rows, int cols) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * dst_ld) return;
+    const long long r = idx / dst_ld;
+    const int c = (int)(idx - r * dst_ld);
+    dst[idx] = (c < cols) ? src[r * src_ld + c] : 0.0;
+}
+
+int launch_repack_rows(const double* src, long long src_ld, double* dst, long long dst_ld, long long rows, int cols,
+                       cudaStream_t s) {
+    repack_rows_kernel<<<cdiv(rows * dst_ld, 256), 256, 0, s>>>(src, src_ld, dst, dst_ld, rows, cols);
+    return launch_status();
+}
+
+// dst[b][j] = (lut[j] >= 0) ? src[b][lut[j]] : 0      (coefficients in set order -> padded lex box)
+__global__ void gather_lut_kernel(const double* __restrict__ src, long long src_stride, const int* __restrict__ lut,
+                                  double* __restrict__ dst, long long dst_stride, long long n_dst, int batch) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_dst) return;
+    const int p = lut[idx];
+    for (int b = blockIdx.y; b < batch; b += gridDim.y)
+        dst[b * dst_stride + idx] = (p >= 0) ? src[b * src_stride + p] : 0.0;
+}
+
+int launch_gather_lut(const double* src, long long src_stride, const int* lut, double* dst, long long dst_stride,
+                      long long n_dst, int batch, cudaStream_t s) {
+    dim3 grid(cdiv(n_dst, 256), batch < 1024 ? batch : 1024);
+    gather_lut_kernel<<<grid, 256, 0, s>>>(src, src_stride, lut, dst, dst_stride, n_dst, batch);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensorize (reference: cpp/src/hermite/tensorize.cpp:86-122 vectors, :197-283 matrices):
+//   vectors : out[i]      = prod_j in_j[ map_j[i] ]
+//   matrices: out[r][c]   = prod_j in_j[ map_j[r] * size_j + map_j[c] ]
+// map_j[i] = position of (m_i restricted to dirs_j) in the j-th factor's index set (host-built LUT).
+__global__ void tensorize_vec_kernel(TensorizeArgs a, double* __restrict__ out, int n_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    double v = 1.0;
+    for (int j = 0; j < a.k; j++) v = __dmul_rn(v, a.in[j][a.map[j][i]]);
+    out[i] = v;
+}
+
+__global__ void tensorize_mat_kernel(TensorizeArgs a, double* __restrict__ out, int n_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n_out) return;
+    // the reference folds factors left to right: ((A0*A1)*A2)...
+    double v = a.in[0][(long long)a.map[0][r] * a.size[0] + a.map[0][c]];
+    for (int j = 1; j < a.k; j++)
+        v = __dmul_rn(v, a.in[j][(long long)a.map[j][r] * a.size[j] + a.map[j][c]]);
+    out[(long long)r * n_out + c] = v;
+}
+
+int launch_tensorize(const TensorizeArgs& a, bool matrices, double* out, int n_out, cudaStream_t s) {
+    if (matrices) {
+        dim3 grid(cdiv(n_out, 256), n_out);
+        tensorize_mat_kernel<<<grid, 256, 0, s>>>(a, out, n_out);
+    } else {
+        tensorize_vec_kernel<<<cdiv(n_out, 256), 256, 0, s>>>(a, out, n_out);
+    }
+    return launch_status();
+}
+
+// project (reference: cpp/src/hermite/project.cpp:35-58, :78-109): out[i] = in[sel[i]],
+// out[r][c] = in[sel[r]][sel[c]], sel[i] = position in the full set of the sub-index i embedded on dirs.
+__global__ void project_vec_kernel(const double* __restrict__ in, const int* __restrict__ sel, double* out, int n_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) out[i] = sel[i] >= 0 ? in[sel[i]] : 0.0;
+}
+__global__ void project_mat_kernel(const double* __restrict__ in, int n_in, const int* __restrict__ sel, double* out,
+                                   int n_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n_out) return;
+    const int sr = sel[r], sc = sel[c];
+    out[(long long)r * n_out + c] = (sr >= 0 && sc >= 0) ? in[(long long)sr * n_in + sc] : 0.0;
+}
+int launch_project(const double* in, int n_in, const int* sel, bool matrix, double* out, int n_out, cudaStream_t s) {
+    if (matrix) {
+        dim3 grid(cdiv(n_out, 256), n_out);
+        project_mat_kernel<<<grid, 256, 0, s>>>(in, n_in, sel, out, n_out);
+    } else {
+        project_vec_kernel<<<cdiv(n_out, 256), 256, 0, s>>>(in, sel, out, n_out);
+    }
+    return launch_status();
+}
+
+// varfd (reference: cpp/src/hermite/varf.cpp:290-376): out[r][c] = fac[c] * var[r][src[c]] where, for a
+// Hermite axis, src[c] = index(m_c - e_dir) and fac[c] = sqrt(m_c[dir]) (0 / unused when m_c[dir]==0).
+__global__ void varfd_kernel(const double* __restrict__ var, const int* __restrict__ src, const double* __restrict__ fac,
+                             double* out, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= n) return;
+    const int sc = src[c];
+    out[(long long)r * n + c] = sc >= 0 ? __dmul_rn(var[(long long)r * n + sc], fac[c]) : 0.0;
+}
+int launch_varfd(const double* var, const int* src, const double* fac, double* out, int n, cudaStream_t s) {
+    dim3 grid(cdiv(n, 256), n);
+    varfd_kernel<<<grid, 256, 0, s>>>(var, src, fac, out, n);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// varf assembly when only a few alpha survive the threshold (reference: varf.cpp:236-262; this is the
+// regime the reference algebra is numerically meaningful in -- polynomial-like f).  One thread per
+// output entry; the retained (alpha, Hf[alpha]) list is walked in the reference's iterator order and
+// each term is formed as ((T[a_0][m_0][n_0] * T[a_1][m_1][n_1]) * ...) * Hf, added without FMA, so
+// the sum reproduces the reference's rounding.  HBM-write-bound: 8 B per entry.
+__global__ void varf_sparse_kernel(VarfSparseArgs a, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = a.row_begin + blockIdx.y;
+    if (c >= a.n_polys) return;
+    int m[HB_MAX_DIM], nn[HB_MAX_DIM];
+    for (int d = 0; d < a.dim; d++) {
+        m[d] = a.midx[(long long)r * a.dim + d];
+        nn[d] = a.midx[(long long)c * a.dim + d];
+    }
+    double acc = 0.0;
+    for (int t = 0; t < a.n_kept; t++) {
+        double prod = 0.0;
+        bool zero = false;
+        for (int d = 0; d < a.dim; d++) {
+            const int al = a.kept_alpha[(long long)t * a.dim + d];
+            const double* T = a.T[d];
+            const double v = T[(long long)al * a.plane[d] + (long long)m[d] * a.Pp[d] + nn[d]];
+            if (v == 0.0) { zero = true; break; }   // the reference only stores non-zeros (sparse.cpp:52)
+            prod = (d == 0) ? v : __dmul_rn(prod, v);
+        }
+        if (zero) continue;
+        acc = __dadd_rn(acc, __dmul_rn(prod, a.kept_val[t]));
+    }
+    out[(long long)blockIdx.y * a.ldo + c] = acc;
+}
+
+int launch_varf_sparse(const VarfSparseArgs& a, double* out, cudaStream_t s) {
+    const int rows = a.row_end - a.row_begin;
+    if (rows <= 0) return HB_OK;
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+        VarfSparseArgs b = a;
+        b.row_begin = a.row_begin + r0;
+        const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        dim3 grid(cdiv(a.n_polys, 128), nr);
+        varf_sparse_kernel<<<grid, 128, 0, s>>>(b, out + (long long)r0 * a.ldo);
+    }
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense -> CSR compaction (exact zeros dropped, as the reference's to_spmat does, sparse.cpp:44-58).
+__global__ void count_nnz_kernel(const double* __restrict__ A, long long ld, int n_cols, long long* row_nnz) {
+    const int r = blockIdx.x;
+    int cnt = 0;
+    for (int c = threadIdx.x; c < n_cols; c += blockDim.x) cnt += (A[(long long)r * ld + c] != 0.0);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    __shared__ int sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < (blockDim.x >> 5); i++) t += sh[i];
+        row_nnz[r] = t;
+    }
+}
+// one warp per row, ordered compaction with ballot/popc
+__global__ void fill_csr_kernel(const double* __restrict__ A, long long ld, int n_rows, int n_cols,
+                                const long long* __restrict__ indptr, int* indices, double* data) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    long long pos = indptr[r];
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const int c = c0 + lane;
+        const double v = c < n_cols ? A[(long long)r * ld + c] : 0.0;
+        const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
+        if (v != 0.0) {
+            const long long p = pos + __popc(mask & ((1u << lane) - 1));
+            indices[p] = c;
+            data[p] = v;
+        }
+        pos += __popc(mask);
+    }
+}
+int launch_count_nnz(const double* A, long long ld, int n_rows, int n_cols, long long* row_nnz, cudaStream_t s) {
+    count_nnz_kernel<<<n_rows, 256, 0, s>>>(A, ld, n_cols, row_nnz);
+    return launch_status();
+}
+int launch_fill_csr(const double* A, long long ld, int n_rows, int n_cols, const long long* indptr, int* indices,
+                    double* data, cudaStream_t s) {
+    fill_csr_kernel<<<cdiv(n_rows, 8), 256, 0, s>>>(A, ld, n_rows, n_cols, indptr, indices, data);
+    return launch_status();
+}
+
+}  // namespace hb

@@ -1,0 +1,47 @@
+// Launchers of the helper kernels in hb_kernels.cu (internal, not part of the C ABI).
+#pragma once
+#include "hb_internal.h"
+
+#define HB_MAX_DIM 8
+#define HB_MAX_FACTORS 8
+
+namespace hb {
+
+int launch_basis_tables(const double* x, const double* w, int n, int P, int fourier, double* plain, double* wgt,
+                        long long ld_ik, double* plainT, double* wgtT, long long ld_ki, cudaStream_t s);
+int launch_pair_table(const double* plain, long long ld_ik, const double* w, int n, int P, int Pp, double* out,
+                      cudaStream_t s);
+int launch_triple_products(int N, int Pp, double* T, cudaStream_t s);
+int launch_repack_rows(const double* src, long long src_ld, double* dst, long long dst_ld, long long rows, int cols,
+                       cudaStream_t s);
+int launch_gather_lut(const double* src, long long src_stride, const int* lut, double* dst, long long dst_stride,
+                      long long n_dst, int batch, cudaStream_t s);
+
+struct TensorizeArgs {
+    int k;
+    const double* in[HB_MAX_FACTORS];
+    const int* map[HB_MAX_FACTORS];
+    int size[HB_MAX_FACTORS];
+};
+int launch_tensorize(const TensorizeArgs& a, bool matrices, double* out, int n_out, cudaStream_t s);
+int launch_project(const double* in, int n_in, const int* sel, bool matrix, double* out, int n_out, cudaStream_t s);
+int launch_varfd(const double* var, const int* src, const double* fac, double* out, int n, cudaStream_t s);
+
+struct VarfSparseArgs {
+    int dim, n_polys, n_kept;
+    int row_begin, row_end;
+    long long ldo;
+    const int* midx;        // n_polys x dim multi-indices (device)
+    const int* kept_alpha;  // n_kept x dim
+    const double* kept_val; // n_kept
+    const double* T[HB_MAX_DIM];  // per-axis triple-product table [k][i][Pp]
+    long long plane[HB_MAX_DIM];  // (N+1)*Pp
+    int Pp[HB_MAX_DIM];
+};
+int launch_varf_sparse(const VarfSparseArgs& a, double* out, cudaStream_t s);
+
+int launch_count_nnz(const double* A, long long ld, int n_rows, int n_cols, long long* row_nnz, cudaStream_t s);
+int launch_fill_csr(const double* A, long long ld, int n_rows, int n_cols, const long long* indptr, int* indices,
+                    double* data, cudaStream_t s);
+
+}  // namespace hb

@@ -1,0 +1,503 @@
+// Plans: sum-factorised d-dimensional Hermite transform (one DMMA GEMM per axis) and the varf
+// assembly, on device-resident data.  Reference behaviour: cpp/src/hermite/transform.cpp:44-149
+// (_transform), cpp/src/hermite/varf.cpp:164-269 (varf).
+#include "hb_plan.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "hb_gemm.cuh"
+#include "hb_kernels.h"
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error '%s' in %s", cudaGetErrorString(e), what);
+    return HB_ERR_CUDA;
+}
+void note_launch(int n) { g_launches += n; }
+long long launch_count(int reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches = 0;
+    return v;
+}
+int launch_status() {
+    note_launch(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HB_OK : cuda_fail(e, "kernel launch");
+}
+
+DevBuf::~DevBuf() { release(); }
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+int DevBuf::ensure(size_t need) {
+    if (need <= bytes) return HB_OK;
+    release();
+    need = (need + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error("cudaMalloc of %zu bytes failed: %s", need, cudaGetErrorString(e));
+        cudaGetLastError();
+        return HB_ERR_NOMEM;
+    }
+    bytes = need;
+    return HB_OK;
+}
+int DevBuf::ensure_zero(size_t need, cudaStream_t s) {
+    HB_TRY(ensure(need));
+    HB_CUDA(cudaMemsetAsync(p, 0, need, s));
+    return HB_OK;
+}
+
+}  // namespace hb
+
+hb_plan::~hb_plan() { delete plan2; }
+
+namespace hb {
+
+// ---------------------------------------------------------------------------------------------
+int plan_create(hb_plan** out, int dim, const int* n_pts, int degree, const double* nodes, const double* weights,
+                const int* do_fourier, int set) {
+    *out = nullptr;
+    if (dim < 1 || dim > HB_MAX_DIM || degree < 0 || !n_pts || !nodes || !weights) {
+        set_error("plan_create: invalid arguments");
+        return HB_ERR_INVALID;
+    }
+    if (set < 0) return HB_ERR_INDEX_SET;
+    for (int a = 0; a < dim; a++) {
+        if (n_pts[a] < 1) return HB_ERR_INVALID;
+        if (do_fourier && do_fourier[a] == 1 && (degree % 2 == 1)) {
+            set_error("Use even degree for Fourier.");  // transform.cpp:92-96
+            return HB_ERR_FOURIER_DEGREE;
+        }
+    }
+    auto iset = get_index_set(set, dim, degree);
+    if (!iset) {
+        set_error("plan_create: index set not constructible (set %d, dim %d, degree %d)", set, dim, degree);
+        return HB_ERR_INVALID;
+    }
+    std::unique_ptr<hb_plan> pl(new hb_plan);
+    pl->dim = dim; pl->degree = degree; pl->set = set; pl->iset = iset;
+    pl->n_polys = iset->size;
+    pl->ax.resize(dim);
+    cudaStream_t st = 0;
+    size_t off = 0;
+    for (int a = 0; a < dim; a++) {
+        Axis& A = pl->ax[a];
+        A.n = n_pts[a];
+        A.P = (int)iset->extent[a];
+        A.Pp = (int)even_up(A.P);
+        A.np = (int)even_up(A.n);
+        A.fourier = do_fourier ? do_fourier[a] : 0;
+        A.h_x.assign(nodes + off, nodes + off + A.n);
+        A.h_w.assign(weights + off, weights + off + A.n);
+        off += A.n;
+        HB_TRY(A.x.ensure(A.n * 8));
+        HB_TRY(A.w.ensure(A.n * 8));
+        HB_CUDA(cudaMemcpyAsync(A.x.p, A.h_x.data(), A.n * 8, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaMemcpyAsync(A.w.p, A.h_w.data(), A.n * 8, cudaMemcpyHostToDevice, st));
+        HB_TRY(A.plain.ensure_zero((size_t)A.n * A.Pp * 8, st));
+        HB_TRY(A.wgt.ensure_zero((size_t)A.n * A.Pp * 8, st));
+        HB_TRY(A.plainT.ensure_zero((size_t)A.P * A.np * 8, st));
+        HB_TRY(A.wgtT.ensure_zero((size_t)A.P * A.np * 8, st));
+        HB_TRY(launch_basis_tables(A.x.d(), A.w.d(), A.n, A.P, A.fourier, A.plain.d(), A.wgt.d(), A.Pp,
+                                   A.plainT.d(), A.wgtT.d(), A.np, st));
+    }
+    pl->grid_rows = 1;
+    pl->box_rows = 1;
+    for (int a = 0; a + 1 < dim; a++) {
+        pl->grid_rows *= pl->ax[a].n;
+        pl->box_rows *= pl->ax[a].P;
+    }
+    pl->grid_size = pl->grid_rows * pl->ax[dim - 1].np;
+    pl->box_size = pl->box_rows * pl->ax[dim - 1].Pp;
+    // padded lexicographic box -> position
+    {
+        std::vector<int> lut((size_t)pl->box_size, -1);
+        const int Pl = pl->ax[dim - 1].P, Ppl = pl->ax[dim - 1].Pp;
+        const size_t n_lex = iset->lex_to_pos.size();
+        for (size_t lex = 0; lex < n_lex; lex++) {
+            const size_t row = lex / Pl, col = lex % Pl;
+            lut[row * Ppl + col] = iset->lex_to_pos[lex];
+        }
+        HB_TRY(pl->lut_box.ensure(lut.size() * 4));
+        HB_CUDA(cudaMemcpyAsync(pl->lut_box.p, lut.data(), lut.size() * 4, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaStreamSynchronize(st));
+    }
+    *out = pl.release();
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward: c[j] = sum_i f[i] prod_d w_d[i_d] phi_{m_j,d}(x_{i_d})   (transform.cpp:115-139), contracted
+// one axis at a time, last axis first.
+int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, double* d_coef,
+                 long long coef_stride, cudaStream_t st) {
+    if (batch <= 0) return HB_OK;
+    const int d = pl->dim;
+    if (d == 1) {
+        const Axis& A = pl->ax[0];
+        GemmArgs g;
+        g.M = batch; g.N = A.P; g.K = A.n;
+        g.A = d_f; g.lda = f_stride;
+        g.B = A.wgt.d(); g.ldb = A.Pp;
+        g.C = d_coef; g.ldc = coef_stride;
+        g.epi = EPI_STORE;  // every 1-D index set enumerates 0..P-1 in natural order
+        return gemm_launch(g, st);
+    }
+    const Axis& L = pl->ax[d - 1];
+    long long cols = L.Pp;
+    const long long rows1 = pl->grid_rows;
+    // workspace: largest intermediate
+    size_t need = (size_t)batch * rows1 * cols;
+    {
+        long long c = cols, prefix = (long long)batch * rows1;
+        for (int a = d - 2; a >= 1; a--) {
+            prefix /= pl->ax[a].n;
+            c *= pl->ax[a].P;
+            need = std::max(need, (size_t)(prefix * c));
+        }
+    }
+    HB_TRY(pl->ws[0].ensure(need * 8));
+    if (d > 2) HB_TRY(pl->ws[1].ensure(need * 8));
+    {
+        GemmArgs g;
+        g.K = L.n; g.N = L.Pp;
+        g.A = d_f; g.lda = L.np;
+        if (f_stride == rows1 * L.np || batch == 1) {
+            g.M = (int)(batch * rows1); g.batch = 1;
+        } else {
+            g.M = (int)rows1; g.batch = batch; g.strideA = f_stride; g.strideC = rows1 * cols;
+        }
+        g.B = L.wgt.d(); g.ldb = L.Pp; g.strideB = 0;
+        g.C = pl->ws[0].d(); g.ldc = cols;
+        HB_TRY(gemm_launch(g, st));
+    }
+    int cur = 0;
+    long long prefix = (long long)batch * rows1;
+    for (int a = d - 2; a >= 0; a--) {
+        const Axis& A = pl->ax[a];
+        prefix /= A.n;
+        GemmArgs g;
+        g.M = A.P; g.K = A.n; g.N = (int)cols; g.batch = (int)prefix;
+        g.A = A.wgtT.d(); g.lda = A.np; g.strideA = 0;
+        g.B = pl->ws[cur].d(); g.ldb = cols; g.strideB = (long long)A.n * cols;
+        if (a == 0) {
+            g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = pl->lut_box.i();
+        } else {
+            g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = (long long)A.P * cols;
+        }
+        HB_TRY(gemm_launch(g, st));
+        cols *= A.P;
+        cur ^= 1;
+    }
+    return HB_OK;
+}
+
+// Backward: f[i] = sum_j c[j] prod_d phi_{m_j,d}(x_{i_d})   (transform.cpp:121-128,143; weight forced to 1).
+int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int batch, double* d_f,
+                  long long f_stride, cudaStream_t st) {
+    if (batch <= 0) return HB_OK;
+    const int d = pl->dim;
+    if (d == 1) {
+        const Axis& A = pl->ax[0];
+        GemmArgs g;
+        g.M = batch; g.N = A.n; g.K = A.P;
+        g.A = d_coef; g.lda = coef_stride;
+        g.B = A.plainT.d(); g.ldb = A.np;
+        g.C = d_f; g.ldc = f_stride;
+        return gemm_launch(g, st);
+    }
+    const Axis& L = pl->ax[d - 1];
+    size_t need = (size_t)batch * pl->box_size;
+    {
+        long long c = L.np, prefix = (long long)batch * pl->box_rows;
+        need = std::max(need, (size_t)(prefix * c));
+        for (int a = d - 2; a >= 1; a--) {
+            prefix /= pl->ax[a].P;
+            c *= pl->ax[a].n;
+            need = std::max(need, (size_t)(prefix * c));
+        }
+    }
+    HB_TRY(pl->ws[0].ensure(need * 8));
+    HB_TRY(pl->ws[1].ensure(need * 8));
+    // coefficients in set order -> zero-padded lexicographic box
+    HB_TRY(launch_gather_lut(d_coef, coef_stride, pl->lut_box.i(), pl->ws[0].d(), pl->box_size, pl->box_size, batch, st));
+    long long cols = L.np;
+    {
+        GemmArgs g;
+        g.M = (int)(batch * pl->box_rows); g.K = L.P; g.N = L.np;
+        g.A = pl->ws[0].d(); g.lda = L.Pp;
+        g.B = L.plainT.d(); g.ldb = L.np;
+        g.C = pl->ws[1].d(); g.ldc = cols;
+        HB_TRY(gemm_launch(g, st));
+    }
+    int cur = 1;
+    long long prefix = (long long)batch * pl->box_rows;
+    for (int a = d - 2; a >= 0; a--) {
+        const Axis& A = pl->ax[a];
+        prefix /= A.P;
+        GemmArgs g;
+        g.M = A.n; g.K = A.P; g.N = (int)cols; g.batch = (int)prefix;
+        g.A = A.plain.d(); g.lda = A.Pp; g.strideA = 0;
+        g.B = pl->ws[cur].d(); g.ldb = cols; g.strideB = (long long)A.P * cols;
+        if (a == 0) {
+            g.C = d_f; g.ldc = cols; g.strideC = f_stride;
+        } else {
+            g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = (long long)A.n * cols;
+        }
+        HB_TRY(gemm_launch(g, st));
+        cols *= A.n;
+        cur ^= 1;
+    }
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fourier triple products (reference: triple_products_fourier, varf.cpp:99-162), from the complex
+// exponential expansion of the basis e_0 = 1/sqrt(2pi), e_{2k} = cos(kx)/sqrt(pi), e_{2k-1} = sin(kx)/sqrt(pi):
+// int e_a e_b e_c over [-pi,pi] = 2pi * sum of coefficient products whose frequencies add up to 0.
+void fourier_triple_products_host(int degree, int Pp, std::vector<double>& out) {
+    const int K = 2 * degree + 1, P = degree + 1;
+    out.assign((size_t)K * P * Pp, 0.0);
+    struct Term { int freq; double re, im; };
+    auto expand = [](int idx, Term t[2]) -> int {
+        if (idx == 0) { t[0] = {0, 1.0 / std::sqrt(2 * M_PI), 0.0}; return 1; }
+        const double s = 1.0 / std::sqrt(M_PI);
+        if (idx % 2 == 0) {  // cos(kx) = (e^{ikx} + e^{-ikx})/2
+            const int k = idx / 2;
+            t[0] = {k, 0.5 * s, 0.0}; t[1] = {-k, 0.5 * s, 0.0};
+        } else {             // sin(kx) = (e^{ikx} - e^{-ikx})/(2i)
+            const int k = (idx + 1) / 2;
+            t[0] = {k, 0.0, -0.5 * s}; t[1] = {-k, 0.0, 0.5 * s};
+        }
+        return 2;
+    };
+    for (int a = 0; a < K; a++)
+        for (int b = 0; b < P; b++)
+            for (int c = 0; c < P; c++) {
+                Term ta[2], tb[2], tc[2];
+                const int na = expand(a, ta), nb = expand(b, tb), nc = expand(c, tc);
+                double acc = 0.0;
+                for (int i = 0; i < na; i++)
+                    for (int j = 0; j < nb; j++)
+                        for (int k = 0; k < nc; k++) {
+                            if (ta[i].freq + tb[j].freq + tc[k].freq != 0) continue;
+                            // real part of the product of three complex coefficients
+                            const double r1 = ta[i].re * tb[j].re - ta[i].im * tb[j].im;
+                            const double i1 = ta[i].re * tb[j].im + ta[i].im * tb[j].re;
+                            acc += r1 * tc[k].re - i1 * tc[k].im;
+                        }
+                out[(size_t)a * P * Pp + (size_t)b * Pp + c] = 2 * M_PI * acc;
+            }
+}
+
+int ensure_triple_products(hb_plan* pl, cudaStream_t st) {
+    const int N = pl->degree;
+    if (pl->Tdeg == N) return HB_OK;
+    pl->TPp = (int)even_up(N + 1);
+    const size_t bytes = (size_t)(2 * N + 1) * (N + 1) * pl->TPp * 8;
+    bool any_h = false, any_f = false;
+    for (const Axis& A : pl->ax) (A.fourier ? any_f : any_h) = true;
+    if (any_h) {
+        HB_TRY(pl->T.ensure(bytes));
+        HB_TRY(launch_triple_products(N, pl->TPp, pl->T.d(), st));
+    }
+    if (any_f) {
+        std::vector<double> h;
+        fourier_triple_products_host(N, pl->TPp, h);
+        HB_TRY(pl->Tf.ensure(bytes));
+        HB_CUDA(cudaMemcpyAsync(pl->Tf.p, h.data(), bytes, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaStreamSynchronize(st));
+    }
+    pl->Tdeg = N;
+    return HB_OK;
+}
+
+static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
+    if (!pl->midx.p) {
+        std::vector<int> m(pl->iset->list.begin(), pl->iset->list.end());
+        HB_TRY(pl->midx.ensure(m.size() * 4));
+        HB_CUDA(cudaMemcpyAsync(pl->midx.p, m.data(), m.size() * 4, cudaMemcpyHostToDevice, st));
+        if (pl->dim == 2) {
+            HB_TRY(pl->lut2d.ensure(pl->iset->lex_to_pos.size() * 4));
+            HB_CUDA(cudaMemcpyAsync(pl->lut2d.p, pl->iset->lex_to_pos.data(), pl->iset->lex_to_pos.size() * 4,
+                                    cudaMemcpyHostToDevice, st));
+        }
+        HB_CUDA(cudaStreamSynchronize(st));
+    }
+    return HB_OK;
+}
+
+// two-stage dense contraction for dim == 2 (see DESIGN.md "varf"):
+//   G[k0][(m1,n1)] = sum_{k1} coef[k0][k1] * R[k1][(m1,n1)]              (stage 1, A K-contiguous)
+//   A[idx(m0,m1)][idx(n0,n1)] = sum_{k0} L[k0][(m0,n0)] * G[k0][(m1,n1)]  (stage 2, A M-contiguous, scatter epilogue)
+static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int K0, int K1, const double* Ltab,
+                         long long ldL, int Pp0, const double* Rtab, long long ldR, int Pp1, double* d_out,
+                         long long ldo, long long row_begin, long long row_end, cudaStream_t st) {
+    const int P0 = pl->ax[0].P, P1 = pl->ax[1].P;
+    const long long ncol = (long long)P1 * Pp1, nrow = (long long)P0 * Pp0;
+    HB_TRY(pl->G.ensure((size_t)K0 * ncol * 8));
+    GemmArgs g1;
+    g1.M = K0; g1.K = K1; g1.N = (int)ncol;
+    g1.A = coef; g1.lda = ld_coef;
+    g1.B = Rtab; g1.ldb = ldR;
+    g1.C = pl->G.d(); g1.ldc = ncol;
+    HB_TRY(gemm_launch(g1, st));
+    GemmArgs g2;
+    g2.M = (int)nrow; g2.K = K0; g2.N = (int)ncol;
+    g2.A = Ltab; g2.lda = ldL; g2.a_mmajor = true;
+    g2.B = pl->G.d(); g2.ldb = ncol;
+    g2.C = d_out; g2.ldc = ldo;
+    g2.epi = EPI_VARF2D; g2.lut = pl->lut2d.i();
+    g2.P0 = P0; g2.Pp0 = Pp0; g2.P1 = P1; g2.Pp1 = Pp1;
+    g2.row_begin = (int)row_begin; g2.row_end = (int)row_end;
+    g2.tri_degree = (pl->set == SET_TRIANGLE) ? pl->degree : -1;
+    g2.cfg = 0;
+    return gemm_launch(g2, st);
+}
+
+static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ldo, long long row_begin,
+                     long long row_end, cudaStream_t st) {
+    if (pl->dim > 2) {
+        set_error("HB_VARF_GRAM supports dim <= 2 (got %d)", pl->dim);
+        return HB_ERR_INVALID;
+    }
+    for (int a = 0; a < pl->dim; a++) {
+        const Axis& A = pl->ax[a];
+        const size_t bytes = (size_t)A.n * A.P * A.Pp * 8;
+        if (pl->pair[a].bytes < bytes) {
+            HB_TRY(pl->pair[a].ensure(bytes));
+            HB_TRY(launch_pair_table(A.plain.d(), A.Pp, A.w.d(), A.n, A.P, A.Pp, pl->pair[a].d(), st));
+        }
+    }
+    if (pl->dim == 1) {
+        const Axis& A = pl->ax[0];
+        const long long ncol = (long long)A.P * A.Pp;
+        HB_TRY(pl->tmp.ensure(ncol * 8));
+        GemmArgs g;
+        g.M = 1; g.K = A.n; g.N = (int)ncol;
+        g.A = d_f; g.lda = A.np;
+        g.B = pl->pair[0].d(); g.ldb = ncol;
+        g.C = pl->tmp.d(); g.ldc = ncol;
+        HB_TRY(gemm_launch(g, st));
+        const long long r0 = std::max(0LL, row_begin), r1 = std::min((long long)A.P, row_end);
+        if (r1 > r0)
+            HB_CUDA(cudaMemcpy2DAsync(d_out, ldo * 8, pl->tmp.d() + r0 * A.Pp, (size_t)A.Pp * 8, (size_t)A.P * 8,
+                                      r1 - r0, cudaMemcpyDeviceToDevice, st));
+        return HB_OK;
+    }
+    const Axis &A0 = pl->ax[0], &A1 = pl->ax[1];
+    return varf_dense_2d(pl, d_f, A1.np, A0.n, A1.n, pl->pair[0].d(), (long long)A0.P * A0.Pp, A0.Pp,
+                         pl->pair[1].d(), (long long)A1.P * A1.Pp, A1.Pp, d_out, ldo, row_begin, row_end, st);
+}
+
+// The reference's algebra (varf.cpp:164-269).
+static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long long ldo, long long row_begin,
+                          long long row_end, cudaStream_t st) {
+    const int d = pl->dim, N = pl->degree;
+    HB_TRY(ensure_triple_products(pl, st));
+    // Hf = transform at degree 2N on the same kind of index set (varf.cpp:181)
+    if (!pl->plan2) {
+        std::vector<int> n_pts(d), four(d);
+        std::vector<double> nodes, weights;
+        for (int a = 0; a < d; a++) {
+            n_pts[a] = pl->ax[a].n;
+            four[a] = pl->ax[a].fourier;
+            nodes.insert(nodes.end(), pl->ax[a].h_x.begin(), pl->ax[a].h_x.end());
+            weights.insert(weights.end(), pl->ax[a].h_w.begin(), pl->ax[a].h_w.end());
+        }
+        HB_TRY(plan_create(&pl->plan2, d, n_pts.data(), 2 * N, nodes.data(), weights.data(), four.data(), pl->set));
+    }
+    hb_plan* p2 = pl->plan2;
+    const long long n2 = p2->n_polys;
+    HB_TRY(pl->Hf.ensure(even_up(n2) * 8));
+    HB_TRY(plan_forward(p2, d_f, pl->grid_size, 1, pl->Hf.d(), even_up(n2), st));
+    pl->h_Hf.resize(n2);
+    HB_CUDA(cudaMemcpyAsync(pl->h_Hf.data(), pl->Hf.p, n2 * 8, cudaMemcpyDeviceToHost, st));
+    HB_CUDA(cudaStreamSynchronize(st));
+    // threshold exactly as the reference: sequential sum of squares, sqrt, max(norm,1) (varf.cpp:190-195),
+    // keep alpha unless |Hf| < 1e-12*norm (:238-241; a NaN coefficient is therefore kept).
+    const std::vector<double>& Hf = pl->h_Hf;
+    double norm = 0;
+    for (long long i = 0; i < n2; i++) norm += std::fabs(Hf[i]) * std::fabs(Hf[i]);
+    norm = std::sqrt(norm);
+    norm = norm < 1 ? 1 : norm;
+    const double thr = 1e-12 * norm;
+    std::vector<int> kept_alpha;
+    std::vector<double> kept_val;
+    for (long long i = 0; i < n2; i++) {
+        if (std::fabs(Hf[i]) < thr) continue;
+        for (int a = 0; a < d; a++) kept_alpha.push_back((int)p2->iset->list[(size_t)i * d + a]);
+        kept_val.push_back(Hf[i]);
+    }
+    const int n_kept = (int)kept_val.size();
+    pl->last_n_kept = n_kept;
+    const bool dense = (d == 2 && n_kept > 96);
+    pl->last_path = dense ? 1 : 0;
+    if (dense) {
+        const int E0 = (int)p2->iset->extent[0], E1 = (int)p2->iset->extent[1];
+        const long long ldc = even_up(E1);
+        std::vector<double> Hc((size_t)E0 * ldc, 0.0);
+        for (int t = 0; t < n_kept; t++) Hc[(size_t)kept_alpha[2 * t] * ldc + kept_alpha[2 * t + 1]] = kept_val[t];
+        HB_TRY(pl->Hc.ensure(Hc.size() * 8));
+        HB_CUDA(cudaMemcpyAsync(pl->Hc.p, Hc.data(), Hc.size() * 8, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaStreamSynchronize(st));
+        const long long plane = (long long)(N + 1) * pl->TPp;
+        const double* T0 = pl->ax[0].fourier ? pl->Tf.d() : pl->T.d();
+        const double* T1 = pl->ax[1].fourier ? pl->Tf.d() : pl->T.d();
+        return varf_dense_2d(pl, pl->Hc.d(), ldc, E0, E1, T0, plane, pl->TPp, T1, plane, pl->TPp, d_out, ldo,
+                             row_begin, row_end, st);
+    }
+    HB_TRY(pl->kept_alpha.ensure(std::max<size_t>(kept_alpha.size(), 1) * 4));
+    HB_TRY(pl->kept_val.ensure(std::max<size_t>(kept_val.size(), 1) * 8));
+    if (n_kept) {
+        HB_CUDA(cudaMemcpyAsync(pl->kept_alpha.p, kept_alpha.data(), kept_alpha.size() * 4, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaMemcpyAsync(pl->kept_val.p, kept_val.data(), kept_val.size() * 8, cudaMemcpyHostToDevice, st));
+        HB_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope
+    }
+    VarfSparseArgs a;
+    a.dim = d; a.n_polys = (int)pl->n_polys; a.n_kept = n_kept;
+    a.row_begin = (int)row_begin; a.row_end = (int)row_end; a.ldo = ldo;
+    a.midx = pl->midx.i(); a.kept_alpha = pl->kept_alpha.i(); a.kept_val = pl->kept_val.d();
+    for (int k = 0; k < d; k++) {
+        a.T[k] = pl->ax[k].fourier ? pl->Tf.d() : pl->T.d();
+        a.plane[k] = (long long)(N + 1) * pl->TPp;
+        a.Pp[k] = pl->TPp;
+    }
+    return launch_varf_sparse(a, d_out, st);
+}
+
+int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
+              long long row_end, cudaStream_t st) {
+    if (row_begin < 0) row_begin = 0;
+    if (row_end > pl->n_polys) row_end = pl->n_polys;
+    if (row_end <= row_begin) return HB_OK;
+    if (ldo < pl->n_polys) return HB_ERR_INVALID;
+    HB_TRY(ensure_varf_tables(pl, st));
+    if (mode == HB_VARF_GRAM) return varf_gram(pl, d_f, d_out, ldo, row_begin, row_end, st);
+    if (mode == HB_VARF_REFERENCE) return varf_reference(pl, d_f, d_out, ldo, row_begin, row_end, st);
+    set_error("unknown varf mode %d", mode);
+    return HB_ERR_INVALID;
+}
+
+}  // namespace hb

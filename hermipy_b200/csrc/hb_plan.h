@@ -1,0 +1,83 @@
+// Plan object: device-resident tables + workspace for one (grid, degree, index set) combination.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "hb_index.h"
+#include "hb_internal.h"
+
+namespace hb {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void note_launch(int n = 1);
+int launch_status();  // counts one launch and maps cudaGetLastError() to a status
+
+#define HB_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+#define HB_TRY(call)            \
+    do {                        \
+        int rc__ = (call);      \
+        if (rc__ != HB_OK) return rc__; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf();
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    int ensure(size_t need);  // grow-only
+    int ensure_zero(size_t need, cudaStream_t s);
+    void release();
+    double* d() const { return static_cast<double*>(p); }
+    int* i() const { return static_cast<int*>(p); }
+};
+
+inline long long even_up(long long v) { return (v + 1) & ~1LL; }
+
+struct Axis {
+    int n = 0, P = 0, Pp = 0, np = 0, fourier = 0;
+    std::vector<double> h_x, h_w;
+    DevBuf x, w;
+    DevBuf plain, wgt;    // [n][Pp]   phi_k(x_i), w_i*phi_k(x_i)
+    DevBuf plainT, wgtT;  // [P][np]
+};
+
+}  // namespace hb
+
+struct hb_plan {
+    int dim = 0, degree = 0, set = 0;
+    std::shared_ptr<const hb::IndexSet> iset;
+    std::vector<hb::Axis> ax;
+    long long n_polys = 0, grid_rows = 0 /* n_0..n_{d-2} */, grid_size = 0, box_rows = 0, box_size = 0;
+    hb::DevBuf lut_box;  // int32[box_size]: padded lexicographic box -> position in the set, -1 absent
+    hb::DevBuf ws[2];
+    // --- varf state (lazy) ---
+    hb_plan* plan2 = nullptr;   // transform plan at degree 2*degree (Hf), owned
+    int Tdeg = -1, TPp = 0;
+    hb::DevBuf T, Tf;           // triple products [2N+1][N+1][TPp] (Hermite / Fourier)
+    hb::DevBuf midx, lut2d, Hf, Hc, G, kept_alpha, kept_val, pair[2], tmp;
+    std::vector<double> h_Hf;
+    int last_n_kept = 0, last_path = 0;
+    ~hb_plan();
+};
+
+namespace hb {
+int plan_create(hb_plan** out, int dim, const int* n_pts, int degree, const double* nodes, const double* weights,
+                const int* do_fourier, int set);
+int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, double* d_coef,
+                 long long coef_stride, cudaStream_t st);
+int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int batch, double* d_f,
+                  long long f_stride, cudaStream_t st);
+int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
+              long long row_end, cudaStream_t st);
+int ensure_triple_products(hb_plan* pl, cudaStream_t st);
+void fourier_triple_products_host(int degree, int Pp, std::vector<double>& out);
+}  // namespace hb

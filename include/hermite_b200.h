@@ -1,9 +1,20 @@
-/* hermite_b200.h -- C ABI of libhermite_b200.so (work in progress).
+/* hermite_b200.h -- C ABI of libhermite_b200.so
  *
- * Drop-in boundary for the numerical core of urbainvaes/hermipy: every entry point replaces one
- * function that the reference registers in its Boost.Python module `hermite_cpp`
- * (cpp/src/hermite/python/module.cpp:45-168) and that hermipy/core.py calls.
- * Plain pointers and sizes only; every function returns an int status and never calls exit().
+ * B200-native (sm_100a CUDA) replacement for the numerical core of urbainvaes/hermipy.  Every entry
+ * point below replaces one function that the reference registers in its Boost.Python module
+ * `hermite_cpp` (reference: cpp/src/hermite/python/module.cpp:45-168) and that the reference's
+ * hermipy/core.py:125-348 calls; the citation next to each declaration names that function.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all floating point data is IEEE double, all index data int32/uint32;
+ *   - `index_set` is one of "triangle", "cross", "cross_nc", "cube", "rectangle" (transform.cpp:160-166);
+ *   - grids are row-major with the LAST axis fastest (Grid_iterator, iterators.cpp:36-66);
+ *   - `nodes` / `weights` are the per-axis arrays concatenated (axis 0 first), lengths in n_pts[dim];
+ *   - every function returns an int status (HB_OK or an HB_ERR_* code) and never calls exit();
+ *     the conditions on which the reference prints a message and exit()s map to error codes;
+ *   - functions without the _dev suffix take HOST pointers and include the host<->device copies;
+ *     hb_plan_* functions take DEVICE pointers (resident data) and a CUDA stream.
+ *   - there is no CPU fallback: with no usable CUDA device every compute entry point returns HB_ERR_CUDA.
  */
 #ifndef HERMITE_B200_H
 #define HERMITE_B200_H
@@ -15,15 +26,110 @@
 extern "C" {
 #endif
 
-/* status codes */
+/* ---- status codes ------------------------------------------------------------------------------ */
 #define HB_OK 0
-#define HB_ERR_INVALID 1   /* bad argument (reference: message + exit(1)) */
-#define HB_ERR_INDEX_SET 2 /* unknown index set (reference: "Invalid index set!" + exit(1)) */
-#define HB_ERR_FOURIER_DEGREE 3 /* odd degree on a Fourier axis (transform.cpp:92-96) */
-#define HB_ERR_DEGREE 4    /* n_polys does not match any degree (lib.cpp:93-99: exit(0)) */
-#define HB_ERR_CUDA 5      /* CUDA runtime/driver failure; hb_last_error() has the text */
-#define HB_ERR_ALIGN 6     /* device operand violates the 16-byte TMA alignment rule */
-#define HB_ERR_NOMEM 7
+#define HB_ERR_INVALID 1        /* bad argument (reference: message + exit(1), e.g. tensorize.cpp:50,64,79) */
+#define HB_ERR_INDEX_SET 2      /* unknown index set ("Invalid index set!" + exit(1), transform.cpp:166) */
+#define HB_ERR_FOURIER_DEGREE 3 /* odd degree on a Fourier axis (transform.cpp:92-96, varf.cpp:103-107) */
+#define HB_ERR_DEGREE 4         /* n_polys matches no degree ("Can't find x" + exit(0), lib.cpp:93-99) */
+#define HB_ERR_CUDA 5           /* CUDA runtime/driver failure or no device; see hb_last_error() */
+#define HB_ERR_ALIGN 6          /* device operand violates the 16-byte pitch rule of the TMA path */
+#define HB_ERR_NOMEM 7          /* device or caller buffer too small */
+
+const char* hb_last_error(void);  /* thread-local text of the last failure ("" if none) */
+const char* hb_version(void);
+int hb_device_count(int* count);  /* HB_ERR_CUDA if no driver */
+
+/* ---- multi-index sets (host only, usable without a GPU) ------------------------------------------
+ * reference: {triangle,cross,cross_nc,cube,rectangle}_{size,get_degree,list_indices}, triangle_index,
+ * cube_index  (module.cpp:143-166; iterators.cpp:106-596). */
+int hb_index_size(const char* index_set, int dim, int degree, long long* size);
+int hb_index_get_degree(const char* index_set, int dim, long long n_polys, int* degree);
+int hb_index_list(const char* index_set, int dim, int degree, uint32_t* out, size_t out_capacity /* entries */);
+int hb_triangle_index(const uint32_t* m, int dim, uint32_t* index);
+int hb_cube_index(const uint32_t* m, int dim, uint32_t* index);
+
+/* ---- Hermite functions by three-term recurrence ---------------------------------------------------
+ * reference: hermite_eval (hermite.cpp:29-41).  out[i*(degree+1) + k] = He_k(x_i)/sqrt(k!). */
+int hb_hermite_eval(const double* x, int n, int degree, double* out);
+
+/* ---- transform ---------------------------------------------------------------------------------------
+ * reference: transform(degree, f_grid, nodes, weights, do_fourier, forward, index_set)
+ * (module.cpp:92, transform.cpp:151-168).  forward: f has prod(n_pts) entries, out has |I| entries;
+ * backward: f has |I| entries, out has prod(n_pts).  hb_transform_batch does `batch` independent
+ * functions in one call (inputs/outputs stored contiguously one after another); the reference has no
+ * batched entry point (callers loop in Python). */
+int hb_transform(int dim, const int* n_pts, int degree, const double* f, const double* nodes,
+                 const double* weights, const int* do_fourier, int forward, const char* index_set, double* out,
+                 size_t out_len);
+int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const double* f, const double* nodes,
+                       const double* weights, const int* do_fourier, int forward, const char* index_set,
+                       double* out, size_t out_len_each);
+/* reference: integrate(f_grid, nodes, weights, do_fourier) (module.cpp:91, transform.cpp:170-181) */
+int hb_integrate(int dim, const int* n_pts, const double* f, const double* nodes, const double* weights,
+                 const int* do_fourier, double* result);
+
+/* ---- triple products and varf ----------------------------------------------------------------------
+ * reference: triple_products(degree) / triple_products_fourier(degree) (module.cpp:98-99,
+ * varf.cpp:49-162): out is (2*degree+1) x (degree+1) x (degree+1), row-major. */
+int hb_triple_products(int degree, double* out);
+int hb_triple_products_fourier(int degree, double* out);
+
+#define HB_VARF_REFERENCE 0 /* the reference's algebra: thresholded sum over alpha of Hf[alpha] * (x) T[alpha_d] */
+#define HB_VARF_GRAM 1      /* quadrature Gram form sum_x w f phi_m phi_n (dense FP64 tensor-core contraction) */
+/* reference: varf(degree, f_grid, nodes, weights, do_fourier, index_set) -> boost_mat (module.cpp:101,
+ * varf.cpp:164-288).  out is n_polys x n_polys row-major. */
+int hb_varf(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
+            const int* do_fourier, const char* index_set, int mode, double* out, size_t n_polys);
+/* reference: varf_sp(...) -> sparse_matrix + row_col_val (module.cpp:102,133; sparse.cpp:28-43).
+ * Two-step: hb_varf_sp computes and returns nnz; hb_sparse_fetch copies the CSR arrays of the last
+ * sparse result of this thread (indptr has n_rows+1 entries). */
+int hb_varf_sp(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
+               const int* do_fourier, const char* index_set, int mode, long long* nnz);
+int hb_sparse_fetch(long long* indptr, int* indices, double* data);
+/* reference: varfd(dim, degree, direction, var, do_fourier, index_set) (module.cpp:103-104, varf.cpp:290-456) */
+int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_polys, int do_fourier,
+             const char* index_set, double* out);
+
+/* ---- tensorize / project / inner ---------------------------------------------------------------------
+ * reference: tensorize_vecs_dirs / tensorize_mats_dirs (module.cpp:116-131, tensorize.cpp:86-381).
+ * k factors; factor j lives on directions dirs[j] (flattened into dirs_flat with lengths dir_lens[k]). */
+int hb_tensorize_vecs(int k, const double* const* inputs, const int* lens, const int* dirs_flat,
+                      const int* dir_lens, const char* index_set, double* out, size_t out_len);
+int hb_tensorize_mats(int k, const double* const* inputs, const int* sizes, const int* dirs_flat,
+                      const int* dir_lens, const char* index_set, double* out, size_t n_out);
+/* reference: project_vec_nd / project_mat_nd (module.cpp:108-113, project.cpp:35-129) */
+int hb_project_vec(const double* input, size_t len, int dim, const int* dirs, int n_dirs, const char* index_set,
+                   double* out, size_t out_len);
+int hb_project_mat(const double* input, size_t n, int dim, const int* dirs, int n_dirs, const char* index_set,
+                   double* out, size_t n_out);
+/* reference: inner(s1, s2, dirs1, dirs2, index_set) (module.cpp:95, inner.cpp:36-233) */
+int hb_inner(const double* s1, size_t n1, const double* s2, size_t n2, const int* dirs1, int nd1, const int* dirs2,
+             int nd2, const char* index_set, double* out, size_t out_len);
+
+/* ---- resident-data API (device pointers) -------------------------------------------------------------
+ * A plan owns the per-axis basis tables, index look-up tables and workspace for one
+ * (nodes, weights, degree, index_set) combination, like an FFT plan.  Device layout of a grid
+ * function: [n_0]...[n_{d-2}][pitch] doubles with pitch = hb_plan_grid_pitch() (n_{d-1} rounded up to
+ * an even count: 16-byte rows for TMA); batch entries are `stride` doubles apart (even).  Coefficient
+ * vectors are dense in index-set order, batch entries `stride` apart (even when dim == 1). */
+typedef struct hb_plan hb_plan;
+int hb_plan_create(hb_plan** plan, int dim, const int* n_pts, int degree, const double* nodes,
+                   const double* weights, const int* do_fourier, const char* index_set);
+void hb_plan_destroy(hb_plan* plan);
+long long hb_plan_n_polys(const hb_plan* plan);
+long long hb_plan_grid_pitch(const hb_plan* plan);   /* padded length of the last grid axis */
+long long hb_plan_grid_size(const hb_plan* plan);    /* doubles per grid function incl. padding */
+int hb_plan_forward(hb_plan* plan, const double* d_f, long long f_stride, int batch, double* d_coef,
+                    long long coef_stride, void* cuda_stream);
+int hb_plan_backward(hb_plan* plan, const double* d_coef, long long coef_stride, int batch, double* d_f,
+                     long long f_stride, void* cuda_stream);
+/* varf of one grid function into the owned rows [row_begin,row_end) of the n_polys x n_polys matrix
+ * (row-major, pitch ldo >= n_polys); row sharding across GPUs = one call per rank with its own range. */
+int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
+                 long long row_end, void* cuda_stream);
+/* number of kernels launched by this library on the calling thread since the last reset */
+long long hb_launch_count(int reset);
 
 #ifdef __cplusplus
 }

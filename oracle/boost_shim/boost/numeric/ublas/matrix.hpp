@@ -4,7 +4,11 @@
 // begin1()/end1() -> begin()/end() -> index1()/index2()/operator* traversal (varf.cpp:342-347).
 // Test infrastructure only (oracle build); never linked into the product library.
 #pragma once
+#include <algorithm>
+#include <cassert>
 #include <cstddef>
+#include <iostream>
+#include <memory>
 #include <vector>
 namespace boost { namespace numeric { namespace ublas {
 struct row_major {};
