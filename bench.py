@@ -1,0 +1,520 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: "Hermite transform Gpts/s and
+varf assembly ms; % of FP64 TC/HBM roofline").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c5|c4]
+
+One JSON line on stdout (rank 0).  Headline step (workload c2 = BASELINE.json configs[1]): forward +
+inverse 2-D Hermite transform of a batch of 17 functions on the 401 x 401 Gauss-Hermite grid at degree
+200 (cube set) with operands resident in HBM; `value` = grid points consumed (forward) + produced
+(inverse) per second over all ranks.  The same line carries the varf assembly times of the same
+config ("varf"), the batched 1-D (c5) and 3-D (c4) configs ("configs"), the roofline of the dominant
+kernel, the end-to-end number through the host-pointer C ABI ("e2e") and the reference's own CPU
+implementation timed on this box's cores ("cpu_baseline").  See DESIGN.md section "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(n=401, degree=200, batch=17, index_set="cube")
+C5 = dict(n_rule=2001, degree=1000, batch=65536)
+C4 = dict(n=256, degree=255)
+
+
+def gauss_hermite(n):
+    import scipy.special as sp
+    x, w = sp.roots_hermitenorm(n)
+    return x, w / np.sqrt(2 * np.pi)
+
+
+def c5_nodes():
+    x, w = gauss_hermite(C5["n_rule"])
+    keep = (w > 0) & (np.abs(x) <= 50)       # the reference formula is finite only here (SURVEY.md finding 4)
+    return x[keep], w[keep]
+
+
+def bistable(X, Y):
+    return X ** 4 / 4 - X ** 2 / 2 + Y ** 4 / 4 - Y ** 2 / 2 + X * Y / 2
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def ev_pair(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+class Flusher:
+    """Write a buffer larger than the 126 MB L2 between timed iterations."""
+
+    def __init__(self, torch):
+        self.buf = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+
+    def __call__(self):
+        self.buf.zero_()
+
+
+def time_steps(torch, fn, steps, warmup, flush, barrier):
+    for _ in range(warmup):
+        flush()
+        fn()
+    barrier()
+    torch.cuda.synchronize()
+    pairs = []
+    for _ in range(steps):
+        flush()
+        e0, e1 = ev_pair(torch)
+        e0.record()
+        fn()
+        e1.record()
+        pairs.append((e0, e1))
+    torch.cuda.synchronize()
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in pairs)  # ms over the K steps
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peak(torch):
+    """FP64 tensor-core GEMM peak is not in MEASURED_PEAKS.json: measure cuBLAS DGEMM 8192^3 here
+    (burst: best of 6; sustained: mean of a ~2 s back-to-back loop)."""
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    best = 1e9
+    for _ in range(6):
+        e0, e1 = ev_pair(torch)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    e0, e1 = ev_pair(torch)
+    reps = 40
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record()
+    torch.cuda.synchronize()
+    flop = 2.0 * 8192 ** 3
+    return flop / best * 1e-9, flop * reps / e0.elapsed_time(e1) * 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+def _ref_slab_job(args):
+    """One worker: the reference's own transform() on a slab of the C2 grid (rows of axis 0), forward and
+    inverse.  The naive loop is linear in the number of grid points, so a slab is a faithful bounded sample."""
+    rows, seed = args
+    from oracle import ref
+    x, w = gauss_hermite(C2["n"])
+    rng = np.random.default_rng(seed)
+    lo = int(rng.integers(0, C2["n"] - rows + 1))
+    xs, ws = x[lo:lo + rows], w[lo:lo + rows]
+    X, Y = np.meshgrid(xs, x, indexing="ij")
+    f = np.exp(-(X ** 2 + X * Y + Y ** 2) / 10).ravel()
+    t0 = time.perf_counter()
+    c = ref.transform(C2["degree"], f, [xs, x], [ws, w], True, index_set=C2["index_set"])
+    ref.transform(C2["degree"], c, [xs, x], [ws, w], False, index_set=C2["index_set"])
+    return time.perf_counter() - t0, 2 * rows * C2["n"]
+
+
+def reference_cpu_pass(rows, cores, pool):
+    """All host cores, each on its own slab (the reference is single-threaded).  Returns (seconds, points)."""
+    t0 = time.perf_counter()
+    res = pool.map(_ref_slab_job, [(rows, 1000 + i) for i in range(cores)])
+    wall = time.perf_counter() - t0
+    return wall, sum(r[1] for r in res)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref, compiled from its unmodified
+    sources) on this box's host cores; same config, metric and unit as our arm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhermite_ref.so missing"}))
+        return
+    cores = os.cpu_count() or 1
+    rows = 2
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            reference_cpu_pass(1, cores, pool)
+        t, pts = 0.0, 0
+        for _ in range(args.steps):
+            dt, p = reference_cpu_pass(rows, cores, pool)
+            t += dt
+            pts += p
+    value = pts / t * 1e-9
+    sample = ("per step: %d processes x (forward + inverse reference transform() of a %d x %d slab of the %d x %d "
+              "grid, degree %d %s)" % (cores, rows, C2["n"], C2["n"], C2["n"], C2["degree"], C2["index_set"]))
+    line = {
+        "impl": "reference", "metric": "hermite_transform_throughput", "value": value, "unit": "Gpts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "Gpts/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "c2: 2-D Hermite transform forward+inverse, degree %d per axis (%s set), %d x %d "
+                        "Gauss-Hermite grid, batch of %d functions per GPU; varf of the same config reported "
+                        "under 'varf'" % (C2["degree"], C2["index_set"], C2["n"], C2["n"], C2["batch"]),
+            "baseline_config": "configs[1] of BASELINE.json",
+            "l2": "256 MB buffer written between timed iterations",
+            "parallelism": "replicas x%d (a single 2-D transform does not shard; see 'configs' for the sharded "
+                           "c4/c5 runs)" % world}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hermipy_b200 import core, _lib
+    from hermipy_b200.plan import Plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = _lib.lib()
+    flush = Flusher(torch)
+    peaks, peaks_src = measured_peaks()
+    dgemm_burst, dgemm_sustained = fp64_peak(torch)
+    K, W = args.steps, args.warmup
+
+    # ---------------- headline: c2 transforms ----------------
+    x, w = gauss_hermite(C2["n"])
+    plan = Plan(C2["degree"], [x, x], [w, w], index_set=C2["index_set"])
+    B, n, P = C2["batch"], C2["n"], C2["degree"] + 1
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    rng = np.random.default_rng(2 + rank)
+    fns = [np.exp(-(X ** 2 + X * Y + Y ** 2) / 10)]
+    for _ in range(B - 1):   # smooth synthetic functions: random low-order polynomial x Gaussian
+        a = rng.standard_normal(6)
+        fns.append((a[0] + a[1] * X + a[2] * Y + a[3] * X * Y + a[4] * X ** 2 + a[5] * Y ** 2) * np.exp(-(X ** 2 + Y ** 2) / 6))
+    F_host = np.stack(fns)
+    F = plan.pack_grid(F_host)
+    Cf = plan.empty_coef(B)
+    G = plan.empty_grid(B)
+
+    def step():
+        plan.forward(F, Cf)
+        plan.backward(Cf, G)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.hb_launch_count(1)
+    total_ms = time_steps(torch, step, K, W, flush, barrier)
+    launches = int(lib.hb_launch_count(0)) - 0
+    clocks = sampler.stop()
+    launches_timed = launches * K // (K + W)
+    total_ms = max_over_ranks(total_ms)
+    pts_per_step = 2 * B * n * n
+    value = world * pts_per_step * K / (total_ms * 1e-3) * 1e-9
+
+    # per-launch device times of the same step (events around every GEMM launch)
+    plan.set_timing(True)
+    acc = {}
+    for _ in range(max(K, 3)):
+        flush()
+        plan.forward(F, Cf)
+        for tag, ms, _ in plan.timings():
+            acc.setdefault(("fwd", tag), []).append(ms)
+        plan.backward(Cf, G)
+        for tag, ms, _ in plan.timings():
+            acc.setdefault(("bwd", tag), []).append(ms)
+    plan.set_timing(False)
+    alg = {("fwd", 2): 2.0 * B * n * n * P, ("fwd", 1): 2.0 * B * P * n * P,
+           ("bwd", 12): 2.0 * B * P * P * n, ("bwd", 11): 2.0 * B * n * P * n}
+    launches_info = {"%s_tag%d" % k: {"ms": float(np.mean(v)), "tflops_algorithmic": alg[k] / np.mean(v) * 1e-9}
+                     for k, v in acc.items() if k in alg}
+    dom = max((k for k in acc if k in alg), key=lambda k: np.mean(acc[k]))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("c2_transform_dominant_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (%s stage, tag %d)" % dom,
+                "achieved": alg[dom] / np.mean(acc[dom]) * 1e-9, "peak": dgemm_burst, "unit": "TFLOP/s",
+                "frac": alg[dom] / np.mean(acc[dom]) * 1e-9 / dgemm_burst, "traffic": traffic,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (burst; FP64 is not in %s); sustained %.1f"
+                               % (peaks_src, dgemm_sustained),
+                "step_tflops_algorithmic": sum(alg.values()) * K / (total_ms * 1e-3) * 1e-12,
+                "launches": launches_info}
+
+    # round-trip property at full size (the oracle cannot run this size in reasonable time), in the
+    # quadrature-weighted L2 norm: un-weighted values at the outer nodes are ill-conditioned by design
+    # (phi_200 ~ 1e82 there), for the reference as much as for this code.
+    step()
+    sw = torch.from_numpy(np.sqrt(np.pad(np.outer(w, w), ((0, 0), (0, plan.grid_pitch - n))).ravel())).cuda()
+    rt = float((((G - F) * sw).norm() / (F * sw).norm()).item())
+
+    # ---------------- e2e: the host-pointer C ABI with pinned host buffers ----------------
+    Fh = torch.empty((B, n * n), dtype=torch.float64).pin_memory()
+    Fh.copy_(torch.from_numpy(F_host.reshape(B, -1)))
+    Fnp = Fh.numpy()
+    Ch = torch.empty((B, plan.n_polys), dtype=torch.float64).pin_memory().numpy()
+    Gh = torch.empty((B, n * n), dtype=torch.float64).pin_memory().numpy()
+    nodes, weights = [x, x], [w, w]
+
+    def e2e_step():
+        core.transform_batch(C2["degree"], Fnp, nodes, weights, True, index_set=C2["index_set"], out=Ch)
+        core.transform_batch(C2["degree"], Ch, nodes, weights, False, index_set=C2["index_set"], out=Gh)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_reps = max(3, min(K, 10))
+    for _ in range(e2e_reps):
+        e2e_step()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    n_polys = plan.n_polys
+    e2e = {"value": world * pts_per_step * e2e_reps / e2e_s * 1e-9, "unit": "Gpts/s",
+           "h2d_bytes_per_step": 8 * B * (n * n + n_polys), "d2h_bytes_per_step": 8 * B * (n * n + n_polys),
+           "api": "hermipy_b200.core.transform_batch (hb_transform_batch: host buffers, copies inside)"}
+
+    # ---------------- varf of the same config ----------------
+    varf = {}
+    if not args.skip_varf:
+        out = torch.empty((n_polys, n_polys), dtype=torch.float64, device="cuda")
+        fV = plan.pack_grid(bistable(X, Y)[None])[0]
+        fE = plan.pack_grid(np.exp(-3 * bistable(X, Y) / 10)[None])[0]
+        vs = max(2, min(K, 5))
+        ms_poly = max_over_ranks(time_steps(torch, lambda: plan.varf(fV, "reference", out), vs, 1, flush, barrier)) / vs
+        kept, path = plan.varf_info()
+        ref_poly = out.clone() if args.check else None
+        ms_gram = max_over_ranks(time_steps(torch, lambda: plan.varf(fE, "gram", out), vs, 1, flush, barrier)) / vs
+        plan.set_timing(True)
+        plan.varf(fE, "gram", out)
+        tl = {tag: ms for tag, ms, _ in plan.timings()}
+        plan.set_timing(False)
+        flops2 = 2.0 * n * float(P) ** 4
+        varf = {
+            "assembly_ms_polynomial_f": ms_poly,
+            "polynomial_f": {"mode": "reference algebra (thresholded sum over alpha, %d alpha kept, path %d)" % (kept, path),
+                             "bound": "hbm", "achieved_gbs": 8.0 * n_polys ** 2 / ms_poly * 1e-6,
+                             "peak_gbs": peaks.get("hbm_gbs"), "frac": 8.0 * n_polys ** 2 / ms_poly * 1e-6 / peaks.get("hbm_gbs")},
+            "assembly_ms_dense_f": ms_gram,
+            "dense_f": {"mode": "Gram form, two-stage DMMA GEMM", "bound": "tensor", "stage2_ms": tl.get(22),
+                        "achieved_tflops": flops2 / tl.get(22, np.nan) * 1e-9, "peak_tflops": dgemm_burst,
+                        "frac": flops2 / tl.get(22, np.nan) * 1e-9 / dgemm_burst,
+                        "algorithmic_flop": flops2 + 2.0 * n * n * P * P},
+            "matrix": "%d x %d dense (%.1f GB), %s set" % (n_polys, n_polys, 8e-9 * n_polys ** 2, C2["index_set"]),
+        }
+        if args.check:
+            plan.varf(fV, "gram", out)
+            varf["gram_vs_reference_algebra_rel_err_polynomial_f"] = float(((out - ref_poly).norm() / ref_poly.norm()).item())
+        del out
+
+    # ---------------- sharded configs ----------------
+    configs = {}
+    if not args.skip_configs:
+        configs["c5"] = bench_c5(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, dgemm_burst)
+        configs["c4"] = bench_c4(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, dgemm_burst)
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        cpu = cpu_baseline(F_host, x, w)
+
+    if rank == 0:
+        line = {
+            "metric": "hermite_transform_throughput", "value": value, "unit": "Gpts/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_timed,
+            "roofline": roofline, "cpu_baseline": cpu, "varf": varf, "configs": configs,
+            "checks": {"c2_roundtrip_rel_err": rt},
+            "peaks": {"hbm_gbs": peaks.get("hbm_gbs"), "hbm_source": peaks_src, "fp64_dgemm_tflops_burst": dgemm_burst,
+                      "fp64_dgemm_tflops_sustained": dgemm_sustained},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_c5(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, peak):
+    """65536 x 1-D degree-1000 transforms, batch-sharded (no data-path collective), strong scaling."""
+    from hermipy_b200.dist import split_range
+    x, w = c5_nodes()
+    n, P = len(x), C5["degree"] + 1
+    lo, hi = split_range(C5["batch"], world, rank)
+    Bl = hi - lo
+    plan = Plan(C5["degree"], [x], [w])
+    gen = torch.Generator(device="cuda").manual_seed(5 + rank)
+    coef = torch.randn((Bl, plan.coef_stride), generator=gen, dtype=torch.float64, device="cuda")
+    coef /= (1.0 + torch.arange(plan.coef_stride, device="cuda", dtype=torch.float64))
+    f = plan.backward(coef)                       # rows = random series evaluated on the grid
+    c = plan.empty_coef(Bl)
+    g = plan.empty_grid(Bl)
+    ms = max_over_ranks(time_steps(torch, lambda: (plan.forward(f, c), plan.backward(c, g)), K, W, flush, barrier)) / K
+    flops = 2 * 2.0 * C5["batch"] * n * P
+    return {"workload": "65536 x 1-D forward+inverse, degree 1000, %d nodes (w>0, |x|<=50 subset of the 2001-point rule)" % n,
+            "scaling": "strong", "ms": ms, "gpts": 2.0 * C5["batch"] * n / ms * 1e-6, "tflops": flops / ms * 1e-9,
+            "frac_of_dgemm_peak_per_gpu": flops / ms * 1e-9 / (peak * world), "collective": "none (batch shard)"}
+
+
+def bench_c4(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, peak):
+    """3-D forward+inverse, 256 nodes per axis, degree 255 (cube box), sharded on the outer axis."""
+    x, w = gauss_hermite(C4["n"])
+    n, P = C4["n"], C4["degree"] + 1
+    plan = Plan(C4["degree"], [x] * 3, [w] * 3, index_set="cube")
+    g = np.exp(-(x[:, None, None] ** 2 + x[None, :, None] ** 2 + x[None, None, :] ** 2) / 8) * (1 + 0.1 * x[None, :, None])
+    flops = 2 * 3 * 2.0 * n ** 4
+    if world == 1:
+        f = plan.pack_grid(g[None])
+        c = plan.empty_coef(1)
+        out = plan.empty_grid(1)
+        ms = time_steps(torch, lambda: (plan.forward(f, c), plan.backward(c, out)), K, W, flush, barrier) / K
+        sw = torch.from_numpy(np.sqrt(w[:, None, None] * w[None, :, None] * w[None, None, :]).ravel()).cuda()
+        rt = float((((out - f) * sw).norm() / (f * sw).norm()).item())
+        coll = "none"
+    else:
+        from hermipy_b200.dist import ShardedTransform, plan_tables_as_tensors
+        T = ShardedTransform([n] * 3, [P] * 3, plan_tables_as_tensors(plan))
+        f = torch.from_numpy(np.ascontiguousarray(g[rank * T.slab:(rank + 1) * T.slab])).cuda()
+        state = {}
+
+        def step():
+            state["c"] = T.forward(f)
+            state["g"] = T.backward(state["c"])
+
+        ms = max_over_ranks(time_steps(torch, step, K, W, flush, barrier)) / K
+        ws = w[rank * T.slab:(rank + 1) * T.slab]
+        sw = torch.from_numpy(np.sqrt(ws[:, None, None] * w[None, :, None] * w[None, None, :])).cuda()
+        rt = float((((state["g"].reshape(f.shape) - f) * sw).norm() / (f * sw).norm()).item())
+        coll = "one all-to-all per direction (NCCL), grid axis 0 <-> coefficient axis 1"
+    return {"workload": "3-D forward+inverse, 256^3 grid, degree 255 per axis (cube box)", "scaling": "strong", "ms": ms,
+            "gpts": 2.0 * n ** 3 / ms * 1e-6, "tflops": flops / ms * 1e-9,
+            "frac_of_dgemm_peak_per_gpu": flops / ms * 1e-9 / (peak * world), "roundtrip_rel_err": rt, "collective": coll}
+
+
+def cpu_baseline(F_host, x, w):
+    """The reference's own code (oracle/_ref) on this box's host cores, bounded sample (~10-30 s), plus a
+    sum-factorised NumPy/BLAS restatement of the same maths as the 'fair CPU' line."""
+    import multiprocessing as mp
+    from oracle import port, ref
+    cores = os.cpu_count() or 1
+    out = None
+    if ref.available():
+        rows = 3
+        with mp.get_context("spawn").Pool(cores) as pool:
+            reference_cpu_pass(1, cores, pool)
+            t, pts = reference_cpu_pass(rows, cores, pool)
+        out = {"value": pts / t * 1e-9, "unit": "Gpts/s", "cores": cores, "kind": "reference",
+               "sample": "%d processes x (forward + inverse reference transform() of a %d x %d slab of the %d x %d grid, "
+                         "degree %d %s); %.1f s wall" % (cores, rows, C2["n"], C2["n"], C2["n"], C2["degree"], C2["index_set"], t)}
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        c = port.transform_sumfac([C2["degree"]] * 2, F_host, [x, x], [w, w], True)
+        port.transform_sumfac([C2["degree"]] * 2, c, [x, x], [w, w], False)
+    dt = (time.perf_counter() - t0) / reps
+    fair = {"value": 2 * F_host.shape[0] * C2["n"] ** 2 / dt * 1e-9, "unit": "Gpts/s", "cores": cores,
+            "kind": "port (sum-factorised NumPy/BLAS, not the reference's algorithm)", "sample": "the full c2 step"}
+    if out is None:
+        return fair
+    out["fair_cpu"] = fair
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-varf", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--check", action="store_true", help="extra full-size consistency checks (slower)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

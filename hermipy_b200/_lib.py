@@ -72,6 +72,14 @@ SIGNATURES = {
     "hb_plan_varf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong,
                                C.c_longlong, C.c_void_p]),
     "hb_launch_count": (C.c_longlong, [C.c_int]),
+    "hb_plan_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "hb_plan_timing_count": (C.c_int, [C.c_void_p]),
+    "hb_plan_timing_get": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_dp, c_dp]),
+    "hb_dev_dgemm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int,
+                               C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong,
+                               C.c_void_p]),
+    "hb_plan_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_llp, c_llp, c_llp]),
+    "hb_plan_varf_info": (C.c_int, [C.c_void_p, c_ip, c_ip]),
 }
 
 

@@ -120,9 +120,10 @@ def transform(degree, fgrid, nodes, weights, forward, do_fourier=None, index_set
     return out
 
 
-def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, index_set="triangle"):
+def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, index_set="triangle", out=None):
     """`batch` independent transforms in one call; fgrids has shape (batch, n_in).  No reference equivalent
-    (the reference loops over hm.Quad.transform in Python)."""
+    (the reference loops over hm.Quad.transform in Python).  `out` may be a preallocated (batch, n_out)
+    float64 array (e.g. page-locked memory) to receive the result."""
     n_pts, nd, wt = _grid(nodes, weights)
     dim = len(n_pts)
     f = _d(fgrids)
@@ -133,7 +134,10 @@ def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, in
     n_in, n_out = (n_grid, n_polys) if forward else (n_polys, n_grid)
     if f.shape[1] != n_in:
         raise ValueError("transform_batch: rows have %d entries, expected %d" % (f.shape[1], n_in))
-    out = np.zeros((batch, n_out))
+    if out is None:
+        out = np.zeros((batch, n_out))
+    elif out.shape != (batch, n_out) or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("transform_batch: out must be a C-contiguous float64 array of shape (%d, %d)" % (batch, n_out))
     check(lib().hb_transform_batch(dim, _ip(n_pts), int(degree), batch, _dp(f), _dp(nd), _dp(wt),
                                    _ip(_fourier(do_fourier, dim)), int(bool(forward)), index_set.encode(),
                                    _dp(out), n_out))

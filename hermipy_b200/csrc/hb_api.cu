@@ -528,4 +528,48 @@ int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long
     return plan_varf(plan, d_f, mode, d_out, ldo, row_begin, row_end, static_cast<cudaStream_t>(stream));
 }
 
+int hb_plan_set_timing(hb_plan* plan, int on) { plan->timing = on != 0; plan->n_timed = 0; return HB_OK; }
+int hb_plan_timing_count(const hb_plan* plan) { return plan->n_timed; }
+int hb_plan_timing_get(hb_plan* plan, int i, int* tag, double* ms, double* padded_flops) {
+    if (i < 0 || i >= plan->n_timed) return HB_ERR_INVALID;
+    hb_plan::Timed& t = plan->timed[i];
+    HB_CUDA(cudaEventSynchronize(t.e1));
+    float el = 0;
+    HB_CUDA(cudaEventElapsedTime(&el, t.e0, t.e1));
+    *tag = t.tag; *ms = el; *padded_flops = t.flops;
+    return HB_OK;
+}
+// Generic device GEMM (row-major FP64, see hb_gemm.cuh) and access to a plan's basis tables, used by
+// the multi-GPU composition in hermipy_b200/dist.py.
+int hb_dev_dgemm(int M, int N, int K, int batch, const double* A, long long lda, long long strideA, int a_mmajor,
+                 const double* B, long long ldb, long long strideB, double* C, long long ldc, long long strideC,
+                 void* stream) {
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.batch = batch;
+    g.A = A; g.lda = lda; g.strideA = strideA; g.a_mmajor = a_mmajor != 0;
+    g.B = B; g.ldb = ldb; g.strideB = strideB;
+    g.C = C; g.ldc = ldc; g.strideC = strideC;
+    const int rc = gemm_launch(g, static_cast<cudaStream_t>(stream));
+    if (rc == HB_ERR_ALIGN) set_error("hb_dev_dgemm: operands need 16-byte aligned bases and even leading dimensions");
+    return rc;
+}
+int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
+                  long long* ld) {
+    if (axis < 0 || axis >= plan->dim) return HB_ERR_INVALID;
+    const Axis& A = plan->ax[axis];
+    switch (kind) {
+        case 0: *ptr = A.plain.d(); *rows = A.n; *cols = A.P; *ld = A.Pp; break;   // phi_k(x_i)        [i][k]
+        case 1: *ptr = A.wgt.d(); *rows = A.n; *cols = A.P; *ld = A.Pp; break;     // w_i phi_k(x_i)    [i][k]
+        case 2: *ptr = A.plainT.d(); *rows = A.P; *cols = A.n; *ld = A.np; break;  // phi_k(x_i)        [k][i]
+        case 3: *ptr = A.wgtT.d(); *rows = A.P; *cols = A.n; *ld = A.np; break;    // w_i phi_k(x_i)    [k][i]
+        default: return HB_ERR_INVALID;
+    }
+    return HB_OK;
+}
+int hb_plan_varf_info(const hb_plan* plan, int* n_kept, int* path) {
+    *n_kept = plan->last_n_kept;
+    *path = plan->last_path;
+    return HB_OK;
+}
+
 }  // extern "C"

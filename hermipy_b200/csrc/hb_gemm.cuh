@@ -74,10 +74,27 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
     const int m_base = tile_m * BM, n_base = tile_n * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (p.epi == EPI_VARF2D && p.tri_degree >= 0) {
-        // Triangle-like index sets keep only m0+m1 <= degree; the smallest m0 and m1 in this tile decide.
-        const int m0_min = m_base / p.Pp0, m1_min = n_base / p.Pp1;
-        if (m0_min + m1_min > p.tri_degree) return;
+    if (p.epi == EPI_VARF2D) {
+        // Tile-level skipping.  GEMM row = (m0, n0), column = (m1, n1); the entry lands at output row
+        // lut[m0,m1], column lut[n0,n1].
+        const int m_last = min(m_base + BM, p.M) - 1, n_last = min(n_base + BN, p.N) - 1;
+        const int m0_lo = m_base / p.Pp0, m0_hi = m_last / p.Pp0;
+        const int m1_lo = n_base / p.Pp1, m1_hi = n_last / p.Pp1;
+        if (p.tri_degree >= 0) {
+            // total-degree sets keep only m0+m1 <= degree and n0+n1 <= degree: the smallest values decide.
+            if (m0_lo + m1_lo > p.tri_degree) return;
+            const int n0_lo = (m0_lo == m0_hi) ? m_base - m0_lo * p.Pp0 : 0;
+            const int n1_lo = (m1_lo == m1_hi) ? n_base - m1_lo * p.Pp1 : 0;
+            if (n0_lo + n1_lo > p.tri_degree) return;
+        }
+        // row sharding: skip the tile unless some (m0, m1) in it maps to an owned output row
+        bool owned = false;
+        for (int a = m0_lo; a <= m0_hi && !owned; a++)
+            for (int c = m1_lo; c <= m1_hi; c++) {
+                const int r = (a < p.P0 && c < p.P1) ? p.lut[a * p.P1 + c] : -1;
+                if (r >= p.row_begin && r < p.row_end) { owned = true; break; }
+            }
+        if (!owned) return;
     }
 
     if (threadIdx.x == 0) {

@@ -70,9 +70,32 @@ int DevBuf::ensure_zero(size_t need, cudaStream_t s) {
 
 }  // namespace hb
 
-hb_plan::~hb_plan() { delete plan2; }
+hb_plan::~hb_plan() {
+    delete plan2;
+    for (Timed& t : timed) {
+        if (t.e0) cudaEventDestroy(t.e0);
+        if (t.e1) cudaEventDestroy(t.e1);
+    }
+}
 
 namespace hb {
+
+int timed_gemm(hb_plan* pl, const GemmArgs& g, int tag, cudaStream_t st) {
+    if (!pl->timing) return gemm_launch(g, st);
+    if (pl->n_timed >= (int)pl->timed.size()) {
+        hb_plan::Timed t;
+        HB_CUDA(cudaEventCreate(&t.e0));
+        HB_CUDA(cudaEventCreate(&t.e1));
+        pl->timed.push_back(t);
+    }
+    hb_plan::Timed& t = pl->timed[pl->n_timed++];
+    t.tag = tag;
+    t.flops = 2.0 * g.M * (double)g.N * g.K * g.batch;
+    HB_CUDA(cudaEventRecord(t.e0, st));
+    const int rc = gemm_launch(g, st);
+    HB_CUDA(cudaEventRecord(t.e1, st));
+    return rc;
+}
 
 // ---------------------------------------------------------------------------------------------
 int plan_create(hb_plan** out, int dim, const int* n_pts, int degree, const double* nodes, const double* weights,
@@ -162,7 +185,8 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         g.B = A.wgt.d(); g.ldb = A.Pp;
         g.C = d_coef; g.ldc = coef_stride;
         g.epi = EPI_STORE;  // every 1-D index set enumerates 0..P-1 in natural order
-        return gemm_launch(g, st);
+        pl->n_timed = 0;
+        return timed_gemm(pl, g, 1, st);
     }
     const Axis& L = pl->ax[d - 1];
     long long cols = L.Pp;
@@ -190,7 +214,8 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         }
         g.B = L.wgt.d(); g.ldb = L.Pp; g.strideB = 0;
         g.C = pl->ws[0].d(); g.ldc = cols;
-        HB_TRY(gemm_launch(g, st));
+        pl->n_timed = 0;
+        HB_TRY(timed_gemm(pl, g, d, st));
     }
     int cur = 0;
     long long prefix = (long long)batch * rows1;
@@ -206,7 +231,7 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         } else {
             g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = (long long)A.P * cols;
         }
-        HB_TRY(gemm_launch(g, st));
+        HB_TRY(timed_gemm(pl, g, 1 + a, st));
         cols *= A.P;
         cur ^= 1;
     }
@@ -225,7 +250,8 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
         g.A = d_coef; g.lda = coef_stride;
         g.B = A.plainT.d(); g.ldb = A.np;
         g.C = d_f; g.ldc = f_stride;
-        return gemm_launch(g, st);
+        pl->n_timed = 0;
+        return timed_gemm(pl, g, 11, st);
     }
     const Axis& L = pl->ax[d - 1];
     size_t need = (size_t)batch * pl->box_size;
@@ -249,7 +275,8 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
         g.A = pl->ws[0].d(); g.lda = L.Pp;
         g.B = L.plainT.d(); g.ldb = L.np;
         g.C = pl->ws[1].d(); g.ldc = cols;
-        HB_TRY(gemm_launch(g, st));
+        pl->n_timed = 0;
+        HB_TRY(timed_gemm(pl, g, 10 + d, st));
     }
     int cur = 1;
     long long prefix = (long long)batch * pl->box_rows;
@@ -265,7 +292,7 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
         } else {
             g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = (long long)A.n * cols;
         }
-        HB_TRY(gemm_launch(g, st));
+        HB_TRY(timed_gemm(pl, g, 11 + a, st));
         cols *= A.n;
         cur ^= 1;
     }
@@ -362,7 +389,7 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g1.A = coef; g1.lda = ld_coef;
     g1.B = Rtab; g1.ldb = ldR;
     g1.C = pl->G.d(); g1.ldc = ncol;
-    HB_TRY(gemm_launch(g1, st));
+    HB_TRY(timed_gemm(pl, g1, 21, st));
     GemmArgs g2;
     g2.M = (int)nrow; g2.K = K0; g2.N = (int)ncol;
     g2.A = Ltab; g2.lda = ldL; g2.a_mmajor = true;
@@ -373,7 +400,7 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.row_begin = (int)row_begin; g2.row_end = (int)row_end;
     g2.tri_degree = (pl->set == SET_TRIANGLE) ? pl->degree : -1;
     g2.cfg = 0;
-    return gemm_launch(g2, st);
+    return timed_gemm(pl, g2, 22, st);
 }
 
 static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ldo, long long row_begin,
@@ -494,6 +521,7 @@ int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long
     if (row_end <= row_begin) return HB_OK;
     if (ldo < pl->n_polys) return HB_ERR_INVALID;
     HB_TRY(ensure_varf_tables(pl, st));
+    pl->n_timed = 0;
     if (mode == HB_VARF_GRAM) return varf_gram(pl, d_f, d_out, ldo, row_begin, row_end, st);
     if (mode == HB_VARF_REFERENCE) return varf_reference(pl, d_f, d_out, ldo, row_begin, row_end, st);
     set_error("unknown varf mode %d", mode);

@@ -66,6 +66,11 @@ struct hb_plan {
     hb::DevBuf midx, lut2d, Hf, Hc, G, kept_alpha, kept_val, pair[2], tmp;
     std::vector<double> h_Hf;
     int last_n_kept = 0, last_path = 0;
+    // optional device timing (CUDA events on the launch stream) of every GEMM launch of the last call
+    struct Timed { cudaEvent_t e0 = nullptr, e1 = nullptr; int tag = 0; double flops = 0; };
+    bool timing = false;
+    std::vector<Timed> timed;
+    int n_timed = 0;
     ~hb_plan();
 };
 
@@ -79,5 +84,7 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
 int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
               long long row_end, cudaStream_t st);
 int ensure_triple_products(hb_plan* pl, cudaStream_t st);
+// GEMM launch bracketed by events when pl->timing; tag: 1+axis forward, 11+axis backward, 21/22 varf stage 1/2
+int timed_gemm(hb_plan* pl, const GemmArgs& g, int tag, cudaStream_t st);
 void fourier_triple_products_host(int degree, int Pp, std::vector<double>& out);
 }  // namespace hb

@@ -1,0 +1,114 @@
+"""Resident-data API: a Plan owns the device tables for one (grid, degree, index set) and works on
+torch CUDA tensors in place (torch is used only for device memory and streams).  Thin wrapper over
+the hb_plan_* entry points of the C ABI."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import c_dp, c_ip, check, lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dgemm(M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, strideA=0, strideB=0, strideC=0, a_mmajor=False):
+    """C[b] = A[b] @ B[b] on device pointers (ints or tensors) through the DMMA/TMA kernel."""
+    ptr = lambda t: t.data_ptr() if hasattr(t, "data_ptr") else int(t)
+    check(lib().hb_dev_dgemm(M, N, K, batch, ptr(A), lda, strideA, int(a_mmajor), ptr(B), ldb, strideB, ptr(Cout), ldc,
+                             strideC, _stream()))
+
+
+class Plan:
+    def __init__(self, degree, nodes, weights, do_fourier=None, index_set="triangle"):
+        nodes = [np.ascontiguousarray(n, dtype=np.float64).ravel() for n in nodes]
+        weights = [np.ascontiguousarray(w, dtype=np.float64).ravel() for w in weights]
+        self.dim = len(nodes)
+        self.n_pts = [len(n) for n in nodes]
+        self.degree = int(degree)
+        self.index_set = index_set
+        n_pts = np.ascontiguousarray(self.n_pts, dtype=np.int32)
+        nd, wt = np.concatenate(nodes), np.concatenate(weights)
+        four = np.ascontiguousarray([0] * self.dim if do_fourier is None else do_fourier, dtype=np.int32)
+        self._h = C.c_void_p()
+        torch.cuda.current_device()  # make sure the CUDA context of this process exists
+        check(lib().hb_plan_create(C.byref(self._h), self.dim, n_pts.ctypes.data_as(c_ip), self.degree,
+                                   nd.ctypes.data_as(c_dp), wt.ctypes.data_as(c_dp), four.ctypes.data_as(c_ip),
+                                   index_set.encode()))
+        self.n_polys = int(lib().hb_plan_n_polys(self._h))
+        self.grid_pitch = int(lib().hb_plan_grid_pitch(self._h))
+        self.grid_size = int(lib().hb_plan_grid_size(self._h))
+        self.coef_stride = (self.n_polys + 1) & ~1
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib._lib is not None:
+            lib().hb_plan_destroy(self._h)
+            self._h = None
+
+    # --- layout helpers -------------------------------------------------------------------------
+    def pack_grid(self, f):
+        """numpy (batch, n_0, ..., n_{d-1}) -> CUDA tensor (batch, grid_size) in the padded device layout."""
+        f = np.asarray(f, dtype=np.float64).reshape((-1,) + tuple(self.n_pts))
+        pad = self.grid_pitch - self.n_pts[-1]
+        if pad:
+            f = np.concatenate([f, np.zeros(f.shape[:-1] + (pad,))], axis=-1)
+        return torch.from_numpy(np.ascontiguousarray(f.reshape(f.shape[0], -1))).cuda()
+
+    def unpack_grid(self, t):
+        a = t.cpu().numpy().reshape((-1,) + tuple(self.n_pts[:-1]) + (self.grid_pitch,))
+        return a[..., :self.n_pts[-1]]
+
+    def empty_grid(self, batch):
+        return torch.zeros((batch, self.grid_size), dtype=torch.float64, device="cuda")
+
+    def empty_coef(self, batch):
+        return torch.zeros((batch, self.coef_stride), dtype=torch.float64, device="cuda")
+
+    # --- compute --------------------------------------------------------------------------------
+    def forward(self, f, out=None):
+        batch = f.shape[0]
+        out = self.empty_coef(batch) if out is None else out
+        check(lib().hb_plan_forward(self._h, f.data_ptr(), f.stride(0), batch, out.data_ptr(), out.stride(0),
+                                    _stream()))
+        return out
+
+    def backward(self, coef, out=None):
+        batch = coef.shape[0]
+        out = self.empty_grid(batch) if out is None else out
+        check(lib().hb_plan_backward(self._h, coef.data_ptr(), coef.stride(0), batch, out.data_ptr(),
+                                     out.stride(0), _stream()))
+        return out
+
+    def varf(self, f, mode="gram", out=None, row_begin=0, row_end=None):
+        """f: one grid function in device layout (grid_size,).  Returns rows [row_begin,row_end) of the matrix."""
+        row_end = self.n_polys if row_end is None else row_end
+        if out is None:
+            out = torch.empty((row_end - row_begin, self.n_polys), dtype=torch.float64, device="cuda")
+        check(lib().hb_plan_varf(self._h, f.data_ptr(), {"reference": 0, "gram": 1}[mode], out.data_ptr(),
+                                 out.stride(0), row_begin, row_end, _stream()))
+        return out
+
+    def set_timing(self, on=True):
+        check(lib().hb_plan_set_timing(self._h, int(on)))
+
+    def timings(self):
+        """[(tag, ms, padded_flops)] for every GEMM launch of the last call (needs set_timing(True))."""
+        out = []
+        for i in range(lib().hb_plan_timing_count(self._h)):
+            tag, ms, fl = C.c_int(0), C.c_double(0), C.c_double(0)
+            check(lib().hb_plan_timing_get(self._h, i, C.byref(tag), C.byref(ms), C.byref(fl)))
+            out.append((tag.value, ms.value, fl.value))
+        return out
+
+    def table(self, axis, kind):
+        """(device pointer, rows, cols, ld) of a basis table; kind: 0 phi[i][k], 1 w*phi[i][k], 2 phi[k][i], 3 w*phi[k][i]."""
+        ptr, r, c, ld = C.c_void_p(), C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        check(lib().hb_plan_table(self._h, axis, kind, C.byref(ptr), C.byref(r), C.byref(c), C.byref(ld)))
+        return ptr.value, r.value, c.value, ld.value
+
+    def varf_info(self):
+        k, p = C.c_int(0), C.c_int(0)
+        check(lib().hb_plan_varf_info(self._h, C.byref(k), C.byref(p)))
+        return k.value, p.value

@@ -128,6 +128,23 @@ int hb_plan_backward(hb_plan* plan, const double* d_coef, long long coef_stride,
  * (row-major, pitch ldo >= n_polys); row sharding across GPUs = one call per rank with its own range. */
 int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
                  long long row_end, void* cuda_stream);
+/* device-side timing (CUDA events on the launch stream) of every GEMM launch of the last hb_plan_*
+ * call, for roofline reporting.  tag: 1+axis forward stage, 11+axis backward stage, 21/22 varf stage
+ * 1/2; padded_flops = 2*M*N*K*batch the launch was asked for (table padding included). */
+int hb_plan_set_timing(hb_plan* plan, int on);
+int hb_plan_timing_count(const hb_plan* plan);
+int hb_plan_timing_get(hb_plan* plan, int i, int* tag, double* ms, double* padded_flops);
+/* building blocks for multi-GPU composition: the FP64 tensor-core GEMM on device operands
+ * (row-major; A is [M][K], or [K][M] if a_mmajor; B is [K][N]; a batch stride of 0 shares the operand;
+ * leading dimensions even, bases 16-byte aligned) and a plan's per-axis basis tables
+ * (kind 0: phi [node][k], 1: w*phi [node][k], 2: phi [k][node], 3: w*phi [k][node]). */
+int hb_dev_dgemm(int M, int N, int K, int batch, const double* A, long long lda, long long strideA, int a_mmajor,
+                 const double* B, long long ldb, long long strideB, double* C, long long ldc, long long strideC,
+                 void* cuda_stream);
+int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
+                  long long* ld);
+/* after hb_plan_varf(HB_VARF_REFERENCE): retained alpha count and path (0 = few-alpha assembly, 1 = dense GEMM) */
+int hb_plan_varf_info(const hb_plan* plan, int* n_kept, int* path);
 /* number of kernels launched by this library on the calling thread since the last reset */
 long long hb_launch_count(int reset);
 
