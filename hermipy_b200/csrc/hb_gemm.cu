@@ -5,6 +5,8 @@
 #include "hb_internal.h"
 #include "hb_plan.h"
 
+#include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <mutex>
 
@@ -49,7 +51,7 @@ static int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1
     return HB_OK;
 }
 
-template <int BM, int BN, int WMc, int WNc, int ST, bool AM>
+template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB>
 static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
     // A batch stride of 0 means "shared operand": the map gets a batch extent of 1 and the kernel
@@ -72,7 +74,7 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
     p.b_bmul = b_batched ? 1 : 0;
     const long long n_cta = (long long)p.tiles_m * p.tiles_n * a.batch;
     if (n_cta > 0x7fffffffLL) return HB_ERR_INVALID;
-    auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM>;
+    auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM, MINB>;
     constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
     static bool attr_set = false;
     if (!attr_set) {
@@ -82,6 +84,31 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
     }
     kern<<<(unsigned)n_cta, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
     return launch_status();
+}
+
+// Tile configurations: {BM, BN, resident CTAs per SM}.  The launcher picks the one with the smallest
+// modelled time = waves x (tile area x co-resident CTAs): small or oddly shaped problems (P = 201,
+// n = 401 ...) lose most of their time to tile quantisation and partial waves otherwise.
+struct TileCfg { int bm, bn, ctas; };
+static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2}};
+static const int kNumCfgs = 5;
+
+static int pick_cfg(const GemmArgs& a) {
+    const double sms = 148.0;
+    double best = 1e300;
+    int best_i = 0;
+    for (int i = 0; i < kNumCfgs; i++) {
+        const TileCfg& c = kCfgs[i];
+        const double tiles = (double)((a.M + c.bm - 1) / c.bm) * ((a.N + c.bn - 1) / c.bn) * a.batch;
+        const double slots = sms * c.ctas;
+        const double waves = std::ceil(tiles / slots);
+        // one wave costs a tile's MMA work times the CTAs sharing the SM, plus a fixed
+        // prologue/epilogue term (in the same units: ~ a 64x64 tile over 8 k-steps)
+        double t = waves * ((double)c.bm * c.bn * c.ctas * ((a.K + 15) / 16) + 64.0 * 64.0 * 8.0);
+        if (c.ctas == 1) t *= 1.04;  // no epilogue/mainloop overlap between co-resident CTAs
+        if (t < best) { best = t; best_i = i; }
+    }
+    return best_i;
 }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
@@ -96,18 +123,29 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.row_begin = a.row_begin; p.row_end = a.row_end; p.tri_degree = a.tri_degree;
     p.alpha = a.alpha;
-    const long long tiles128 = (long long)((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;
     int cfg = a.cfg;
-    if (cfg < 0) cfg = (tiles128 >= 148) ? 0 : 1;
+    if (cfg < 0) {
+        static const char* env = getenv("HB_GEMM_CFG_FIXED");      // developer override, read once
+        const char* dyn = getenv("HB_GEMM_CFG");                   // developer sweep (tools/cfg_sweep.py)
+        if (dyn && dyn[0] && dyn[0] != '-') cfg = atoi(dyn);
+        else if (env && env[0]) cfg = atoi(env);
+    }
+    if (cfg < 0 || cfg >= kNumCfgs) cfg = pick_cfg(a);
     if (a.a_mmajor) {
         switch (cfg) {
-            case 0: return launch_cfg<128, 128, 4, 2, 4, true>(a, p, stream);
-            default: return launch_cfg<64, 64, 2, 2, 6, true>(a, p, stream);
+            case 0: return launch_cfg<128, 128, 4, 2, 4, true, 1>(a, p, stream);
+            case 1: return launch_cfg<64, 64, 2, 2, 6, true, 2>(a, p, stream);
+            case 2: return launch_cfg<64, 128, 2, 2, 4, true, 2>(a, p, stream);
+            case 3: return launch_cfg<64, 208, 4, 2, 4, true, 1>(a, p, stream);
+            default: return launch_cfg<32, 208, 2, 2, 3, true, 2>(a, p, stream);
         }
     } else {
         switch (cfg) {
-            case 0: return launch_cfg<128, 128, 4, 2, 4, false>(a, p, stream);
-            default: return launch_cfg<64, 64, 2, 2, 6, false>(a, p, stream);
+            case 0: return launch_cfg<128, 128, 4, 2, 4, false, 1>(a, p, stream);
+            case 1: return launch_cfg<64, 64, 2, 2, 6, false, 2>(a, p, stream);
+            case 2: return launch_cfg<64, 128, 2, 2, 4, false, 2>(a, p, stream);
+            case 3: return launch_cfg<64, 208, 4, 2, 4, false, 1>(a, p, stream);
+            default: return launch_cfg<32, 208, 2, 2, 3, false, 2>(a, p, stream);
         }
     }
 }

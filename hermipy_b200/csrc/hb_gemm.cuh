@@ -52,14 +52,14 @@ constexpr int gemm_smem_bytes() {
     return STAGES * (BM + BN) * GEMM_BK * 8 + 1024 /*alignment slack*/ + 2 * STAGES * 8;
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool A_MMAJOR>
-__global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool A_MMAJOR, int MIN_CTAS>
+__global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
     dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MI = WM / 8, NJ = WN / 8;
-    static_assert(WM % 16 == 0 && WN % 16 == 0, "warp tile must be a multiple of 16");
+    static_assert(WN % 8 == 0 && WM % 8 == 0 && BN % 16 == 0 && (!A_MMAJOR || BM % 16 == 0), "tile granularity");
     constexpr int A_BYTES = BM * GEMM_BK * 8, B_BYTES = BN * GEMM_BK * 8;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 
@@ -149,9 +149,9 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
 #pragma unroll
     for (int mi = 0; mi < MI; mi++) {
         if (A_MMAJOR) {
-            const int m_in = 4 * (mi & 1) + cm;
-            a_off[mi] = ((wm * WM) / 16 + (mi >> 1)) * 2048 + t * 128 + ((((m_in >> 1) ^ t)) << 4) +
-                        (m_in & 1) * 8;
+            const int im = wm * MI + mi;  // MMA slot along M: 16-wide group im>>1, half im&1
+            const int m_in = 4 * (im & 1) + cm;
+            a_off[mi] = (im >> 1) * 2048 + t * 128 + ((((m_in >> 1) ^ t)) << 4) + (m_in & 1) * 8;
         } else {
             const int row = wm * WM + 8 * mi + rm;
             a_off[mi] = row * 128 + (((t >> 1) ^ rm) << 4) + (t & 1) * 8;
@@ -159,9 +159,9 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
     }
 #pragma unroll
     for (int nj = 0; nj < NJ; nj++) {
-        const int n_in = 4 * (nj & 1) + cm;
-        b_off[nj] = A_BYTES + ((wn * WN) / 16 + (nj >> 1)) * 2048 + t * 128 + ((((n_in >> 1) ^ t)) << 4) +
-                    (n_in & 1) * 8;
+        const int jn = wn * NJ + nj;  // MMA slot along N: 16-wide group jn>>1, half jn&1
+        const int n_in = 4 * (jn & 1) + cm;
+        b_off[nj] = A_BYTES + (jn >> 1) * 2048 + t * 128 + ((((n_in >> 1) ^ t)) << 4) + (n_in & 1) * 8;
     }
 
     double acc[MI][NJ][2];
@@ -202,12 +202,13 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
     // ---------------- epilogue ----------------
 #pragma unroll
     for (int mi = 0; mi < MI; mi++) {
-        const int row = m_base + wm * WM +
-                        (A_MMAJOR ? (16 * (mi >> 1) + 4 * (mi & 1) + cm) : (8 * mi + rm));
+        const int im = wm * MI + mi;
+        const int row = m_base + (A_MMAJOR ? (16 * (im >> 1) + 4 * (im & 1) + cm) : (wm * WM + 8 * mi + rm));
         if (row >= p.M) continue;
 #pragma unroll
         for (int nj = 0; nj < NJ; nj++) {
-            const int col = n_base + wn * WN + 16 * (nj >> 1) + 4 * (nj & 1) + 8 * (t & 1) + 2 * (t >> 1);
+            const int jn = wn * NJ + nj;
+            const int col = n_base + 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
             if (col >= p.N) continue;
             const double v0 = acc[mi][nj][0] * p.alpha, v1 = acc[mi][nj][1] * p.alpha;
             const bool has1 = (col + 1 < p.N);
@@ -231,16 +232,18 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, 1)
             } else {  // EPI_VARF2D
                 const int m0 = row / p.Pp0, n0 = row - m0 * p.Pp0;
                 if (n0 >= p.P0) continue;
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    if (e == 1 && !has1) break;
-                    const int c = col + e;
-                    const int m1 = c / p.Pp1, n1 = c - m1 * p.Pp1;
-                    if (n1 >= p.P1) continue;
-                    const int r_out = p.lut[m0 * p.P1 + m1];
-                    const int c_out = p.lut[n0 * p.P1 + n1];
-                    if (r_out >= p.row_begin && r_out < p.row_end && c_out >= 0)
-                        p.C[(long long)(r_out - p.row_begin) * p.ldc + c_out] = (e == 0 ? v0 : v1);
+                const int m1 = col / p.Pp1, n1 = col - m1 * p.Pp1;   // col is even and Pp1 is even:
+                if (n1 >= p.P1) continue;                            // col and col+1 share m1
+                const int r_out = p.lut[m0 * p.P1 + m1];
+                if (r_out < p.row_begin || r_out >= p.row_end) continue;
+                double* orow = p.C + (long long)(r_out - p.row_begin) * p.ldc;
+                const int c0 = p.lut[n0 * p.P1 + n1];
+                const int c1 = (has1 && n1 + 1 < p.P1) ? p.lut[n0 * p.P1 + n1 + 1] : -1;
+                if (c1 == c0 + 1 && c0 >= 0 && ((reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0)) {
+                    *reinterpret_cast<double2*>(orow + c0) = make_double2(v0, v1);   // one 16-byte store
+                } else {
+                    if (c0 >= 0) orow[c0] = v0;
+                    if (c1 >= 0) orow[c1] = v1;
                 }
             }
         }

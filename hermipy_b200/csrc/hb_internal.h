@@ -21,7 +21,7 @@ struct GemmArgs {
     const int* lut = nullptr;
     int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, tri_degree = -1;
     double alpha = 1.0;
-    int cfg = -1;  // -1 auto, 0 = 128x128 tiles, 1 = 64x64 tiles
+    int cfg = -1;  // -1 auto (cost model), else index into the tile-configuration table of hb_gemm.cu
 };
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);

@@ -293,6 +293,57 @@ int launch_varf_sparse(const VarfSparseArgs& a, double* out, cudaStream_t s) {
     return launch_status();
 }
 
+// Banded variant of the same assembly: T[k][i][j] vanishes unless |i-j| <= k, so with the retained
+// alpha bounded by amax[d] per axis only the entries with |m_d - n_d| <= amax[d] can be non-zero --
+// for polynomial f a few dozen per row out of |I|.  The matrix is zero-filled once (a plain memset,
+// HBM-write-bound) and only the band is computed: one thread per (row, band offset), same term order
+// and rounding as varf_sparse_kernel.
+__global__ void varf_band_kernel(VarfSparseArgs a, VarfBandArgs b, double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)(a.row_end - a.row_begin) * b.width_total;
+    if (idx >= total) return;
+    const int r = a.row_begin + (int)(idx / b.width_total);
+    int off = (int)(idx % b.width_total);
+    int m[HB_MAX_DIM], nn[HB_MAX_DIM];
+    long long lex = 0;
+    for (int d = a.dim - 1; d >= 0; d--) {          // offsets: last axis fastest
+        const int w = 2 * b.amax[d] + 1;
+        const int o = off % w;
+        off /= w;
+        m[d] = a.midx[(long long)r * a.dim + d];
+        nn[d] = m[d] + o - b.amax[d];
+        if (nn[d] < 0 || nn[d] >= b.extent[d]) return;
+    }
+    for (int d = 0; d < a.dim; d++) lex = lex * (d == a.dim - 1 ? b.pitch_last : b.extent[d]) + nn[d];
+    const int c = b.lut_box[lex];
+    if (c < 0) return;
+    double acc = 0.0;
+    for (int t = 0; t < a.n_kept; t++) {
+        double prod = 0.0;
+        bool zero = false;
+        for (int d = 0; d < a.dim; d++) {
+            const int al = a.kept_alpha[(long long)t * a.dim + d];
+            const double v = a.T[d][(long long)al * a.plane[d] + (long long)m[d] * a.Pp[d] + nn[d]];
+            if (v == 0.0) { zero = true; break; }
+            prod = (d == 0) ? v : __dmul_rn(prod, v);
+        }
+        if (zero) continue;
+        acc = __dadd_rn(acc, __dmul_rn(prod, a.kept_val[t]));
+    }
+    out[(long long)(r - a.row_begin) * a.ldo + c] = acc;
+}
+
+int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s) {
+    const long long rows = a.row_end - a.row_begin;
+    if (rows <= 0) return HB_OK;
+    if (cudaMemset2DAsync(out, (size_t)a.ldo * 8, 0, (size_t)a.n_polys * 8, (size_t)rows, s) != cudaSuccess)
+        return HB_ERR_CUDA;
+    const long long total = rows * b.width_total;
+    if (total == 0) return HB_OK;
+    varf_band_kernel<<<cdiv(total, 256), 256, 0, s>>>(a, b, out);
+    return launch_status();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dense -> CSR compaction (exact zeros dropped, as the reference's to_spmat does, sparse.cpp:44-58).
 __global__ void count_nnz_kernel(const double* __restrict__ A, long long ld, int n_cols, long long* row_nnz) {

@@ -39,6 +39,14 @@ struct VarfSparseArgs {
     int Pp[HB_MAX_DIM];
 };
 int launch_varf_sparse(const VarfSparseArgs& a, double* out, cudaStream_t s);
+struct VarfBandArgs {
+    int amax[HB_MAX_DIM];     // largest retained alpha per axis = half band width
+    int extent[HB_MAX_DIM];   // bounding box of the index set
+    int pitch_last;           // padded extent of the last axis in lut_box
+    long long width_total;    // prod (2*amax+1)
+    const int* lut_box;       // padded lexicographic box -> position (-1 absent)
+};
+int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s);
 
 int launch_count_nnz(const double* A, long long ld, int n_rows, int n_cols, long long* row_nnz, cudaStream_t s);
 int launch_fill_csr(const double* A, long long ld, int n_rows, int n_cols, const long long* indptr, int* indices,

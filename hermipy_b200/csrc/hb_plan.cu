@@ -399,7 +399,6 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.P0 = P0; g2.Pp0 = Pp0; g2.P1 = P1; g2.Pp1 = Pp1;
     g2.row_begin = (int)row_begin; g2.row_end = (int)row_end;
     g2.tri_degree = (pl->set == SET_TRIANGLE) ? pl->degree : -1;
-    g2.cfg = 0;
     return timed_gemm(pl, g2, 22, st);
 }
 
@@ -510,6 +509,23 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
         a.T[k] = pl->ax[k].fourier ? pl->Tf.d() : pl->T.d();
         a.plane[k] = (long long)(N + 1) * pl->TPp;
         a.Pp[k] = pl->TPp;
+    }
+    // band width from the retained alpha; zero-fill + band when that is much smaller than a full row
+    VarfBandArgs b;
+    b.width_total = 1;
+    for (int k = 0; k < d; k++) {
+        b.amax[k] = 0;
+        for (int t = 0; t < n_kept; t++) b.amax[k] = std::max(b.amax[k], kept_alpha[(size_t)t * d + k]);
+        b.extent[k] = pl->ax[k].P;
+        b.width_total *= std::min(2 * b.amax[k] + 1, 2 * pl->ax[k].P - 1);
+    }
+    b.pitch_last = pl->ax[d - 1].Pp;
+    b.lut_box = pl->lut_box.i();
+    if (b.width_total * 4 <= pl->n_polys) {
+        b.width_total = 1;
+        for (int k = 0; k < d; k++) b.width_total *= 2 * b.amax[k] + 1;
+        pl->last_path = 2;
+        return launch_varf_band(a, b, d_out, st);
     }
     return launch_varf_sparse(a, d_out, st);
 }
