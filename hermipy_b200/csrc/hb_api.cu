@@ -497,10 +497,65 @@ int hb_project_mat(const double* input, size_t n, int dim, const int* dirs, int 
     return project_impl(input, n, dim, dirs, n_dirs, index_set, true, out, n_out);
 }
 
-int hb_inner(const double*, size_t, const double*, size_t, const int*, int, const int*, int, const char*, double*,
-             size_t) {
-    set_error("hb_inner: not implemented yet (SURVEY.md section 8f, rank 3)");
-    return HB_ERR_INVALID;
+int hb_inner(const double* s1, size_t n1, const double* s2, size_t n2, const int* dirs1, int nd1, const int* dirs2,
+             int nd2, const char* index_set, double* out, size_t out_len) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    if (nd1 < 1 || nd2 < 1) return HB_ERR_INVALID;
+    // merge the (increasing) direction lists: shared directions are contracted, the others survive
+    // in increasing order (inner.cpp:61-84)
+    std::vector<int> from1, slot, inner1, inner2;   // for every result axis: comes from s1? which axis there
+    int i = 0, j = 0;
+    while (i < nd1 || j < nd2) {
+        if (i == nd1 || (j < nd2 && dirs1[i] > dirs2[j])) { from1.push_back(0); slot.push_back(j++); }
+        else if (j == nd2 || (i < nd1 && dirs1[i] < dirs2[j])) { from1.push_back(1); slot.push_back(i++); }
+        else { inner1.push_back(i++); inner2.push_back(j++); }
+    }
+    const int dim_res = (int)slot.size(), dim_in = (int)inner1.size();
+    int degree = 0, degree2 = 0;
+    if (index_get_degree(set, nd1, (long long)n1, &degree) || index_get_degree(set, nd2, (long long)n2, &degree2) ||
+        degree != degree2) {
+        set_error("inner: the two series do not have the same degree");
+        return HB_ERR_DEGREE;
+    }
+    auto it1 = get_index_set(set, nd1, degree), it2 = get_index_set(set, nd2, degree);
+    std::shared_ptr<const IndexSet> it_res = dim_res ? get_index_set(set, dim_res, degree) : nullptr;
+    std::shared_ptr<const IndexSet> it_in = dim_in ? get_index_set(set, dim_in, degree) : nullptr;
+    if (!it1 || !it2 || (dim_res && !it_res) || (dim_in && !it_in)) return HB_ERR_INVALID;
+    const int n_res = dim_res ? (int)it_res->size : 1, n_in = dim_in ? (int)it_in->size : 1;
+    if (out_len != (size_t)n_res) { set_error("inner: output size %zu != %d", out_len, n_res); return HB_ERR_INVALID; }
+    std::vector<int> ind1((size_t)n_res * n_in), ind2((size_t)n_res * n_in);
+    std::vector<uint32_t> m1(nd1), m2(nd2);
+    for (int r = 0; r < n_res; r++) {
+        for (int k = 0; k < dim_res; k++) {
+            const uint32_t v = it_res->list[(size_t)r * dim_res + k];
+            if (from1[k]) m1[slot[k]] = v; else m2[slot[k]] = v;
+        }
+        for (int q = 0; q < n_in; q++) {
+            for (int k = 0; k < dim_in; k++) {
+                const uint32_t v = it_in->list[(size_t)q * dim_in + k];
+                m1[inner1[k]] = v;
+                m2[inner2[k]] = v;
+            }
+            ind1[(size_t)q * n_res + r] = it1->position(m1.data());
+            ind2[(size_t)q * n_res + r] = it2->position(m2.data());
+        }
+    }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(g_aux[0].ensure(n1 * 8));
+    HB_TRY(g_aux[1].ensure(n2 * 8));
+    HB_TRY(g_auxi[0].ensure(ind1.size() * 4));
+    HB_TRY(g_auxi[1].ensure(ind2.size() * 4));
+    HB_TRY(g_out.ensure((size_t)n_res * 8));
+    HB_CUDA(cudaMemcpyAsync(g_aux[0].p, s1, n1 * 8, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_aux[1].p, s2, n2 * 8, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_auxi[0].p, ind1.data(), ind1.size() * 4, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_auxi[1].p, ind2.data(), ind2.size() * 4, cudaMemcpyHostToDevice, 0));
+    HB_TRY(launch_inner(g_aux[0].d(), g_aux[1].d(), g_auxi[0].i(), g_auxi[1].i(), n_res, n_in, g_out.d(), 0));
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, (size_t)n_res * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -344,6 +344,28 @@ int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out
     return launch_status();
 }
 
+// inner (reference: cpp/src/hermite/inner.cpp:36-217): result[i] = sum_j s1[ind1[j][i]] * s2[ind2[j][i]],
+// j over the shared ("inner") index set in iterator order, pairs outside either set skipped (:193-194).
+// One thread per result entry; the maps are stored [j][i] so that warps read them coalesced; products
+// are added sequentially without FMA, as the reference does.
+__global__ void inner_kernel(const double* __restrict__ s1, const double* __restrict__ s2, const int* __restrict__ ind1,
+                             const int* __restrict__ ind2, int n_res, int n_inner, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_res) return;
+    double acc = 0.0;
+    for (int j = 0; j < n_inner; j++) {
+        const int a = ind1[(long long)j * n_res + i], b = ind2[(long long)j * n_res + i];
+        if (a < 0 || b < 0) continue;
+        acc = __dadd_rn(acc, __dmul_rn(s1[a], s2[b]));
+    }
+    out[i] = acc;
+}
+int launch_inner(const double* s1, const double* s2, const int* ind1, const int* ind2, int n_res, int n_inner,
+                 double* out, cudaStream_t s) {
+    inner_kernel<<<cdiv(n_res, 128), 128, 0, s>>>(s1, s2, ind1, ind2, n_res, n_inner, out);
+    return launch_status();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dense -> CSR compaction (exact zeros dropped, as the reference's to_spmat does, sparse.cpp:44-58).
 __global__ void count_nnz_kernel(const double* __restrict__ A, long long ld, int n_cols, long long* row_nnz) {

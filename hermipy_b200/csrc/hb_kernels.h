@@ -48,6 +48,8 @@ struct VarfBandArgs {
 };
 int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s);
 
+int launch_inner(const double* s1, const double* s2, const int* ind1, const int* ind2, int n_res, int n_inner,
+                 double* out, cudaStream_t s);
 int launch_count_nnz(const double* A, long long ld, int n_rows, int n_cols, long long* row_nnz, cudaStream_t s);
 int launch_fill_csr(const double* A, long long ld, int n_rows, int n_cols, const long long* indptr, int* indices,
                     double* data, cudaStream_t s);

@@ -202,3 +202,20 @@ def test_tensorize_project(core, ref, index_set):
     for dirs in ([0], [1]):
         assert np.array_equal(core.project(M, 2, dirs, index_set=index_set),
                               ref.project(M, 2, dirs, index_set=index_set))
+
+
+@pytest.mark.parametrize("index_set", ["triangle", "cube", "cross"])
+def test_inner(core, ref, index_set):
+    """Series contraction behind Series.__mul__ (series.py:35-78 -> inner.cpp); three cases of inner.cpp:109-216."""
+    rng = np.random.default_rng(8)
+    degree = 6
+    n1, n2, n3 = (core.iterator_size(d, degree, index_set) for d in (1, 2, 3))
+    a1, b1 = rng.standard_normal(n1), rng.standard_normal(n1)
+    a2, b3 = rng.standard_normal(n2), rng.standard_normal(n3)
+    cases = [(a1, b1, [0], [1]),          # no shared direction: tensor product
+             (a1, b1, [0], [0]),          # all shared: scalar product
+             (a2, b3, [0, 2], [0, 1, 2]),  # partial contraction
+             (a2, a1, [0, 1], [1])]
+    for s1, s2, d1, d2 in cases:
+        assert np.array_equal(core.inner(s1, s2, d1, d2, index_set=index_set),
+                              ref.inner(s1, s2, d1, d2, index_set=index_set, variant="_o2")), (d1, d2)

@@ -51,10 +51,10 @@ if "c2" in which:
         print("C2 %s varf reference(poly): %.2f ms  kept=%d path=%d  %.1f GB/s written" % (s, t, k, p, pl.n_polys**2*8/t*1e-6))
         sym = (out - out.T).abs().max().item(); print("   symmetry err", sym)
         ref_poly = out.clone()
-        t = timeit(lambda: pl.varf(fV, "gram", out), reps=3, warm=1); ms, fl = pl.last_gemm()
+        t = timeit(lambda: pl.varf(fV, "gram", out), reps=3, warm=1); ms, fl = [(m_, f_) for t_, m_, f_ in pl.timings() if t_ == 22][0]
         print("C2 %s varf gram(poly): %.2f ms ; stage2 gemm %.2f ms %.2f TF(padded)" % (s, t, ms, fl/ms*1e-9))
         print("   gram vs reference rel err %.3e" % ((out-ref_poly).norm()/ref_poly.norm()).item())
-        t = timeit(lambda: pl.varf(fE, "gram", out), reps=3, warm=1); ms, fl = pl.last_gemm()
+        t = timeit(lambda: pl.varf(fE, "gram", out), reps=3, warm=1); ms, fl = [(m_, f_) for t_, m_, f_ in pl.timings() if t_ == 22][0]
         print("C2 %s varf gram(dense f): %.2f ms ; stage2 gemm %.2f ms %.2f TF(padded)" % (s, t, ms, fl/ms*1e-9))
         del out, ref_poly, pl
 
@@ -73,5 +73,5 @@ if "c3" in which:
     X, Y = np.meshgrid(x, x, indexing="ij"); V = X**4/4 - X**2/2 + Y**4/4 - Y**2/2 + X*Y/2
     fE = pl.pack_grid(np.exp(-3*V/10)[None])[0]
     out = torch.empty((pl.n_polys, pl.n_polys), dtype=torch.float64, device="cuda"); pl.set_timing(True)
-    t = timeit(lambda: pl.varf(fE, "gram", out), reps=2, warm=1); ms, fl = pl.last_gemm()
+    t = timeit(lambda: pl.varf(fE, "gram", out), reps=2, warm=1); ms, fl = [(m_, f_) for t_, m_, f_ in pl.timings() if t_ == 22][0]
     print("C3 triangle varf gram: %.1f ms ; stage2 gemm %.1f ms %.2f TF(padded full-square flops)" % (t, ms, fl/ms*1e-9))
