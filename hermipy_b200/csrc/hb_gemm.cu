@@ -87,25 +87,31 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
 }
 
 // Tile configurations: {BM, BN, resident CTAs per SM}.  The launcher picks the one with the smallest
-// modelled time = waves x (tile area x co-resident CTAs): small or oddly shaped problems (P = 201,
-// n = 401 ...) lose most of their time to tile quantisation and partial waves otherwise.
+// modelled time: small or oddly shaped problems (P = 201, n = 401, batch 17 ...) otherwise lose most of
+// their time to tile quantisation and partial waves over the 148 SMs.
 struct TileCfg { int bm, bn, ctas; };
-static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2}};
-static const int kNumCfgs = 5;
+static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2},
+                                {48, 208, 1},  {96, 128, 1}, {32, 128, 2}};
+static const int kNumCfgs = 8;
 
 static int pick_cfg(const GemmArgs& a) {
     const double sms = 148.0;
+    const double ksteps = (a.K + 15) / 16;
     double best = 1e300;
     int best_i = 0;
     for (int i = 0; i < kNumCfgs; i++) {
         const TileCfg& c = kCfgs[i];
-        const double tiles = (double)((a.M + c.bm - 1) / c.bm) * ((a.N + c.bn - 1) / c.bn) * a.batch;
-        const double slots = sms * c.ctas;
-        const double waves = std::ceil(tiles / slots);
-        // one wave costs a tile's MMA work times the CTAs sharing the SM, plus a fixed
-        // prologue/epilogue term (in the same units: ~ a 64x64 tile over 8 k-steps)
-        double t = waves * ((double)c.bm * c.bn * c.ctas * ((a.K + 15) / 16) + 64.0 * 64.0 * 8.0);
-        if (c.ctas == 1) t *= 1.04;  // no epilogue/mainloop overlap between co-resident CTAs
+        const long long tiles = (long long)((a.M + c.bm - 1) / c.bm) * ((a.N + c.bn - 1) / c.bn) * a.batch;
+        // DMMA-bound time of one tile in SM clocks (one DMMA.8x8x4 per 4 clocks per SM), plus a fixed
+        // prologue/epilogue cost that co-resident CTAs overlap with each other's main loop.
+        const double tile_t = (double)c.bm * c.bn * ksteps * 16.0 / 256.0 * 4.0;
+        const double fixed = 5000.0 + 0.02 * c.bm * c.bn;
+        const long long slots = (long long)sms * c.ctas;
+        const long long full = tiles / slots, rem = tiles % slots;
+        double t = full * (c.ctas * tile_t + (c.ctas > 1 ? 0.3 : 1.0) * fixed);
+        if (rem) t += std::ceil((double)rem / sms) * tile_t + fixed;
+        // small tiles re-read their operands more often (shared-memory and L2 traffic per flop)
+        t *= 1.0 + 6.0 / c.bm + 6.0 / c.bn;
         if (t < best) { best = t; best_i = i; }
     }
     return best_i;
@@ -137,7 +143,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
             case 1: return launch_cfg<64, 64, 2, 2, 6, true, 2>(a, p, stream);
             case 2: return launch_cfg<64, 128, 2, 2, 4, true, 2>(a, p, stream);
             case 3: return launch_cfg<64, 208, 4, 2, 4, true, 1>(a, p, stream);
-            default: return launch_cfg<32, 208, 2, 2, 3, true, 2>(a, p, stream);
+            case 4: return launch_cfg<32, 208, 2, 2, 3, true, 2>(a, p, stream);
+            case 5: return launch_cfg<48, 208, 3, 2, 4, true, 1>(a, p, stream);
+            case 6: return launch_cfg<96, 128, 3, 2, 4, true, 1>(a, p, stream);
+            default: return launch_cfg<32, 128, 2, 2, 4, true, 2>(a, p, stream);
         }
     } else {
         switch (cfg) {
@@ -145,7 +154,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
             case 1: return launch_cfg<64, 64, 2, 2, 6, false, 2>(a, p, stream);
             case 2: return launch_cfg<64, 128, 2, 2, 4, false, 2>(a, p, stream);
             case 3: return launch_cfg<64, 208, 4, 2, 4, false, 1>(a, p, stream);
-            default: return launch_cfg<32, 208, 2, 2, 3, false, 2>(a, p, stream);
+            case 4: return launch_cfg<32, 208, 2, 2, 3, false, 2>(a, p, stream);
+            case 5: return launch_cfg<48, 208, 3, 2, 4, false, 1>(a, p, stream);
+            case 6: return launch_cfg<96, 128, 3, 2, 4, false, 1>(a, p, stream);
+            default: return launch_cfg<32, 128, 2, 2, 4, false, 2>(a, p, stream);
         }
     }
 }

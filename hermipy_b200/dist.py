@@ -49,15 +49,23 @@ def device_gemm(A, B, out):
 
 
 class ShardedTransform:
-    """d-dimensional (d >= 2) transform with the outer grid axis sharded over the ranks of `group`.
+    """d-dimensional (d >= 3) transform with the outer grid axis sharded over the ranks of `group`.
 
     Grid functions: each rank holds f[x_0 in slab][x_1]...[x_{d-1}] (last axis padded to an even pitch).
     Coefficients: the lexicographic box c[m_0][m_1 in slice][m_2]...[m_{d-1}] (padded last axis), i.e.
     sharded along coefficient axis 1.  `tables[a]` = (phi[n_a, P_a], w_phi[n_a, P_a]) as torch tensors
-    on the compute device with even row pitch (views of the plan's device tables, or CPU tensors).
+    on the compute device (views of the plan's device tables, or CPU tensors for the gloo tests).
+
+    exchange = "nccl": the axis-1 GEMMs write a send buffer laid out [dest][x0][m1 in slice][rest] and one
+               all_to_all_single moves it;
+    exchange = "p2p":  the axis-1 GEMM for destination r stores its tile rows straight into rank r's
+               receive buffer through NVLink peer memory (torch symmetric memory gives the mapped
+               pointers), so the all-to-all is the GEMM epilogue; two device-side barriers fence it.
+    All buffers are allocated on first use and reused, so a step is a fixed launch sequence
+    (capturable in a CUDA graph: see `capture`).
     """
 
-    def __init__(self, n_pts, P, tables, group=None, gemm=device_gemm):
+    def __init__(self, n_pts, P, tables, group=None, gemm=device_gemm, exchange="nccl"):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -67,23 +75,43 @@ class ShardedTransform:
         assert self.n_pts[0] % self.world == 0, "outer grid axis must divide evenly over the ranks"
         self.slab = self.n_pts[0] // self.world
         self.Ps = -(-self.P[1] // self.world)  # coefficient-axis-1 slice width (last slices zero-padded)
-        self.tables = tables
         self.gemm = gemm
         self.np_last = even_up(self.n_pts[-1])
         self.Pp_last = even_up(self.P[-1])
         t = tables[0][0]
         self.dev, self.dtype = t.device, t.dtype
+        self.exchange = exchange if self.world > 1 else "none"
+        self._bufs = {}
+        self._symm = {}
+        # row-major copies of the tables with even pitch: phi[i][k], (w phi)^T[k][i], phi^T[k][i]
+        self.phi = [self._padded(tables[a][0][:, :self.P[a]]) for a in range(self.dim)]
+        self.wphi = [self._padded(tables[a][1][:, :self.P[a]]) for a in range(self.dim)]
+        self.wphiT = [self._padded(tables[a][1][:, :self.P[a]].t()) for a in range(self.dim)]
+        self.phiT = [self._padded(tables[a][0][:, :self.P[a]].t()) for a in range(self.dim)]
+        self._graphs = {}
 
-    # -- helpers ----------------------------------------------------------------------------------
-    def _empty(self, *shape):
-        return torch.zeros(shape, dtype=self.dtype, device=self.dev)
+    # -- buffers ----------------------------------------------------------------------------------
+    def _padded(self, t):
+        out = torch.zeros((t.shape[0], even_up(t.shape[1])), dtype=self.dtype, device=self.dev)
+        out[:, :t.shape[1]] = t
+        return out[:, :t.shape[1]]
 
-    def _exchange(self, send):
-        if self.world == 1:
-            return send
-        recv = torch.empty_like(send)
-        dist.all_to_all_single(recv, send, group=self.group)
-        return recv
+    def _buf(self, name, *shape):
+        key = (name, shape)
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(shape, dtype=self.dtype, device=self.dev)
+        return self._bufs[key]
+
+    def _symm_buf(self, name, *shape):
+        """symmetric-memory receive buffer + rendezvous handle (p2p exchange)"""
+        key = (name, shape)
+        if key not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(*shape, dtype=self.dtype, device=self.dev)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self._symm[key] = (t, hdl)
+        return self._symm[key]
 
     def local_grid_shape(self):
         return (self.slab, *self.n_pts[1:-1], self.np_last)
@@ -91,90 +119,117 @@ class ShardedTransform:
     def local_coef_shape(self):
         return (self.P[0], self.Ps, *self.P[2:-1], self.Pp_last)
 
+    # -- the exchange (grid axis 0 <-> coefficient axis 1) -------------------------------------------
+    def _scatter_gemms(self, name, A_rows, Bmat, block_shape):
+        """For every destination r: out_r = A_rows(r) @ Bmat, where out_r is this rank's block of rank r's
+        receive buffer [src][...block_shape].  Returns the local receive buffer, complete."""
+        g = self.world
+        if self.exchange == "p2p":
+            recv, hdl = self._symm_buf(name, g, *block_shape)
+            hdl.barrier(channel=0)              # peers have finished reading the previous contents
+            for r in range(g):
+                A = A_rows(r)
+                if A is None:
+                    continue
+                peer = hdl.get_buffer(r, (g, *block_shape), self.dtype)
+                self.gemm(A, Bmat, self._clip(peer[self.rank], A))
+            hdl.barrier(channel=1)              # every peer's stores have landed
+            return recv
+        send = self._buf(name + "_send", g, *block_shape)
+        for r in range(g):
+            A = A_rows(r)
+            if A is not None:
+                self.gemm(A, Bmat, self._clip(send[r], A))
+        if self.exchange == "none":
+            return send
+        recv = self._buf(name + "_recv", g, *block_shape)
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+    @staticmethod
+    def _clip(block, A):
+        """rows of the destination block actually produced by A (the last slice may be short)"""
+        rows = A.shape[-2]
+        return block[..., :rows, :] if block.shape[-2] != rows else block
+
     # -- forward ----------------------------------------------------------------------------------
     def forward(self, f):
         d, g, s, Ps = self.dim, self.world, self.slab, self.Ps
         cur = f.reshape(s, *self.n_pts[1:-1], self.np_last)
-        # local contractions: axes d-1 ... 2 (if any)
-        for a in range(d - 1, 1, -1):
-            cur = self._contract_forward(cur, a)
-        # axis 1, written straight into the send layout [dest][x0][m1 in slice][rest]
-        rest = int(np.prod(cur.shape[2:]))
+        for a in range(d - 1, 1, -1):            # local contractions of axes d-1 ... 2
+            cur = self._contract(cur, a, forward=True)
+        rest_shape = tuple(cur.shape[2:])
+        rest = int(np.prod(rest_shape))
         cur2 = cur.reshape(s, self.n_pts[1], rest)
-        send = self._empty(g, s, Ps, rest)
-        wT = self._rowmajor(self._wphi(1).t())                                          # [P1][n1]
-        for r in range(g):
+
+        def rows_for(r):
             lo, hi = r * Ps, min((r + 1) * Ps, self.P[1])
-            if hi > lo:
-                self.gemm(wT[lo:hi], cur2, send[r, :, :hi - lo])
-        recv = self._exchange(send)                                                    # [src][x0l][ml][rest]
+            return self.wphiT[1][lo:hi] if hi > lo else None
+
+        # axis 1, written straight into the exchange layout [dest][x0][m1 in slice][rest]
+        recv = self._scatter_gemms("fwd", rows_for, cur2, (s, Ps, rest))      # [src][x0l][ml][rest]
         cols = Ps * rest
-        cols_p = even_up(cols)
-        R = recv.reshape(self.n_pts[0], cols)
-        if cols_p != cols:
-            Rp = self._empty(self.n_pts[0], cols_p)
-            Rp[:, :cols] = R
-            R = Rp
-        out = self._empty(self.P[0], cols_p)
-        self.gemm(self._rowmajor(self._wphi(0).t()), R, out)
-        return out[:, :cols].reshape(self.P[0], Ps, *cur.shape[2:])
+        out = self._buf("fwd_out", self.P[0], cols)
+        self.gemm(self.wphiT[0], recv.reshape(self.n_pts[0], cols), out)
+        return out.reshape(self.P[0], Ps, *rest_shape)
 
-    def _wphi(self, a):
-        return self.tables[a][1][:, :self.P[a]]
-
-    def _phi(self, a):
-        return self.tables[a][0][:, :self.P[a]]
-
-    def _rowmajor(self, t):
-        """contiguous copy with an even row pitch (tables are tiny; done once per call)"""
-        out = self._empty(t.shape[0], even_up(t.shape[1]))
-        out[:, :t.shape[1]] = t
-        return out[:, :t.shape[1]]
-
-    def _contract_forward(self, cur, a):
-        """contract grid axis a (>= 2) of cur[x0][x1]...[x_a][cols] with w_phi_a -> [...][m_a][cols]"""
+    def _contract(self, cur, a, forward):
+        """contract axis a (>= 2) of cur[x0][x1]...[axis a][cols]"""
         d = self.dim
+        n_in, n_out = (self.n_pts[a], self.P[a]) if forward else (self.P[a], self.n_pts[a])
+        tag = "f" if forward else "b"
         if a == d - 1:
+            p_in, p_out = (self.np_last, self.Pp_last) if forward else (self.Pp_last, self.np_last)
             rows = int(np.prod(cur.shape[:-1]))
-            out = self._empty(rows, self.Pp_last)
-            self.gemm(cur.reshape(rows, self.np_last)[:, :self.n_pts[a]], self._wphi(a), out[:, :self.P[a]])
-            return out.reshape(*cur.shape[:-1], self.Pp_last)
+            out = self._buf("c%s%d" % (tag, a), rows, p_out)
+            table = self.wphi[a] if forward else self.phiT[a]          # [n_in][n_out]
+            self.gemm(cur.reshape(rows, p_in)[:, :n_in], table, out[:, :n_out])
+            return out.reshape(*cur.shape[:-1], p_out)
         lead = int(np.prod(cur.shape[:a]))
         cols = int(np.prod(cur.shape[a + 1:]))
-        out = self._empty(lead, self.P[a], cols)
-        self.gemm(self._rowmajor(self._wphi(a).t()), cur.reshape(lead, self.n_pts[a], cols), out)
-        return out.reshape(*cur.shape[:a], self.P[a], *cur.shape[a + 1:])
+        out = self._buf("c%s%d" % (tag, a), lead, n_out, cols)
+        table = self.wphiT[a] if forward else self.phi[a]              # [n_out][n_in]
+        self.gemm(table, cur.reshape(lead, n_in, cols), out)
+        return out.reshape(*cur.shape[:a], n_out, *cur.shape[a + 1:])
 
     # -- backward ---------------------------------------------------------------------------------
     def backward(self, c):
         d, g, s, Ps = self.dim, self.world, self.slab, self.Ps
-        rest_shape = c.shape[2:]
+        rest_shape = tuple(c.shape[2:])
         rest = int(np.prod(rest_shape))
         cols = Ps * rest
-        X = self._empty(self.n_pts[0], cols)
-        self.gemm(self._rowmajor(self._phi(0)), c.reshape(self.P[0], cols), X)          # [x0][ml][rest]
-        recv = self._exchange(X.reshape(g, s, Ps, rest))                               # [src][x0l][ml][rest]
-        Y = recv.permute(1, 0, 2, 3).reshape(s, g * Ps, rest)[:, :self.P[1]].contiguous()   # [x0l][m1][rest]
-        cur = self._empty(s, self.n_pts[1], rest)
-        self.gemm(self._rowmajor(self._phi(1)), Y, cur)                                 # [x0l][x1][rest]
+        c2 = c.reshape(self.P[0], cols)
+
+        def rows_for(r):                                                # grid rows x0 owned by rank r
+            return self.phi[0][r * s:(r + 1) * s]
+
+        # axis 0: X[x0][ml][rest] = phi_0 @ c, rows of destination r stored into its receive buffer
+        recv = self._scatter_gemms("bwd", rows_for, c2, (s, cols))       # [src][x0l][(ml, rest)]
+        # contract m1 = (src, ml): gather the slices of one x0l next to each other
+        Y = self._buf("bwd_Y", s, g * Ps, rest)
+        Y.copy_(recv.reshape(g, s, Ps, rest).permute(1, 0, 2, 3).reshape(s, g * Ps, rest))
+        cur = self._buf("bwd_x1", s, self.n_pts[1], rest)
+        self.gemm(self.phi[1], Y[:, :self.P[1]], cur)                    # [x0l][x1][rest]
         cur = cur.reshape(s, self.n_pts[1], *rest_shape)
         for a in range(2, d):
-            cur = self._contract_backward(cur, a)
+            cur = self._contract(cur, a, forward=False)
         return cur
 
-    def _contract_backward(self, cur, a):
-        d = self.dim
-        if a == d - 1:
-            rows = int(np.prod(cur.shape[:-1]))
-            out = self._empty(rows, self.np_last)
-            self.gemm(cur.reshape(rows, self.Pp_last)[:, :self.P[a]], self._rowmajor(self._phi(a).t()),
-                      out[:, :self.n_pts[a]])
-            return out.reshape(*cur.shape[:-1], self.np_last)
-        lead = int(np.prod(cur.shape[:a]))
-        cols = int(np.prod(cur.shape[a + 1:]))
-        out = self._empty(lead, self.n_pts[a], cols)
-        self.gemm(self._rowmajor(self._phi(a)), cur.reshape(lead, self.P[a], cols), out)
-        return out.reshape(*cur.shape[:a], self.n_pts[a], *cur.shape[a + 1:])
+    # -- CUDA graph of a forward+backward round trip on fixed buffers ---------------------------------
+    def capture(self, f):
+        """Warm up (allocates every buffer), then capture forward(f) -> backward as one CUDA graph.
+        Returns (graph, coefficient tensor, grid tensor); graph.replay() re-runs the launch sequence."""
+        for _ in range(2):
+            c = self.forward(f)
+            gout = self.backward(c)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(self.group)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            c = self.forward(f)
+            gout = self.backward(c)
+        return graph, c, gout
 
 
 def plan_tables_as_tensors(plan):
