@@ -43,6 +43,8 @@ SIGNATURES = {
     "hb_triangle_index": (C.c_int, [c_up, C.c_int, c_up]),
     "hb_cube_index": (C.c_int, [c_up, C.c_int, c_up]),
     "hb_hermite_eval": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp]),
+    "hb_discretize": (C.c_int, [C.c_char_p, C.c_int, c_ip, c_dp, c_dp, c_dp, c_dp, C.c_size_t]),
+    "hb_plan_discretize": (C.c_int, [C.c_void_p, C.c_char_p, c_dp, c_dp, C.c_void_p, C.c_void_p]),
     "hb_transform": (C.c_int, [C.c_int, c_ip, C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_char_p, c_dp,
                                C.c_size_t]),
     "hb_transform_batch": (C.c_int, [C.c_int, c_ip, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_char_p,

@@ -95,6 +95,20 @@ def hermite_eval(x, degree):
     return out
 
 
+def discretize(function, nodes, translation, dilation):
+    """hermipy/core.py:128-130: `function` is the C expression in v[i] produced by Function.ccode()
+    (function.py:118-123); evaluated on the GPU at translation + dilation @ node for every grid node."""
+    nodes = [_d(n).ravel() for n in nodes]
+    n_pts = _i([len(n) for n in nodes])
+    dim = len(nodes)
+    nd = _d(np.concatenate(nodes))
+    tr = _d(translation).ravel()
+    di = _d(dilation).reshape(dim, dim)
+    out = np.zeros(int(np.prod(n_pts)))
+    check(lib().hb_discretize(str(function).encode(), dim, _ip(n_pts), _dp(nd), _dp(tr), _dp(di), _dp(out), out.size))
+    return out
+
+
 def integrate(fgrid, nodes, weights, do_fourier=None):
     n_pts, nd, wt = _grid(nodes, weights)
     f = _d(fgrid).ravel()

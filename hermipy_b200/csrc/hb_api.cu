@@ -257,6 +257,25 @@ int hb_integrate(int dim, const int* n_pts, const double* f, const double* nodes
 }
 
 // ---------------------------------------------------------------------------------------------
+// discretize (module.cpp:88 -> discretize.cpp:112-126)
+int hb_discretize(const char* body, int dim, const int* n_pts, const double* nodes, const double* translation,
+                  const double* dilation, double* out, size_t out_len) {
+    HB_TRY(check_device());
+    if (!body || dim < 1 || dim > HB_MAX_DIM || !n_pts || !nodes) return HB_ERR_INVALID;
+    size_t tot = 0, total = 1;
+    for (int a = 0; a < dim; a++) { if (n_pts[a] < 1) return HB_ERR_INVALID; tot += n_pts[a]; total *= n_pts[a]; }
+    if (out_len != total) { set_error("discretize: out_len %zu != grid size %zu", out_len, total); return HB_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(g_in.ensure(tot * 8));
+    HB_TRY(g_out.ensure(total * 8));
+    HB_CUDA(cudaMemcpyAsync(g_in.p, nodes, tot * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(discretize_device(body, dim, n_pts, g_in.d(), translation, dilation, g_out.d(), n_pts[dim - 1], 0));
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, total * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 static int triple_products_impl(int degree, bool fourier, double* out) {
     HB_TRY(check_device());
     if (degree < 0) return HB_ERR_INVALID;
@@ -583,6 +602,25 @@ int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long
     return plan_varf(plan, d_f, mode, d_out, ldo, row_begin, row_end, static_cast<cudaStream_t>(stream));
 }
 
+int hb_plan_discretize(hb_plan* plan, const char* body, const double* translation, const double* dilation,
+                       double* d_f, void* stream) {
+    // nodes of all axes, concatenated on the device (built on first use)
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!plan->nodes_cat.p) {
+        size_t tot = 0;
+        for (const Axis& A : plan->ax) tot += A.n;
+        HB_TRY(plan->nodes_cat.ensure(tot * 8));
+        size_t off = 0;
+        for (const Axis& A : plan->ax) {
+            HB_CUDA(cudaMemcpyAsync(plan->nodes_cat.d() + off, A.x.p, (size_t)A.n * 8, cudaMemcpyDeviceToDevice, st));
+            off += A.n;
+        }
+    }
+    std::vector<int> n_pts;
+    for (const Axis& A : plan->ax) n_pts.push_back(A.n);
+    return discretize_device(body, plan->dim, n_pts.data(), plan->nodes_cat.d(), translation, dilation, d_f,
+                             plan->ax[plan->dim - 1].np, st);
+}
 int hb_plan_set_timing(hb_plan* plan, int on) { plan->timing = on != 0; plan->n_timed = 0; return HB_OK; }
 int hb_plan_timing_count(const hb_plan* plan) { return plan->n_timed; }
 int hb_plan_timing_get(hb_plan* plan, int i, int* tag, double* ms, double* padded_flops) {

@@ -59,6 +59,7 @@ struct hb_plan {
     long long n_polys = 0, grid_rows = 0 /* n_0..n_{d-2} */, grid_size = 0, box_rows = 0, box_size = 0;
     hb::DevBuf lut_box;  // int32[box_size]: padded lexicographic box -> position in the set, -1 absent
     hb::DevBuf ws[2];
+    hb::DevBuf nodes_cat;  // all axes' nodes, concatenated (discretize)
     // --- varf state (lazy) ---
     hb_plan* plan2 = nullptr;   // transform plan at degree 2*degree (Hf), owned
     int Tdeg = -1, TPp = 0;
@@ -87,4 +88,6 @@ int ensure_triple_products(hb_plan* pl, cudaStream_t st);
 // GEMM launch bracketed by events when pl->timing; tag: 1+axis forward, 11+axis backward, 21/22 varf stage 1/2
 int timed_gemm(hb_plan* pl, const GemmArgs& g, int tag, cudaStream_t st);
 void fourier_triple_products_host(int degree, int Pp, std::vector<double>& out);
+int discretize_device(const char* body, int dim, const int* n_pts, const double* d_nodes, const double* translation,
+                      const double* dilation, double* d_out, long long pitch_last, cudaStream_t st);
 }  // namespace hb

@@ -90,6 +90,16 @@ class Plan:
                                  out.stride(0), row_begin, row_end, _stream()))
         return out
 
+    def discretize(self, body, translation=None, dilation=None, out=None):
+        """Evaluate the C expression `body` (in v[i]) on this plan's grid, directly in device layout."""
+        out = self.empty_grid(1)[0] if out is None else out
+        tr = None if translation is None else np.ascontiguousarray(translation, dtype=np.float64)
+        di = None if dilation is None else np.ascontiguousarray(dilation, dtype=np.float64)
+        check(lib().hb_plan_discretize(self._h, str(body).encode(),
+                                       None if tr is None else tr.ctypes.data_as(c_dp),
+                                       None if di is None else di.ctypes.data_as(c_dp), out.data_ptr(), _stream()))
+        return out
+
     def set_timing(self, on=True):
         check(lib().hb_plan_set_timing(self._h, int(on)))
 

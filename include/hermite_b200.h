@@ -53,6 +53,15 @@ int hb_cube_index(const uint32_t* m, int dim, uint32_t* index);
  * reference: hermite_eval (hermite.cpp:29-41).  out[i*(degree+1) + k] = He_k(x_i)/sqrt(k!). */
 int hb_hermite_eval(const double* x, int n, int degree, double* out);
 
+/* ---- discretize --------------------------------------------------------------------------------------
+ * reference: discretize(function_body, nodes, translation, dilation) (module.cpp:88,
+ * discretize.cpp:112-126).  `body` is a C expression in v[0..dim-1] (what sympy.ccode produces after
+ * hermipy/function.py:118-123); it is evaluated at translation + dilation * node for every node of the
+ * tensor grid (dilation: dim x dim row-major; NULL = identity, translation NULL = 0).  The expression
+ * is compiled at run time with NVRTC for sm_100a (the reference shells out to the host C++ compiler). */
+int hb_discretize(const char* body, int dim, const int* n_pts, const double* nodes, const double* translation,
+                  const double* dilation, double* out, size_t out_len);
+
 /* ---- transform ---------------------------------------------------------------------------------------
  * reference: transform(degree, f_grid, nodes, weights, do_fourier, forward, index_set)
  * (module.cpp:92, transform.cpp:151-168).  forward: f has prod(n_pts) entries, out has |I| entries;
@@ -124,6 +133,9 @@ int hb_plan_forward(hb_plan* plan, const double* d_f, long long f_stride, int ba
                     long long coef_stride, void* cuda_stream);
 int hb_plan_backward(hb_plan* plan, const double* d_coef, long long coef_stride, int batch, double* d_f,
                      long long f_stride, void* cuda_stream);
+/* evaluate an expression on the plan's grid straight into the padded device layout (no host round trip) */
+int hb_plan_discretize(hb_plan* plan, const char* body, const double* translation, const double* dilation,
+                       double* d_f, void* cuda_stream);
 /* varf of one grid function into the owned rows [row_begin,row_end) of the n_polys x n_polys matrix
  * (row-major, pitch ldo >= n_polys); row sharding across GPUs = one call per rank with its own range. */
 int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,

@@ -66,6 +66,17 @@ def hermite_eval(x, degree, variant=""):
     return out
 
 
+def discretize(function, nodes, translation, dilation, variant=""):
+    nodes = [_d(n) for n in nodes]
+    dim = len(nodes)
+    n_pts = _i([len(n) for n in nodes])
+    nd, tr, di = _d(np.concatenate(nodes)), _d(translation), _d(dilation).reshape(dim, dim)
+    out = np.zeros(int(np.prod(n_pts)))
+    rc = lib(variant).ref_discretize(str(function).encode(), dim, _ip(n_pts), _dp(nd), _dp(tr), _dp(di), _dp(out), out.size)
+    assert rc == 0, rc
+    return out
+
+
 def iterator_size(dim, degree, index_set="triangle", variant=""):
     return int(lib(variant).ref_index_size(index_set.encode(), dim, degree))
 

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "hermite/discretize.hpp"
 #include "hermite/hermite.hpp"
 #include "hermite/inner.hpp"
 #include "hermite/iterators.hpp"
@@ -61,6 +62,16 @@ void ref_hermite_eval(double x, unsigned degree, double* out) {
     vec v(degree + 2, 0.);  // +1 slot: the reference writes values[1] even for degree 0
     hermite_eval(x, degree, v);
     memcpy(out, v.data(), (degree + 1) * sizeof(double));
+}
+
+// discretize.cpp:112-126 (writes /tmp/<hash>.cpp, compiles it with the host c++ and dlopen()s the result)
+int ref_discretize(const char* body, int dim, const int* n_pts, const double* nodes, const double* translation,
+                   const double* dilation, double* out, int out_len) {
+    vec r = discretize_from_string(body, unflatten(nodes, n_pts, dim), vec(translation, translation + dim),
+                                   to_mat(dilation, dim, dim));
+    if ((int)r.size() != out_len) return (int)r.size();
+    memcpy(out, r.data(), r.size() * sizeof(double));
+    return 0;
 }
 
 // transform.cpp:151-168

@@ -91,3 +91,23 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in text.replace("oracle/", "oracle/").lower() or fn == "README.md", \
                     "%s mentions the oracle" % os.path.join(dirpath, fn)
+
+
+def test_gauss_hermite_generator_beyond_numpy_limit():
+    """hermipy/lib.py:24-33 replacement: correct for n >= 371 where numpy's hermegauss breaks (SURVEY finding 3)."""
+    import scipy.special as sp
+    from hermipy_b200.lib import hermegauss, hermegauss_nd
+    for n in (1, 2, 7, 128, 401, 1001):
+        x, w = hermegauss(n)
+        assert len(x) == n and np.all(np.diff(x) > 0) and np.all(w >= 0) and np.all(np.isfinite(w))
+        assert abs(w.sum() - 1) < 1e-14
+        if n >= 3:
+            assert abs(np.sum(w * x ** 2) - 1) < 1e-13 and abs(np.sum(w * x ** 4) - 3) < 1e-12   # tests/test_quad.py:39-51
+        if n > 1:
+            xs, ws = sp.roots_hermitenorm(n)
+            ws = ws / np.sqrt(2 * np.pi)
+            assert np.abs(x - xs).max() < 1e-12
+            big = ws > 1e-280
+            assert np.max(np.abs(w[big] - ws[big]) / ws[big]) < 1e-11
+    nodes, weights = hermegauss_nd([3, 5])
+    assert [len(n) for n in nodes] == [3, 5] and [len(w) for w in weights] == [3, 5]

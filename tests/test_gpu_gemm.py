@@ -1,0 +1,59 @@
+"""GPU tests of the DMMA/TMA GEMM engine on its own: every tile configuration, both A layouts, ragged
+shapes, batch strides and shared operands, against torch.matmul in FP64 (the one floating-point kernel
+for which a torch reference is the right oracle)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+N_CFGS = 8
+
+
+def _run(torch, M, N, K, batch, a_mmajor, shared_a, cfg):
+    from hermipy_b200.plan import dgemm
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + batch)
+    ev = lambda v: (v + 1) & ~1
+    nb_a = 1 if shared_a else batch
+    if a_mmajor:
+        A = torch.randn((nb_a, K, ev(M)), generator=g, dtype=torch.float64, device="cuda")
+        A_log = A[:, :, :M].transpose(1, 2)
+        lda = ev(M)
+    else:
+        A = torch.randn((nb_a, M, ev(K)), generator=g, dtype=torch.float64, device="cuda")
+        A_log = A[:, :, :K]
+        lda = ev(K)
+    B = torch.randn((batch, K, ev(N)), generator=g, dtype=torch.float64, device="cuda")
+    C = torch.full((batch, M, ev(N)), float("nan"), dtype=torch.float64, device="cuda")
+    os.environ["HB_GEMM_CFG"] = str(cfg)
+    try:
+        dgemm(M, N, K, A, lda, B, ev(N), C, ev(N), batch=batch, strideA=0 if shared_a else A.stride(0),
+              strideB=B.stride(0), strideC=C.stride(0), a_mmajor=a_mmajor)
+    finally:
+        os.environ["HB_GEMM_CFG"] = "-1"
+    want = torch.matmul(A_log, B[:, :, :N])
+    got = C[:, :, :N]
+    assert torch.isfinite(got).all(), "unwritten output entries"
+    scale = torch.matmul(A_log.abs(), B[:, :, :N].abs()).max().item()
+    return (got - want).abs().max().item() / scale
+
+
+@pytest.mark.parametrize("cfg", list(range(N_CFGS)) + [-1])
+@pytest.mark.parametrize("a_mmajor", [False, True])
+def test_every_tile_configuration(cfg, a_mmajor):
+    import torch
+    for (M, N, K, batch, shared) in [(300, 200, 100, 1, False), (33, 209, 17, 3, True), (257, 131, 402, 2, False),
+                                     (32, 256, 256, 4, True), (1, 64, 64, 1, False), (515, 333, 77, 2, True)]:
+        err = _run(torch, M, N, K, batch, a_mmajor, shared, cfg)
+        assert err < 1e-14, (cfg, a_mmajor, M, N, K, batch, shared, err)
+
+
+def test_alignment_is_checked():
+    import torch
+    from hermipy_b200 import HermiteB200Error
+    from hermipy_b200.plan import dgemm
+    A = torch.zeros((8, 7), dtype=torch.float64, device="cuda")     # odd leading dimension
+    B = torch.zeros((7, 8), dtype=torch.float64, device="cuda")
+    C = torch.zeros((8, 8), dtype=torch.float64, device="cuda")
+    with pytest.raises(HermiteB200Error):
+        dgemm(8, 8, 7, A, 7, B, 8, C, 8)

@@ -219,3 +219,35 @@ def test_inner(core, ref, index_set):
     for s1, s2, d1, d2 in cases:
         assert np.array_equal(core.inner(s1, s2, d1, d2, index_set=index_set),
                               ref.inner(s1, s2, d1, d2, index_set=index_set, variant="_o2")), (d1, d2)
+
+
+def test_discretize_nvrtc_vs_reference(core, ref):
+    """Function -> grid values (quad.py:249-254 -> discretize.cpp:112-126).  The reference compiles the
+    expression with the host c++ at -Ofast; here NVRTC compiles it for sm_100a: agreement to a few ulp."""
+    x, _ = gauss_hermite(9)
+    y, _ = gauss_hermite(6)
+    body = "exp(-v[0]*v[0]/4)*cos(3*v[1]) + pow(v[1], 3)/(1 + v[0]*v[0]) + M_PI"
+    tr, di = [0.3, -1.0], [[2.0, 0.5], [0.0, 0.7]]
+    got = core.discretize(body, [x, y], tr, di)
+    want = ref.discretize(body, [x, y], tr, di)
+    assert got.shape == want.shape == (54,)
+    assert rel_err(got, want) < 1e-14
+    z, _ = gauss_hermite(4)
+    got3 = core.discretize("v[0] + 10*v[1] + 100*v[2]", [x, y, z], [0, 0, 0], np.eye(3))
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    assert np.allclose(got3, (X + 10 * Y + 100 * Z).ravel(), rtol=1e-15, atol=1e-13)   # row-major, last axis fastest
+    from hermipy_b200 import HermiteB200Error
+    with pytest.raises(HermiteB200Error):
+        core.discretize("this is not C", [x], [0.0], [[1.0]])
+
+
+def test_plan_discretize_feeds_transform_without_host_round_trip(ref):
+    import torch
+    from hermipy_b200.plan import Plan
+    x, w = gauss_hermite(31)
+    plan = Plan(12, [x, x], [w, w], index_set="triangle")
+    f_dev = plan.discretize("exp(-(v[0]*v[0] + v[0]*v[1] + v[1]*v[1])/10)")
+    c = plan.forward(f_dev[None])[0, :plan.n_polys].cpu().numpy()
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    f = np.exp(-(X ** 2 + X * Y + Y ** 2) / 10)
+    assert rel_err(c, ref.transform(12, f.ravel(), [x, x], [w, w], True)) < 1e-12
