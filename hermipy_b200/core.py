@@ -142,10 +142,12 @@ def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, in
     dim = len(n_pts)
     f = _d(fgrids)
     batch = f.shape[0]
-    f = f.reshape(batch, -1)
     n_grid = int(np.prod(n_pts))
     n_polys = iterator_size(dim, int(degree), index_set)
     n_in, n_out = (n_grid, n_polys) if forward else (n_polys, n_grid)
+    if batch == 0:
+        return np.zeros((0, n_out))
+    f = f.reshape(batch, -1)
     if f.shape[1] != n_in:
         raise ValueError("transform_batch: rows have %d entries, expected %d" % (f.shape[1], n_in))
     if out is None:

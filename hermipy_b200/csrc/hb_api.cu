@@ -646,6 +646,22 @@ int hb_dev_dgemm(int M, int N, int K, int batch, const double* A, long long lda,
     if (rc == HB_ERR_ALIGN) set_error("hb_dev_dgemm: operands need 16-byte aligned bases and even leading dimensions");
     return rc;
 }
+int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long long lda, long long strideA,
+                         int a_mmajor, const double* B, long long ldb, long long strideB, double* const* blocks,
+                         int n_blocks, int block_rows, long long ldc, long long strideC, void* stream) {
+    if (n_blocks < 1 || n_blocks > 16 || block_rows < 1 || (long long)n_blocks * block_rows < M) {
+        set_error("hb_dev_dgemm_scatter: need 1..16 row blocks covering M");
+        return HB_ERR_INVALID;
+    }
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.batch = batch;
+    g.A = A; g.lda = lda; g.strideA = strideA; g.a_mmajor = a_mmajor != 0;
+    g.B = B; g.ldb = ldb; g.strideB = strideB;
+    g.C = blocks[0]; g.ldc = ldc; g.strideC = strideC;
+    g.block_rows = block_rows;
+    for (int i = 0; i < n_blocks; i++) g.blocks[i] = blocks[i];
+    return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
 int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
                   long long* ld) {
     if (axis < 0 || axis >= plan->dim) return HB_ERR_INVALID;

@@ -129,6 +129,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.row_begin = a.row_begin; p.row_end = a.row_end; p.tri_degree = a.tri_degree;
     p.alpha = a.alpha;
+    p.block_rows = a.block_rows;
+    for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.blocks[i] = a.blocks[i];
+    if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) return HB_ERR_INVALID;
     int cfg = a.cfg;
     if (cfg < 0) {
         static const char* env = getenv("HB_GEMM_CFG_FIXED");      // developer override, read once

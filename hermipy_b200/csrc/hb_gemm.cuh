@@ -29,6 +29,8 @@ enum EpilogueMode : int {
     EPI_VARF2D = 2,   // row=(m0,n0), col=(m1,n1): out[(lut[m0*P+m1]-row_begin)*ldc + lut[n0*P+n1]] = v
 };
 
+constexpr int GEMM_MAX_BLOCKS = 16;
+
 struct GemmParams {
     int M, N, K, batch;
     double* C;
@@ -43,6 +45,11 @@ struct GemmParams {
     double alpha;       // result scale
     int tiles_m, tiles_n;    // grid is linear: blockIdx.x = (b*tiles_m + tile_m)*tiles_n + tile_n
     int a_bmul, b_bmul;      // 0: operand shared by all batch entries, 1: batched
+    // EPI_STORE with row blocks: output row r goes to blocks[r / block_rows] + (r % block_rows)*ldc.
+    // The block pointers may be peer-GPU addresses (NVLink P2P): this is how a GEMM's epilogue performs
+    // the all-to-all of the sharded transform.
+    int block_rows;          // 0 = off
+    double* blocks[GEMM_MAX_BLOCKS];
 };
 
 constexpr int GEMM_BK = 16;  // doubles per k-tile = one 128-byte swizzle span
@@ -213,7 +220,8 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
             const double v0 = acc[mi][nj][0] * p.alpha, v1 = acc[mi][nj][1] * p.alpha;
             const bool has1 = (col + 1 < p.N);
             if (p.epi == EPI_STORE) {
-                double* dst = p.C + (long long)b * p.strideC + (long long)row * p.ldc + col;
+                double* dst = (p.block_rows ? p.blocks[row / p.block_rows] + (long long)(row % p.block_rows) * p.ldc
+                                            : p.C + (long long)row * p.ldc) + (long long)b * p.strideC + col;
                 if (has1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                     *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
                 } else {

@@ -21,6 +21,8 @@ struct GemmArgs {
     const int* lut = nullptr;
     int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, tri_degree = -1;
     double alpha = 1.0;
+    int block_rows = 0;              // EPI_STORE: rows [i*block_rows, (i+1)*block_rows) -> blocks[i] (C unused)
+    double* blocks[16] = {nullptr};
     int cfg = -1;  // -1 auto (cost model), else index into the tile-configuration table of hb_gemm.cu
 };
 

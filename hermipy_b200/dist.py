@@ -120,31 +120,8 @@ class ShardedTransform:
         return (self.P[0], self.Ps, *self.P[2:-1], self.Pp_last)
 
     # -- the exchange (grid axis 0 <-> coefficient axis 1) -------------------------------------------
-    def _scatter_gemms(self, name, A_rows, Bmat, block_shape):
-        """For every destination r: out_r = A_rows(r) @ Bmat, where out_r is this rank's block of rank r's
-        receive buffer [src][...block_shape].  Returns the local receive buffer, complete."""
-        g = self.world
-        if self.exchange == "p2p":
-            recv, hdl = self._symm_buf(name, g, *block_shape)
-            hdl.barrier(channel=0)              # peers have finished reading the previous contents
-            for r in range(g):
-                A = A_rows(r)
-                if A is None:
-                    continue
-                peer = hdl.get_buffer(r, (g, *block_shape), self.dtype)
-                self.gemm(A, Bmat, self._clip(peer[self.rank], A))
-            hdl.barrier(channel=1)              # every peer's stores have landed
-            return recv
-        send = self._buf(name + "_send", g, *block_shape)
-        for r in range(g):
-            A = A_rows(r)
-            if A is not None:
-                self.gemm(A, Bmat, self._clip(send[r], A))
-        if self.exchange == "none":
-            return send
-        recv = self._buf(name + "_recv", g, *block_shape)
-        dist.all_to_all_single(recv, send, group=self.group)
-        return recv
+    def _peer_ptrs(self, hdl, byte_offset):
+        return [int(hdl.buffer_ptrs[r]) + byte_offset for r in range(self.world)]
 
     @staticmethod
     def _clip(block, A):
@@ -161,13 +138,27 @@ class ShardedTransform:
         rest_shape = tuple(cur.shape[2:])
         rest = int(np.prod(rest_shape))
         cur2 = cur.reshape(s, self.n_pts[1], rest)
-
-        def rows_for(r):
-            lo, hi = r * Ps, min((r + 1) * Ps, self.P[1])
-            return self.wphiT[1][lo:hi] if hi > lo else None
-
-        # axis 1, written straight into the exchange layout [dest][x0][m1 in slice][rest]
-        recv = self._scatter_gemms("fwd", rows_for, cur2, (s, Ps, rest))      # [src][x0l][ml][rest]
+        # axis 1: G[x0][m1][rest] = (w phi_1)^T @ cur[x0], delivered as [src][x0l][m1 in slice][rest]
+        if self.exchange == "p2p":
+            from .plan import dgemm_scatter
+            recv, hdl = self._symm_buf("fwd", g, s, Ps, rest)
+            hdl.barrier(channel=0)               # every rank has finished reading its previous contents
+            blocks = self._peer_ptrs(hdl, self.rank * s * Ps * rest * 8)
+            A = self.wphiT[1]
+            dgemm_scatter(self.P[1], rest, self.n_pts[1], A, A.stride(0), cur2, rest, blocks, Ps, rest, batch=s,
+                          strideA=0, strideB=cur2.stride(0), strideC=Ps * rest)
+            hdl.barrier(channel=1)               # every peer's stores have landed
+        else:
+            send = self._buf("fwd_send", g, s, Ps, rest)
+            for r in range(g):
+                lo, hi = r * Ps, min((r + 1) * Ps, self.P[1])
+                if hi > lo:
+                    self.gemm(self.wphiT[1][lo:hi], cur2, send[r, :, :hi - lo])
+            if self.exchange == "none":
+                recv = send
+            else:
+                recv = self._buf("fwd_recv", g, s, Ps, rest)
+                dist.all_to_all_single(recv, send, group=self.group)
         cols = Ps * rest
         out = self._buf("fwd_out", self.P[0], cols)
         self.gemm(self.wphiT[0], recv.reshape(self.n_pts[0], cols), out)
@@ -199,15 +190,27 @@ class ShardedTransform:
         rest = int(np.prod(rest_shape))
         cols = Ps * rest
         c2 = c.reshape(self.P[0], cols)
-
-        def rows_for(r):                                                # grid rows x0 owned by rank r
-            return self.phi[0][r * s:(r + 1) * s]
-
-        # axis 0: X[x0][ml][rest] = phi_0 @ c, rows of destination r stored into its receive buffer
-        recv = self._scatter_gemms("bwd", rows_for, c2, (s, cols))       # [src][x0l][(ml, rest)]
-        # contract m1 = (src, ml): gather the slices of one x0l next to each other
-        Y = self._buf("bwd_Y", s, g * Ps, rest)
-        Y.copy_(recv.reshape(g, s, Ps, rest).permute(1, 0, 2, 3).reshape(s, g * Ps, rest))
+        # axis 0: X[x0][(ml, rest)] = phi_0 @ c; the rows of rank r's slab are delivered to rank r, next to
+        # the slices of the other ranks: Y[x0l][m1 = (src, ml)][rest]
+        if self.exchange == "p2p":
+            from .plan import dgemm_scatter
+            Y, hdl = self._symm_buf("bwd", s, g * Ps, rest)
+            hdl.barrier(channel=0)
+            blocks = self._peer_ptrs(hdl, self.rank * cols * 8)
+            A = self.phi[0]
+            dgemm_scatter(self.n_pts[0], cols, self.P[0], A, A.stride(0), c2, c2.stride(0), blocks, s, g * cols)
+            hdl.barrier(channel=1)
+        else:
+            send = self._buf("bwd_send", g, s, cols)
+            for r in range(g):
+                self.gemm(self.phi[0][r * s:(r + 1) * s], c2, send[r])
+            if self.exchange == "none":
+                recv = send
+            else:
+                recv = self._buf("bwd_recv", g, s, cols)
+                dist.all_to_all_single(recv, send, group=self.group)
+            Y = self._buf("bwd_Y", s, g * Ps, rest)
+            Y.copy_(recv.reshape(g, s, Ps, rest).permute(1, 0, 2, 3).reshape(s, g * Ps, rest))
         cur = self._buf("bwd_x1", s, self.n_pts[1], rest)
         self.gemm(self.phi[1], Y[:, :self.P[1]], cur)                    # [x0l][x1][rest]
         cur = cur.reshape(s, self.n_pts[1], *rest_shape)

@@ -21,6 +21,16 @@ def dgemm(M, N, K, A, lda, B, ldb, Cout, ldc, batch=1, strideA=0, strideB=0, str
                              strideC, _stream()))
 
 
+def dgemm_scatter(M, N, K, A, lda, B, ldb, blocks, block_rows, ldc, batch=1, strideA=0, strideB=0, strideC=0,
+                  a_mmajor=False):
+    """Like dgemm, but rows [i*block_rows, (i+1)*block_rows) of the result go to blocks[i] (device pointers or
+    tensors, possibly peer-GPU memory)."""
+    ptr = lambda t: t.data_ptr() if hasattr(t, "data_ptr") else int(t)
+    arr = (C.c_void_p * len(blocks))(*[ptr(b) for b in blocks])
+    check(lib().hb_dev_dgemm_scatter(M, N, K, batch, ptr(A), lda, strideA, int(a_mmajor), ptr(B), ldb, strideB, arr,
+                                     len(blocks), block_rows, ldc, strideC, _stream()))
+
+
 class Plan:
     def __init__(self, degree, nodes, weights, do_fourier=None, index_set="triangle"):
         nodes = [np.ascontiguousarray(n, dtype=np.float64).ravel() for n in nodes]

@@ -153,6 +153,12 @@ int hb_plan_timing_get(hb_plan* plan, int i, int* tag, double* ms, double* padde
 int hb_dev_dgemm(int M, int N, int K, int batch, const double* A, long long lda, long long strideA, int a_mmajor,
                  const double* B, long long ldb, long long strideB, double* C, long long ldc, long long strideC,
                  void* cuda_stream);
+/* same GEMM, but output rows [i*block_rows, (i+1)*block_rows) are stored at blocks[i] + (row % block_rows)*ldc
+ * (+ b*strideC + col).  The block pointers may be peer-GPU addresses mapped over NVLink, which turns the
+ * epilogue into the all-to-all of the sharded transform (hermipy_b200/dist.py). */
+int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long long lda, long long strideA,
+                         int a_mmajor, const double* B, long long ldb, long long strideB, double* const* blocks,
+                         int n_blocks, int block_rows, long long ldc, long long strideC, void* cuda_stream);
 int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
                   long long* ld);
 /* after hb_plan_varf(HB_VARF_REFERENCE): retained alpha count and path (0 = few-alpha assembly, 1 = dense GEMM) */
