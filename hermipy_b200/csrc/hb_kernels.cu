@@ -86,6 +86,39 @@ int launch_pair_table(const double* plain, long long ld_ik, const double* w, int
     return launch_status();
 }
 
+// Blocked pair tables for the two-stage dense varf (dim 2).  Pairs (i, j) of basis indices are laid out
+// in 8x8 blocks, p(i,j) = ((i>>3)*nb + (j>>3))*64 + (i&7)*8 + (j&7), nb = ceil(P/8), so that a 64-row GEMM
+// tile is exactly one block: skipping by symmetry (i <= j blocks only) and by total degree then works
+// at a granularity of 8 instead of the tile width.  Entries with i >= P or j >= P are zero.
+//   mode 0: out[x][p] = w_x * phi_i(x) * phi_j(x)      (Gram form; src = phi[x][k] with pitch ld, w may be null)
+//   mode 1: out[k][p] = T[k][i][j]                     (reference algebra; src = T with plane/pitch)
+__global__ void blocked_pair_table_kernel(int mode, const double* __restrict__ src, long long ld, long long plane,
+                                          const double* __restrict__ w, int P, int nb, double* __restrict__ out) {
+    const int x = blockIdx.y;
+    const long long np = (long long)nb * nb * 64;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    const int blk = (int)(p >> 6), bi = blk / nb, bj = blk - bi * nb;
+    const int i = 8 * bi + (int)((p >> 3) & 7), j = 8 * bj + (int)(p & 7);
+    double v = 0.0;
+    if (i < P && j < P) {
+        if (mode == 0) {
+            v = src[(long long)x * ld + i] * src[(long long)x * ld + j];
+            if (w) v = (w[x] == 0.0) ? 0.0 : v * w[x];
+        } else {
+            v = src[(long long)x * plane + (long long)i * ld + j];
+        }
+    }
+    out[(long long)x * np + p] = v;
+}
+
+int launch_blocked_pair_table(int mode, const double* src, long long ld, long long plane, const double* w, int rows,
+                              int P, int nb, double* out, cudaStream_t s) {
+    dim3 grid(cdiv((long long)nb * nb * 64, 256), rows);
+    blocked_pair_table_kernel<<<grid, 256, 0, s>>>(mode, src, ld, plane, w, P, nb, out);
+    return launch_status();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Exact Hermite triple products T[k][i][j] = <phi_i phi_j, phi_k>, k <= 2N, i,j <= N.
 // Reference: triple_products_1d, cpp/src/hermite/varf.cpp:49-94.  The recursion raises i at fixed j

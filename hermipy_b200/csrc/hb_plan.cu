@@ -375,30 +375,40 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
     return HB_OK;
 }
 
-// two-stage dense contraction for dim == 2 (see DESIGN.md "varf"):
-//   G[k0][(m1,n1)] = sum_{k1} coef[k0][k1] * R[k1][(m1,n1)]              (stage 1, A K-contiguous)
-//   A[idx(m0,m1)][idx(n0,n1)] = sum_{k0} L[k0][(m0,n0)] * G[k0][(m1,n1)]  (stage 2, A M-contiguous, scatter epilogue)
+// two-stage dense contraction for dim == 2 (see DESIGN.md "varf"), on blocked pair tables:
+//   G[k0][q] = sum_{k1} coef[k0][k1] * R[k1][q]                       (stage 1, A K-contiguous)
+//   A[idx(m0,m1)][idx(n0,n1)] = sum_{k0} L[k0][p] * G[k0][q]           (stage 2, A M-contiguous, scatter epilogue)
+// with p = blocked pair (m0,n0) of axis 0 and q = blocked pair (m1,n1) of axis 1.  When the whole matrix
+// is requested only the blocks with m0 <= n0 are computed and mirrored (A is symmetric, bit for bit:
+// the tables are symmetric in (i,j) and every dot product runs over k in the same order).
+static inline int blocks8(int P) { return (P + 7) / 8; }
+
 static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int K0, int K1, const double* Ltab,
-                         long long ldL, int Pp0, const double* Rtab, long long ldR, int Pp1, double* d_out,
-                         long long ldo, long long row_begin, long long row_end, cudaStream_t st) {
+                         const double* Rtab, double* d_out, long long ldo, long long row_begin, long long row_end,
+                         cudaStream_t st) {
     const int P0 = pl->ax[0].P, P1 = pl->ax[1].P;
-    const long long ncol = (long long)P1 * Pp1, nrow = (long long)P0 * Pp0;
+    const int nb0 = blocks8(P0), nb1 = blocks8(P1);
+    const long long nrow = (long long)nb0 * nb0 * 64, ncol = (long long)nb1 * nb1 * 64;
     HB_TRY(pl->G.ensure((size_t)K0 * ncol * 8));
     GemmArgs g1;
     g1.M = K0; g1.K = K1; g1.N = (int)ncol;
     g1.A = coef; g1.lda = ld_coef;
-    g1.B = Rtab; g1.ldb = ldR;
+    g1.B = Rtab; g1.ldb = ncol;
     g1.C = pl->G.d(); g1.ldc = ncol;
     HB_TRY(timed_gemm(pl, g1, 21, st));
     GemmArgs g2;
     g2.M = (int)nrow; g2.K = K0; g2.N = (int)ncol;
-    g2.A = Ltab; g2.lda = ldL; g2.a_mmajor = true;
+    g2.A = Ltab; g2.lda = nrow; g2.a_mmajor = true;
     g2.B = pl->G.d(); g2.ldb = ncol;
     g2.C = d_out; g2.ldc = ldo;
     g2.epi = EPI_VARF2D; g2.lut = pl->lut2d.i();
-    g2.P0 = P0; g2.Pp0 = Pp0; g2.P1 = P1; g2.Pp1 = Pp1;
-    g2.row_begin = (int)row_begin; g2.row_end = (int)row_end;
+    g2.P0 = P0; g2.Pp0 = nb0; g2.P1 = P1; g2.Pp1 = nb1;
+    const bool full = (row_begin == 0 && row_end == pl->n_polys);
+    g2.row_begin = (int)row_begin; g2.row_end = full ? 0x7fffffff : (int)row_end;
+    g2.symmetric = full ? 1 : 0;
     g2.tri_degree = (pl->set == SET_TRIANGLE) ? pl->degree : -1;
+    g2.lut_mode = (pl->set == SET_CUBE) ? 1 : (pl->set == SET_TRIANGLE ? 2 : 0);
+    g2.cfg = 2;   // 64 x 128 tiles, two CTAs per SM: one 8x8 row block per tile, epilogues overlap main loops
     return timed_gemm(pl, g2, 22, st);
 }
 
@@ -408,16 +418,13 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
         set_error("HB_VARF_GRAM supports dim <= 2 (got %d)", pl->dim);
         return HB_ERR_INVALID;
     }
-    for (int a = 0; a < pl->dim; a++) {
-        const Axis& A = pl->ax[a];
-        const size_t bytes = (size_t)A.n * A.P * A.Pp * 8;
-        if (pl->pair[a].bytes < bytes) {
-            HB_TRY(pl->pair[a].ensure(bytes));
-            HB_TRY(launch_pair_table(A.plain.d(), A.Pp, A.w.d(), A.n, A.P, A.Pp, pl->pair[a].d(), st));
-        }
-    }
     if (pl->dim == 1) {
         const Axis& A = pl->ax[0];
+        const size_t bytes = (size_t)A.n * A.P * A.Pp * 8;
+        if (pl->pair[0].bytes < bytes) {
+            HB_TRY(pl->pair[0].ensure(bytes));
+            HB_TRY(launch_pair_table(A.plain.d(), A.Pp, A.w.d(), A.n, A.P, A.Pp, pl->pair[0].d(), st));
+        }
         const long long ncol = (long long)A.P * A.Pp;
         HB_TRY(pl->tmp.ensure(ncol * 8));
         GemmArgs g;
@@ -425,16 +432,24 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
         g.A = d_f; g.lda = A.np;
         g.B = pl->pair[0].d(); g.ldb = ncol;
         g.C = pl->tmp.d(); g.ldc = ncol;
-        HB_TRY(gemm_launch(g, st));
+        HB_TRY(timed_gemm(pl, g, 21, st));
         const long long r0 = std::max(0LL, row_begin), r1 = std::min((long long)A.P, row_end);
         if (r1 > r0)
             HB_CUDA(cudaMemcpy2DAsync(d_out, ldo * 8, pl->tmp.d() + r0 * A.Pp, (size_t)A.Pp * 8, (size_t)A.P * 8,
                                       r1 - r0, cudaMemcpyDeviceToDevice, st));
         return HB_OK;
     }
+    for (int a = 0; a < 2; a++) {
+        if (pl->pairB_ok[a]) continue;
+        const Axis& A = pl->ax[a];
+        const int nb = blocks8(A.P);
+        HB_TRY(pl->pairB[a].ensure((size_t)A.n * nb * nb * 64 * 8));
+        HB_TRY(launch_blocked_pair_table(0, A.plain.d(), A.Pp, 0, A.w.d(), A.n, A.P, nb, pl->pairB[a].d(), st));
+        pl->pairB_ok[a] = true;
+    }
     const Axis &A0 = pl->ax[0], &A1 = pl->ax[1];
-    return varf_dense_2d(pl, d_f, A1.np, A0.n, A1.n, pl->pair[0].d(), (long long)A0.P * A0.Pp, A0.Pp,
-                         pl->pair[1].d(), (long long)A1.P * A1.Pp, A1.Pp, d_out, ldo, row_begin, row_end, st);
+    return varf_dense_2d(pl, d_f, A1.np, A0.n, A1.n, pl->pairB[0].d(), pl->pairB[1].d(), d_out, ldo, row_begin,
+                         row_end, st);
 }
 
 // The reference's algebra (varf.cpp:164-269).
@@ -489,10 +504,18 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
         HB_CUDA(cudaMemcpyAsync(pl->Hc.p, Hc.data(), Hc.size() * 8, cudaMemcpyHostToDevice, st));
         HB_CUDA(cudaStreamSynchronize(st));
         const long long plane = (long long)(N + 1) * pl->TPp;
-        const double* T0 = pl->ax[0].fourier ? pl->Tf.d() : pl->T.d();
-        const double* T1 = pl->ax[1].fourier ? pl->Tf.d() : pl->T.d();
-        return varf_dense_2d(pl, pl->Hc.d(), ldc, E0, E1, T0, plane, pl->TPp, T1, plane, pl->TPp, d_out, ldo,
-                             row_begin, row_end, st);
+        for (int a = 0; a < 2; a++) {
+            if (pl->TB_ok[a]) continue;
+            if (a == 1 && pl->ax[1].fourier == pl->ax[0].fourier && pl->ax[1].P == pl->ax[0].P) continue;  // shares TB[0]
+            const int nb = blocks8(pl->ax[a].P);
+            const double* T = pl->ax[a].fourier ? pl->Tf.d() : pl->T.d();
+            HB_TRY(pl->TB[a].ensure((size_t)(2 * N + 1) * nb * nb * 64 * 8));
+            HB_TRY(launch_blocked_pair_table(1, T, pl->TPp, plane, nullptr, 2 * N + 1, pl->ax[a].P, nb, pl->TB[a].d(), st));
+            pl->TB_ok[a] = true;
+        }
+        const double* T0 = pl->TB[0].d();
+        const double* T1 = pl->TB_ok[1] ? pl->TB[1].d() : pl->TB[0].d();
+        return varf_dense_2d(pl, pl->Hc.d(), ldc, E0, E1, T0, T1, d_out, ldo, row_begin, row_end, st);
     }
     HB_TRY(pl->kept_alpha.ensure(std::max<size_t>(kept_alpha.size(), 1) * 4));
     HB_TRY(pl->kept_val.ensure(std::max<size_t>(kept_val.size(), 1) * 8));
