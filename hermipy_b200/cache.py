@@ -1,0 +1,130 @@
+"""On-disk memoisation of numerical results (reference: hermipy/cache.py:30-167).
+
+File naming and content hashing follow the reference exactly, so an existing `.cache/` directory
+written by the reference stays valid:  <cachedir>/<function name>-<md5>.npy (dense array or scalar)
+or .npz (scipy CSR).  The md5 is built from the md5 of every positional argument and of every keyword
+name and value:
+
+    str            md5 of the utf-8 bytes                      (cache.py:40-42)
+    ndarray        md5 of the buffer                           (:47-48)
+    csr_matrix     digest of [data, indices, indptr, shape]    (:43-46)
+    sympy object   digest of str(obj)                          (:49-50)
+    list/tuple/frozenset   digest of 'list' + '-'.join(digests of the elements)   (:51-53)
+    dict           digest of ['k', *key digests, 'v', *value digests]             (:54-57)
+    int / float    digest of str(hash(x))                      (:58-59)
+    None           digest of ''                                (:60-61)
+
+Differences from the reference: when a cached file disagrees with a recomputed result (caching off,
+file present) the reference drops into pdb (cache.py:152-159); here a ValueError is raised unless
+`quiet`.  NumPy scalar arguments hash like the Python numbers they equal.
+"""
+import functools
+import hashlib
+import os
+
+import numpy as np
+import numpy.linalg as la
+import scipy.sparse as sparse
+import sympy as sym
+
+from .settings import settings
+
+
+def _md5(data):
+    return hashlib.md5(data).hexdigest()
+
+
+def gen_hash(extend=None):
+    def digest(obj):
+        if isinstance(obj, str):
+            return _md5(obj.encode('utf-8'))
+        if isinstance(obj, sparse.csr_matrix):
+            return digest([obj.data, obj.indices, obj.indptr, obj.shape])
+        if isinstance(obj, np.ndarray):
+            return _md5(np.ascontiguousarray(obj))
+        if isinstance(obj, sym.Basic):
+            return digest(str(obj))
+        if isinstance(obj, (list, tuple, frozenset)):
+            return digest('list' + '-'.join(digest(e) for e in obj))
+        if isinstance(obj, dict):
+            keys = ['k'] + [digest(k) for k in obj]
+            values = ['v'] + [digest(obj[k]) for k in obj]
+            return digest(keys + values)
+        if isinstance(obj, (np.integer, np.floating)):
+            obj = obj.item()
+        if isinstance(obj, (int, float)):
+            return digest(str(hash(obj)))
+        if obj is None:
+            return digest("")
+        if extend is None:
+            raise ValueError("Argument type not supported: " + str(type(obj)))
+        return digest(extend(obj))
+    return digest
+
+
+def gen_error(extend=None):
+    def distance(u, v):
+        if isinstance(u, (float, int, np.integer, np.floating)):
+            return abs(u - v)
+        if isinstance(u, np.ndarray):
+            return la.norm(np.ravel(u - v), 2)
+        if isinstance(u, sparse.csr_matrix):
+            if not isinstance(v, sparse.csr_matrix):
+                raise ValueError("Type mismatch")
+            return la.norm(u.data - v.data, 2)
+        if isinstance(u, tuple):
+            return sum(distance(a, b) for a, b in zip(u, v))
+        if extend is None:
+            raise ValueError("Invalid types: " + str(type(u)) + ", " + str(type(v)))
+        return extend(u, v)
+    return distance
+
+
+def _load_dense(filename):
+    value = np.load(filename)
+    return float(value) if value.shape == () else value
+
+
+# Use only for functions that do not depend on global library options!
+def cache(hash_extend=None, error_extend=None, quiet=False):
+    digest = gen_hash(extend=hash_extend)
+    distance = gen_error(extend=error_extend)
+
+    def decorate(function):
+        @functools.wraps(function)
+        def wrapper(*args, **kwargs):
+            use_cache = kwargs.pop('cache', settings['cache'])
+            stored = None
+            parts = [digest(a) for a in args]
+            for name, value in kwargs.items():
+                parts += [digest(name), digest(value)]
+            if settings['debug']:
+                print("Hash of arguments: " + function.__name__ + '-' + '-'.join(parts))
+            if not use_cache and not settings['cache'] and not os.path.isdir(settings['cachedir']):
+                return function(*args, **kwargs)       # nothing to read, nothing to write
+            os.makedirs(settings['cachedir'], exist_ok=True)
+            base = os.path.join(settings['cachedir'], function.__name__ + '-' + digest('-'.join(parts)))
+            for suffix, loader in (('.npy', _load_dense), ('.npz', sparse.load_npz)):
+                if os.path.isfile(base + suffix):
+                    try:
+                        stored = (loader(base + suffix), suffix == '.npz')
+                    except ValueError:
+                        stored = None
+                    break
+            if stored is not None and use_cache:
+                value = stored[0]
+                if isinstance(value, float) and value.is_integer():
+                    value = int(value)
+                return value
+            result = function(*args, **kwargs)
+            result_sparse = isinstance(result, sparse.csr_matrix)
+            if stored is not None:
+                ok = stored[1] is result_sparse and distance(result, stored[0]) < 1e-10
+                if not ok and not quiet:
+                    raise ValueError("Result does not correspond to cache (" + base + ")")
+                return result
+            if settings['cache']:
+                (sparse.save_npz if result_sparse else np.save)(base, result)
+            return result
+        return wrapper
+    return decorate

@@ -1,0 +1,50 @@
+"""Developer script: a short, fixed launch sequence for `ncu --set full` captures (run via gpurun).
+
+    python tools/profile_target.py c2        # 2 x (forward + inverse) C2 transform step, batch 17
+    python tools/profile_target.py varf      # C2 cube varf: polynomial f (banded assembly) + dense f (Gram GEMM)
+    python tools/profile_target.py c5        # one C5 forward+inverse over 8192 rows
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.special as sp
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hermipy_b200.plan import Plan  # noqa: E402
+
+
+def gh(n):
+    x, w = sp.roots_hermitenorm(n)
+    return x, w / np.sqrt(2 * np.pi)
+
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+if which == "c2":
+    x, w = gh(401)
+    pl = Plan(200, [x, x], [w, w], index_set="cube")
+    F = torch.randn(17, pl.grid_size, dtype=torch.float64, device="cuda")
+    C = pl.empty_coef(17)
+    G = pl.empty_grid(17)
+    for _ in range(2):
+        pl.forward(F, C)
+        pl.backward(C, G)
+elif which == "varf":
+    x, w = gh(401)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    V = X ** 4 / 4 - X ** 2 / 2 + Y ** 4 / 4 - Y ** 2 / 2 + X * Y / 2
+    pl = Plan(200, [x, x], [w, w], index_set=sys.argv[2] if len(sys.argv) > 2 else "cube")
+    out = torch.empty((pl.n_polys, pl.n_polys), dtype=torch.float64, device="cuda")
+    fV, fE = pl.pack_grid(V[None])[0], pl.pack_grid(np.exp(-3 * V / 10)[None])[0]
+    pl.varf(fV, "reference", out)
+    pl.varf(fE, "gram", out)
+elif which == "c5":
+    x, w = gh(2001)
+    keep = (w > 0) & (np.abs(x) <= 50)
+    pl = Plan(1000, [x[keep]], [w[keep]])
+    f = torch.randn(8192, pl.grid_size, dtype=torch.float64, device="cuda")
+    c = pl.forward(f)
+    pl.backward(c)
+torch.cuda.synchronize()
+print("done", which)
