@@ -95,13 +95,14 @@ def cache(hash_extend=None, error_extend=None, quiet=False):
         def wrapper(*args, **kwargs):
             use_cache = kwargs.pop('cache', settings['cache'])
             stored = None
+            if not use_cache and not settings['cache'] and not settings['debug'] \
+                    and not os.path.isdir(settings['cachedir']):
+                return function(*args, **kwargs)       # nothing to read, nothing to write: skip the hashing
             parts = [digest(a) for a in args]
             for name, value in kwargs.items():
                 parts += [digest(name), digest(value)]
             if settings['debug']:
                 print("Hash of arguments: " + function.__name__ + '-' + '-'.join(parts))
-            if not use_cache and not settings['cache'] and not os.path.isdir(settings['cachedir']):
-                return function(*args, **kwargs)       # nothing to read, nothing to write
             os.makedirs(settings['cachedir'], exist_ok=True)
             base = os.path.join(settings['cachedir'], function.__name__ + '-' + digest('-'.join(parts)))
             for suffix, loader in (('.npy', _load_dense), ('.npz', sparse.load_npz)):

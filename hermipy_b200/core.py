@@ -282,3 +282,19 @@ def inner(s1, s2, d1, d2, index_set="triangle"):
     check(lib().hb_inner(_dp(s1), len(s1), _dp(s2), len(s2), _ip(d1), len(d1), _ip(d2), len(d2),
                          index_set.encode(), _dp(out), n))
     return out
+
+
+# ---- decorators of the reference's wrappers (hermipy/core.py:125-348: @cache() @debug() @log_stats()) ----
+# Applied here, after the plain definitions, so that the undecorated functions stay reachable as
+# `<name>.__wrapped__`.  `cache=` becomes a keyword of every wrapped function (hermipy/cache.py:107-110).
+def _decorate():
+    from .cache import cache
+    from .stats import debug, log_stats
+    names = ("discretize", "integrate", "transform", "triple_products", "triple_products_fourier", "varf", "varfd",
+             "tensorize", "project", "inner", "iterator_get_degree", "iterator_index", "iterator_size",
+             "iterator_list_indices")
+    for name in names:
+        globals()[name] = cache()(debug()(log_stats()(globals()[name])))
+
+
+_decorate()

@@ -55,3 +55,23 @@ def hermegauss_nd(n_points):
         nodes.append(x)
         weights.append(w)
     return nodes, weights
+
+
+def cross_in_triangle(dim, degree):
+    """Positions, in the triangle enumeration, of the multi-indices of the cross set (hermipy/lib.py:36-38)."""
+    from . import core
+    return [core.iterator_index(m) for m in core.iterator_list_indices(dim, degree, index_set="cross")]
+
+
+def finest_common(set1, set2):
+    """Finest partition that both partitions (sets of frozensets of directions) refine (hermipy/lib.py:41-68):
+    the connected components of the 'shares a direction' relation over all blocks of both partitions."""
+    blocks = [frozenset(b) for b in list(set1) + list(set2) if b]   # the empty block (constant factor) is not a group
+    merged = []
+    for block in blocks:
+        touching = [m for m in merged if m & block]
+        for m in touching:
+            merged.remove(m)
+            block = block | m
+        merged.append(block)
+    return set(merged)
