@@ -206,6 +206,34 @@ int hb_hermite_eval(const double* x, int n, int degree, double* out) {
     return HB_OK;
 }
 
+// Copy-in / compute / copy-out pipeline of the host-pointer batch transform: the batch is cut into chunks, and
+// chunk i+1 is uploaded (H2D engine) while chunk i is transformed (SMs) and chunk i-1 is downloaded (D2H
+// engine).  Three non-blocking streams chained by events; chunks run in order on the compute stream, so the
+// plan's workspace is never used by two chunks at once.
+namespace hb {
+namespace {
+struct Pipeline {
+    static const int kMaxChunks = 8;
+    cudaStream_t in = nullptr, compute = nullptr, out = nullptr;
+    cudaEvent_t uploaded[kMaxChunks] = {nullptr}, computed[kMaxChunks] = {nullptr};
+    bool ok = false;
+    int init() {
+        if (ok) return HB_OK;
+        HB_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+        HB_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+        for (int i = 0; i < kMaxChunks; i++) {
+            HB_CUDA(cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming));
+            HB_CUDA(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+        }
+        ok = true;
+        return HB_OK;
+    }
+};
+Pipeline g_pipe;
+}  // namespace
+}  // namespace hb
+
 int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const double* f, const double* nodes,
                        const double* weights, const int* do_fourier, int forward, const char* index_set,
                        double* out, size_t out_len_each) {
@@ -213,28 +241,50 @@ int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const d
     HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
     if (batch < 1) return HB_OK;
     std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(g_pipe.init());
     const Axis& L = pl->ax[dim - 1];
     const long long n_grid = pl->grid_rows * L.n;
     const long long cstride = even_up(pl->n_polys);
-    if (forward) {
-        if (out_len_each != (size_t)pl->n_polys) { set_error("transform: out_len %zu != n_polys %lld", out_len_each, pl->n_polys); return HB_ERR_INVALID; }
-        HB_TRY(g_in.ensure((size_t)batch * pl->grid_size * 8));
-        HB_TRY(g_out.ensure((size_t)batch * cstride * 8));
-        HB_TRY(upload_grid(pl, f, batch, g_in.d()));
-        HB_TRY(plan_forward(pl, g_in.d(), pl->grid_size, batch, g_out.d(), cstride, 0));
-        HB_CUDA(cudaMemcpy2DAsync(out, (size_t)pl->n_polys * 8, g_out.p, (size_t)cstride * 8, (size_t)pl->n_polys * 8,
-                                  batch, cudaMemcpyDeviceToHost, 0));
-    } else {
-        if (out_len_each != (size_t)n_grid) { set_error("transform: out_len %zu != grid size %lld", out_len_each, n_grid); return HB_ERR_INVALID; }
-        HB_TRY(g_in.ensure((size_t)batch * cstride * 8));
-        HB_TRY(g_out.ensure((size_t)batch * pl->grid_size * 8));
-        HB_CUDA(cudaMemcpy2DAsync(g_in.p, (size_t)cstride * 8, f, (size_t)pl->n_polys * 8, (size_t)pl->n_polys * 8,
-                                  batch, cudaMemcpyHostToDevice, 0));
-        HB_TRY(plan_backward(pl, g_in.d(), cstride, batch, g_out.d(), pl->grid_size, 0));
-        HB_CUDA(cudaMemcpy2DAsync(out, (size_t)L.n * 8, g_out.p, (size_t)L.np * 8, (size_t)L.n * 8,
-                                  (size_t)pl->grid_rows * batch, cudaMemcpyDeviceToHost, 0));
+    const size_t expect = forward ? (size_t)pl->n_polys : (size_t)n_grid;
+    if (out_len_each != expect) {
+        set_error("transform: out_len %zu != %s %zu", out_len_each, forward ? "n_polys" : "grid size", expect);
+        return HB_ERR_INVALID;
     }
-    HB_CUDA(cudaStreamSynchronize(0));
+    const long long in_dev = forward ? pl->grid_size : cstride, out_dev = forward ? cstride : pl->grid_size;
+    HB_TRY(g_in.ensure((size_t)batch * in_dev * 8));
+    HB_TRY(g_out.ensure((size_t)batch * out_dev * 8));
+    // chunks of >= 2 MB of grid data, at most kMaxChunks
+    const double grid_mb = (double)pl->grid_size * 8e-6;
+    int n_chunks = (int)std::min<double>(Pipeline::kMaxChunks, std::max(1.0, batch * grid_mb / 2.0));
+    n_chunks = std::min(n_chunks, batch);
+    const int per = (batch + n_chunks - 1) / n_chunks;
+    for (int c = 0, b0 = 0; b0 < batch; c++, b0 += per) {
+        const int nb = std::min(per, batch - b0);
+        double* d_in = g_in.d() + (size_t)b0 * in_dev;
+        double* d_out = g_out.d() + (size_t)b0 * out_dev;
+        if (forward) {   // host rows of n doubles -> device rows padded to an even count (16-byte TMA rows)
+            HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)L.np * 8, f + (size_t)b0 * n_grid, (size_t)L.n * 8, (size_t)L.n * 8,
+                                      (size_t)pl->grid_rows * nb, cudaMemcpyHostToDevice, g_pipe.in));
+        } else {
+            HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)cstride * 8, f + (size_t)b0 * pl->n_polys, (size_t)pl->n_polys * 8,
+                                      (size_t)pl->n_polys * 8, nb, cudaMemcpyHostToDevice, g_pipe.in));
+        }
+        HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.uploaded[c], 0));
+        if (forward) HB_TRY(plan_forward(pl, d_in, pl->grid_size, nb, d_out, cstride, g_pipe.compute));
+        else HB_TRY(plan_backward(pl, d_in, cstride, nb, d_out, pl->grid_size, g_pipe.compute));
+        HB_CUDA(cudaEventRecord(g_pipe.computed[c], g_pipe.compute));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.computed[c], 0));
+        if (forward) {
+            HB_CUDA(cudaMemcpy2DAsync(out + (size_t)b0 * pl->n_polys, (size_t)pl->n_polys * 8, d_out, (size_t)cstride * 8,
+                                      (size_t)pl->n_polys * 8, nb, cudaMemcpyDeviceToHost, g_pipe.out));
+        } else {
+            HB_CUDA(cudaMemcpy2DAsync(out + (size_t)b0 * n_grid, (size_t)L.n * 8, d_out, (size_t)L.np * 8, (size_t)L.n * 8,
+                                      (size_t)pl->grid_rows * nb, cudaMemcpyDeviceToHost, g_pipe.out));
+        }
+    }
+    HB_CUDA(cudaStreamSynchronize(g_pipe.out));
+    HB_CUDA(cudaStreamSynchronize(g_pipe.compute));
     return HB_OK;
 }
 

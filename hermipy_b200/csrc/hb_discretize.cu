@@ -60,6 +60,35 @@ std::map<std::string, Compiled> g_cache;  // key: "<dim>|<body>"
 
 const char* kPrologue =
     "#define M_PI 3.14159265358979323846\n"
+    "#define M_E 2.71828182845904523536\n"
+    "#define M_LOG2E 1.44269504088896340736\n"
+    "#define M_LOG10E 0.434294481903251827651\n"
+    "#define M_LN2 0.693147180559945309417\n"
+    "#define M_LN10 2.30258509299404568402\n"
+    "#define M_PI_2 1.57079632679489661923\n"
+    "#define M_PI_4 0.785398163397448309616\n"
+    "#define M_1_PI 0.318309886183790671538\n"
+    "#define M_2_PI 0.636619772367581343076\n"
+    "#define M_2_SQRTPI 1.12837916709551257390\n"
+    "#define M_SQRT2 1.41421356237309504880\n"
+    "#define M_SQRT1_2 0.707106781186547524401\n"
+    // sympy.ccode writes integer literals as function arguments (sqrt(3), pow(2, v[0])); with <cmath> the host
+    // compiler of the reference promotes them to double, NVRTC's built-in overload set is ambiguous instead
+    "#define HB_PROMOTE1(f) __device__ inline double f(int x) { return f((double)x); } "
+    "__device__ inline double f(long long x) { return f((double)x); }\n"
+    "HB_PROMOTE1(sqrt) HB_PROMOTE1(cbrt) HB_PROMOTE1(exp) HB_PROMOTE1(exp2) HB_PROMOTE1(expm1) HB_PROMOTE1(log) "
+    "HB_PROMOTE1(log2) HB_PROMOTE1(log10) HB_PROMOTE1(log1p) HB_PROMOTE1(sin) HB_PROMOTE1(cos) HB_PROMOTE1(tan) "
+    "HB_PROMOTE1(asin) HB_PROMOTE1(acos) HB_PROMOTE1(atan) HB_PROMOTE1(sinh) HB_PROMOTE1(cosh) HB_PROMOTE1(tanh) "
+    "HB_PROMOTE1(asinh) HB_PROMOTE1(acosh) HB_PROMOTE1(atanh) HB_PROMOTE1(erf) HB_PROMOTE1(erfc) "
+    "HB_PROMOTE1(tgamma) HB_PROMOTE1(lgamma) HB_PROMOTE1(fabs) HB_PROMOTE1(floor) HB_PROMOTE1(ceil)\n"
+    "__device__ inline double pow(int a, int b) { return pow((double)a, b); }\n"
+    "__device__ inline double pow(int a, double b) { return pow((double)a, b); }\n"
+    "__device__ inline double atan2(int a, double b) { return atan2((double)a, b); }\n"
+    "__device__ inline double atan2(double a, int b) { return atan2(a, (double)b); }\n"
+    "__device__ inline double fmax(int a, double b) { return fmax((double)a, b); }\n"
+    "__device__ inline double fmax(double a, int b) { return fmax(a, (double)b); }\n"
+    "__device__ inline double fmin(int a, double b) { return fmin((double)a, b); }\n"
+    "__device__ inline double fmin(double a, int b) { return fmin(a, (double)b); }\n"
     "struct HbGrid { int dim; int n[8]; long long pitch_last; long long total; double t[8]; double d[64]; };\n"
     "extern \"C\" __global__ void hb_discretize_kernel(const double* __restrict__ nodes, HbGrid g, double* out) {\n"
     "    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n"

@@ -1,9 +1,7 @@
 // Host launcher for the DMMA/TMA GEMM: builds the TMA tensor maps (cuTensorMapEncodeTiled obtained
 // through cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda) and picks
 // a tile configuration.
-#include "hb_gemm.cuh"
-#include "hb_internal.h"
-#include "hb_plan.h"
+#include "hb_gemm_launch.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -31,7 +29,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // rank-3 FP64 map: dims {d0 (contiguous), d1 (pitch ld elements), d2 (batch, stride elements)}
-static int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2,
+int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2,
                     uint64_t ld, uint64_t stride, uint32_t b0, uint32_t b1) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return HB_ERR_CUDA;
@@ -51,48 +49,13 @@ static int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1
     return HB_OK;
 }
 
-template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB>
-static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {
-    CUtensorMap tmA, tmB;
-    // A batch stride of 0 means "shared operand": the map gets a batch extent of 1 and the kernel
-    // multiplies the batch coordinate by a_bmul/b_bmul = 0.
-    const bool a_batched = a.batch > 1 && a.strideA != 0, b_batched = a.batch > 1 && a.strideB != 0;
-    const uint64_t strideA = a_batched ? (uint64_t)a.strideA : (uint64_t)a.lda * (AM ? a.K : a.M);
-    const uint64_t strideB = b_batched ? (uint64_t)a.strideB : (uint64_t)a.ldb * a.K;
-    int rc;
-    if (AM)
-        rc = make_map(&tmA, a.A, a.M, a.K, a_batched ? a.batch : 1, a.lda, strideA, 16, GEMM_BK);
-    else
-        rc = make_map(&tmA, a.A, a.K, a.M, a_batched ? a.batch : 1, a.lda, strideA, GEMM_BK, BM);
-    if (rc) return rc;
-    rc = make_map(&tmB, a.B, a.N, a.K, b_batched ? a.batch : 1, a.ldb, strideB, 16, GEMM_BK);
-    if (rc) return rc;
-    GemmParams p = p_in;
-    p.tiles_m = (a.M + BM - 1) / BM;
-    p.tiles_n = (a.N + BN - 1) / BN;
-    p.a_bmul = a_batched ? 1 : 0;
-    p.b_bmul = b_batched ? 1 : 0;
-    const long long n_cta = (long long)p.tiles_m * p.tiles_n * a.batch;
-    if (n_cta > 0x7fffffffLL) return HB_ERR_INVALID;
-    auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM, MINB>;
-    constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return HB_ERR_CUDA;
-        attr_set = true;
-    }
-    kern<<<(unsigned)n_cta, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
-    return launch_status();
-}
-
 // Tile configurations: {BM, BN, resident CTAs per SM}.  The launcher picks the one with the smallest
 // modelled time: small or oddly shaped problems (P = 201, n = 401, batch 17 ...) otherwise lose most of
 // their time to tile quantisation and partial waves over the 148 SMs.
 struct TileCfg { int bm, bn, ctas; };
+static const int kNumCfgs = 8;
 static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2},
                                 {48, 208, 1},  {96, 128, 1}, {32, 128, 2}};
-static const int kNumCfgs = 8;
 
 static int pick_cfg(const GemmArgs& a) {
     const double sms = 148.0;
@@ -110,8 +73,10 @@ static int pick_cfg(const GemmArgs& a) {
         const long long full = tiles / slots, rem = tiles % slots;
         double t = full * (c.ctas * tile_t + (c.ctas > 1 ? 0.3 : 1.0) * fixed);
         if (rem) t += std::ceil((double)rem / sms) * tile_t + fixed;
-        // small tiles re-read their operands more often (shared-memory and L2 traffic per flop)
-        t *= 1.0 + 6.0 / c.bm + 6.0 / c.bn;
+        // steady-state DMMA rate of each configuration relative to the best one, measured on large problems
+        // (tools/cfg_sweep.py on B200: C5 forward GEMM and the C2 varf stage-2 shape)
+        static const double kEff[kNumCfgs] = {0.96, 1.00, 0.94, 0.94, 0.93, 0.82, 0.99, 0.95};
+        t /= kEff[i];
         if (t < best) { best = t; best_i = i; }
     }
     return best_i;
@@ -141,29 +106,15 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         else if (env && env[0]) cfg = atoi(env);
     }
     if (cfg < 0 || cfg >= kNumCfgs) cfg = pick_cfg(a);
-    if (a.a_mmajor) {
-        switch (cfg) {
-            case 0: return launch_cfg<128, 128, 4, 2, 4, true, 1>(a, p, stream);
-            case 1: return launch_cfg<64, 64, 2, 2, 6, true, 2>(a, p, stream);
-            case 2: return launch_cfg<64, 128, 2, 2, 4, true, 2>(a, p, stream);
-            case 3: return launch_cfg<64, 208, 4, 2, 4, true, 1>(a, p, stream);
-            case 4: return launch_cfg<32, 208, 2, 2, 3, true, 2>(a, p, stream);
-            case 5: return launch_cfg<48, 208, 3, 2, 4, true, 1>(a, p, stream);
-            case 6: return launch_cfg<96, 128, 3, 2, 4, true, 1>(a, p, stream);
-            default: return launch_cfg<32, 128, 2, 2, 4, true, 2>(a, p, stream);
-        }
-    } else {
-        switch (cfg) {
-            case 0: return launch_cfg<128, 128, 4, 2, 4, false, 1>(a, p, stream);
-            case 1: return launch_cfg<64, 64, 2, 2, 6, false, 2>(a, p, stream);
-            case 2: return launch_cfg<64, 128, 2, 2, 4, false, 2>(a, p, stream);
-            case 3: return launch_cfg<64, 208, 4, 2, 4, false, 1>(a, p, stream);
-            case 4: return launch_cfg<32, 208, 2, 2, 3, false, 2>(a, p, stream);
-            case 5: return launch_cfg<48, 208, 3, 2, 4, false, 1>(a, p, stream);
-            case 6: return launch_cfg<96, 128, 3, 2, 4, false, 1>(a, p, stream);
-            default: return launch_cfg<32, 128, 2, 2, 4, false, 2>(a, p, stream);
-        }
+    if (a.epi == EPI_VARF2D) {
+        if (!a.a_mmajor) { set_error("gemm: the varf epilogue needs an M-contiguous A operand"); return HB_ERR_INVALID; }
+        return gemm_dispatch_varf_m(2, a, p, stream);
     }
+    if (a.epi == EPI_LUT) {
+        if (a.a_mmajor) { set_error("gemm: the look-up-table epilogue needs a K-contiguous A operand"); return HB_ERR_INVALID; }
+        return gemm_dispatch_lut_k(cfg, a, p, stream);
+    }
+    return a.a_mmajor ? gemm_dispatch_store_m(cfg, a, p, stream) : gemm_dispatch_store_k(cfg, a, p, stream);
 }
 
 }  // namespace hb

@@ -47,7 +47,8 @@ struct GemmParams {
     int row_begin, row_end;  // EPI_VARF2D: owned output rows [row_begin,row_end) (row sharding)
     int tri_degree;     // EPI_VARF2D: >=0 -> skip tiles with m0+m1 > tri_degree (triangle-like sets)
     double alpha;       // result scale
-    int tiles_m, tiles_n;    // grid is linear: blockIdx.x = (b*tiles_m + tile_m)*tiles_n + tile_n
+    int tiles_m, tiles_n;    // grid is linear: blockIdx.x = b*tiles_m*tiles_n + (grouped tile order, see the kernel)
+    int group_m;             // tile rows per rasterisation group (>= 1)
     int a_bmul, b_bmul;      // 0: operand shared by all batch entries, 1: batched
     // EPI_STORE with row blocks: output row r goes to blocks[r / block_rows] + (r % block_rows)*ldc.
     // The block pointers may be peer-GPU addresses (NVLink P2P): this is how a GEMM's epilogue performs
@@ -75,7 +76,7 @@ constexpr int gemm_smem_bytes() {
     return STAGES * (BM + BN) * GEMM_BK * 8 + 1024 /*alignment slack*/ + 2 * STAGES * 8;
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool A_MMAJOR, int MIN_CTAS>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool A_MMAJOR, int MIN_CTAS, int EPI>
 __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
     dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -91,13 +92,22 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES]
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    const int tile_n = blockIdx.x % p.tiles_n;
-    const int tile_m = (blockIdx.x / p.tiles_n) % p.tiles_m;
-    const int b = blockIdx.x / (p.tiles_n * p.tiles_m);
+    // Tile order inside one batch entry: groups of `group_m` tile rows, tile row fastest inside a group, so
+    // that the CTAs resident at the same time share a few A row-tiles and a few B column-tiles in L2
+    // (group_m = 1 is the plain row-major order).
+    const int per_batch = p.tiles_n * p.tiles_m;
+    const int b = blockIdx.x / per_batch;
+    const int t_in = blockIdx.x - b * per_batch;
+    const int per_group = p.group_m * p.tiles_n;
+    const int first_m = (t_in / per_group) * p.group_m;
+    const int g_rows = min(p.group_m, p.tiles_m - first_m);
+    const int t_grp = t_in - (t_in / per_group) * per_group;
+    const int tile_m = first_m + t_grp % g_rows;
+    const int tile_n = t_grp / g_rows;
     const int m_base = tile_m * BM, n_base = tile_n * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (p.epi == EPI_VARF2D) {
+    if constexpr (EPI == EPI_VARF2D) {
         // Tile-level skipping.  GEMM row = blocked pair (m0, n0), column = blocked pair (m1, n1); the entry
         // lands at output row lut[m0,m1], column lut[n0,n1].  A tile is a few 8x8 blocks on each side:
         // it is needed if some (row block, column block) combination is.
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
 
     // ---------------- epilogue ----------------
     if constexpr (BM == 64 && BN == 128 && A_MMAJOR) {
-        if (p.epi == EPI_VARF2D) {
+        if constexpr (EPI == EPI_VARF2D) {
             // Coalesced scatter through shared memory.  The tile is one 8x8 block of (m0,n0) pairs by two
             // 8x8 blocks of (m1,n1) pairs.  Output runs are contiguous along n1 or n0 (direct entry
             // A[idx(m0,m1)][idx(n0,n1)]) and along m1 or m0 (mirrored entry), never along a register
@@ -292,6 +302,36 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
             return;
         }
     }
+    if constexpr (EPI == EPI_LUT) {
+        // Scatter through the look-up table (last stage of a d-dim forward transform).  The table entries
+        // of one accumulator row are fetched first (independent loads in flight together), then stored.
+        double* out = p.C + (long long)b * p.strideC;
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++) {
+            const int im = wm * MI + mi;
+            const int row = m_base + (A_MMAJOR ? (16 * (im >> 1) + 4 * (im & 1) + cm) : (wm * WM + 8 * mi + rm));
+            if (row >= p.M) continue;
+            const int* __restrict__ lrow = p.lut + (long long)row * p.N;
+            int2 idx[NJ];
+#pragma unroll
+            for (int nj = 0; nj < NJ; nj++) {
+                const int jn = wn * NJ + nj;
+                const int col = n_base + 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
+                idx[nj] = make_int2(-1, -1);
+                if (col + 1 < p.N && (p.N & 1) == 0) idx[nj] = __ldg(reinterpret_cast<const int2*>(lrow + col));
+                else {
+                    if (col < p.N) idx[nj].x = __ldg(lrow + col);
+                    if (col + 1 < p.N) idx[nj].y = __ldg(lrow + col + 1);
+                }
+            }
+#pragma unroll
+            for (int nj = 0; nj < NJ; nj++) {
+                if (idx[nj].x >= 0) out[idx[nj].x] = acc[mi][nj][0] * p.alpha;
+                if (idx[nj].y >= 0) out[idx[nj].y] = acc[mi][nj][1] * p.alpha;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int mi = 0; mi < MI; mi++) {
         const int im = wm * MI + mi;
@@ -304,7 +344,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
             if (col >= p.N) continue;
             const double v0 = acc[mi][nj][0] * p.alpha, v1 = acc[mi][nj][1] * p.alpha;
             const bool has1 = (col + 1 < p.N);
-            if (p.epi == EPI_STORE) {
+            if constexpr (EPI == EPI_STORE) {
                 double* dst = (p.block_rows ? p.blocks[row / p.block_rows] + (long long)(row % p.block_rows) * p.ldc
                                             : p.C + (long long)row * p.ldc) + (long long)b * p.strideC + col;
                 if (has1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -313,16 +353,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
                     dst[0] = v0;
                     if (has1) dst[1] = v1;
                 }
-            } else if (p.epi == EPI_LUT) {
-                double* out = p.C + (long long)b * p.strideC;
-                const long long li = (long long)row * p.N + col;
-                const int i0 = p.lut[li];
-                if (i0 >= 0) out[i0] = v0;
-                if (has1) {
-                    const int i1 = p.lut[li + 1];
-                    if (i1 >= 0) out[i1] = v1;
-                }
-            } else {  // EPI_VARF2D
+            } else if constexpr (EPI == EPI_VARF2D) {
                 const int rb = row >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
                 const int m0 = 8 * bm0 + ((row >> 3) & 7), n0 = 8 * bn0 + (row & 7);
                 if (m0 >= p.P0 || n0 >= p.P0 || (p.symmetric && m0 > n0)) continue;

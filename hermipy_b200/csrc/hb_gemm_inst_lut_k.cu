@@ -1,0 +1,11 @@
+// Instantiations of the DMMA/TMA GEMM kernel: epilogue EPI_LUT, A operand K-contiguous ([M][K]).
+#include "hb_gemm_launch.cuh"
+
+namespace hb {
+int gemm_dispatch_lut_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
+    switch (cfg) {
+        HB_GEMM_CONFIGS(HB_GEMM_CASE, false, EPI_LUT)
+        default: return HB_ERR_INVALID;
+    }
+}
+}  // namespace hb

@@ -1,0 +1,72 @@
+// Host-side launch template of the DMMA/TMA GEMM, shared by the translation units that instantiate the
+// kernel (hb_gemm_inst_*.cu: one per (epilogue, A layout) so that they compile in parallel).
+#pragma once
+#include "hb_gemm.cuh"
+#include "hb_internal.h"
+#include "hb_plan.h"
+
+namespace hb {
+
+// rank-3 FP64 tensor map: dims {d0 (contiguous), d1 (pitch ld elements), d2 (batch, stride elements)}
+int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld, uint64_t stride,
+             uint32_t b0, uint32_t b1);
+
+// Tile configurations {BM, BN, warps along M, warps along N, pipeline stages, resident CTAs per SM}.  The number
+// of consumer warps is a multiple of 4 everywhere: FP64 DMMA issues at one instruction per 16 clocks per SM
+// sub-partition, so 6 consumer warps (2+2+1+1 over the four sub-partitions) cap the tile at 75 % of the rate.
+#define HB_GEMM_CONFIGS(X, AM, EPI)   \
+    X(0, 128, 128, 4, 2, 4, AM, 1, EPI) \
+    X(1, 64, 64, 2, 2, 6, AM, 2, EPI)   \
+    X(2, 64, 128, 2, 2, 4, AM, 2, EPI)  \
+    X(3, 64, 208, 4, 2, 4, AM, 1, EPI)  \
+    X(4, 32, 208, 2, 2, 3, AM, 2, EPI)  \
+    X(5, 48, 208, 2, 2, 4, AM, 1, EPI)  \
+    X(6, 96, 128, 4, 2, 4, AM, 1, EPI)  \
+    X(7, 32, 128, 2, 2, 4, AM, 2, EPI)
+
+template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB, int EPI>
+static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    // A batch stride of 0 means "shared operand": the map gets a batch extent of 1 and the kernel
+    // multiplies the batch coordinate by a_bmul/b_bmul = 0.
+    const bool a_batched = a.batch > 1 && a.strideA != 0, b_batched = a.batch > 1 && a.strideB != 0;
+    const uint64_t strideA = a_batched ? (uint64_t)a.strideA : (uint64_t)a.lda * (AM ? a.K : a.M);
+    const uint64_t strideB = b_batched ? (uint64_t)a.strideB : (uint64_t)a.ldb * a.K;
+    int rc;
+    if (AM)
+        rc = make_map(&tmA, a.A, a.M, a.K, a_batched ? a.batch : 1, a.lda, strideA, 16, GEMM_BK);
+    else
+        rc = make_map(&tmA, a.A, a.K, a.M, a_batched ? a.batch : 1, a.lda, strideA, GEMM_BK, BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, a.B, a.N, a.K, b_batched ? a.batch : 1, a.ldb, strideB, 16, GEMM_BK);
+    if (rc) return rc;
+    GemmParams p = p_in;
+    p.tiles_m = (a.M + BM - 1) / BM;
+    p.tiles_n = (a.N + BN - 1) / BN;
+    p.group_m = a.group_m > 0 ? a.group_m : 1;
+    p.a_bmul = a_batched ? 1 : 0;
+    p.b_bmul = b_batched ? 1 : 0;
+    const long long n_cta = (long long)p.tiles_m * p.tiles_n * a.batch;
+    if (n_cta > 0x7fffffffLL) return HB_ERR_INVALID;
+    auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM, MINB, EPI>;
+    constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return HB_ERR_CUDA;
+        attr_set = true;
+    }
+    kern<<<(unsigned)n_cta, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
+    return launch_status();
+}
+
+#define HB_GEMM_CASE(ID, BM, BN, WM, WN, ST, AM, MINB, EPI) \
+    case ID: return launch_cfg<BM, BN, WM, WN, ST, AM, MINB, EPI>(a, p, stream);
+
+// one dispatcher per (epilogue, A layout); each lives in its own translation unit
+int gemm_dispatch_store_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);  // A K-contiguous
+int gemm_dispatch_store_m(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);  // A M-contiguous
+int gemm_dispatch_lut_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);
+int gemm_dispatch_varf_m(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);   // cfg 2 only
+
+}  // namespace hb

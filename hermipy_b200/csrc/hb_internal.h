@@ -23,6 +23,7 @@ struct GemmArgs {
     double alpha = 1.0;
     int block_rows = 0;              // EPI_STORE: rows [i*block_rows, (i+1)*block_rows) -> blocks[i] (C unused)
     double* blocks[16] = {nullptr};
+    int group_m = 1;                 // tile rows per rasterisation group (L2 locality of big GEMMs)
     int cfg = -1;  // -1 auto (cost model), else index into the tile-configuration table of hb_gemm.cu
 };
 

@@ -25,6 +25,16 @@ def quad_gh(hm, n_points, **kwargs):
     return hm.Quad([r[0] for r in rules], [r[1] for r in rules], **kwargs)
 
 
+def wl2(quad, values):
+    """Grid values times sqrt(quadrature weight): the inverse transform evaluates He_k/sqrt(k!) un-weighted, which
+    reaches 1e45 and beyond at the outer nodes where the coefficients' rounding noise is amplified alike (for the
+    reference as much as for any other implementation), so evaluations are compared in the discrete L2(w) sense."""
+    w = np.ones(1)
+    for wi in quad.weights:
+        w = np.multiply.outer(w, np.asarray(wi)).ravel()
+    return np.asarray(values) * np.sqrt(w)
+
+
 def dense(m):
     return np.asarray(m.todense()) if hasattr(m, "todense") else np.asarray(m)
 
@@ -44,16 +54,16 @@ def case_fokker_planck_1d(hm, out):
         out["fp1d/%s/factor_grid" % name] = quad.discretize(factor)
     series = quad.transform('exp(-x*x/8)*cos(3*x)', degree)
     out["fp1d/transform"] = series.coeffs
-    out["fp1d/eval"] = quad.eval(series)
+    out["fp1d/eval"] = wl2(quad, quad.eval(series))
     out["fp1d/varf_x4"] = dense(quad.varf('x**4/4 - x**2/2', degree).matrix)
     out["fp1d/integrate_flat"] = np.array([quad.integrate(sym.exp(-beta * (x ** 4 / 4 - x ** 2 / 2)), flat=True)])
     # a quadrature with a weight factor: transform divides by it, eval multiplies by it
     quad_w = quad_gh(hm, [120], mean=[.3], cov=[[.7]], factor=sym.exp(-x * x / 5))
     s = quad_w.transform('exp(-x*x/3)*(1 + x)', 40)
     out["fp1d/weighted_transform"] = s.coeffs
-    out["fp1d/weighted_eval"] = quad_w.eval(s)
+    out["fp1d/weighted_eval"] = wl2(quad_w, quad_w.eval(s))
     other = quad_gh(hm, [90], mean=[-1.], cov=[[.1]])
-    out["fp1d/eval_other_grid"] = other.eval(quad_gh(hm, [100], mean=[2.], cov=[[2.]]).transform('x', 50))
+    out["fp1d/eval_other_grid"] = wl2(other, other.eval(quad_gh(hm, [100], mean=[2.], cov=[[2.]]).transform('x', 50)))
 
 
 def case_2d(hm, out):
@@ -68,7 +78,7 @@ def case_2d(hm, out):
         degree = 12
         s = quad.transform(bump, degree, index_set=index_set)
         out["2d/%s/transform" % index_set] = s.coeffs
-        out["2d/%s/eval" % index_set] = quad.eval(s)
+        out["2d/%s/eval" % index_set] = wl2(quad, quad.eval(s))
         out["2d/%s/varf_poly" % index_set] = dense(quad.varf(poly, degree, index_set=index_set).matrix)
     for tensorize in (False, True):
         tag = "tensorized" if tensorize else "direct"
@@ -135,7 +145,7 @@ def case_fourier(hm, out):
     q = hm.Quad.fourier(32, dirs=[0]) * quad_gh(hm, [32], dirs=[1])     # the reference needs equal point counts
     s = q.transform('cos(x)*y + sin(2*x) + 1', 8, index_set="cube", tensorize=False)
     out["fourier/transform"] = s.coeffs
-    out["fourier/eval"] = q.eval(s)
+    out["fourier/eval"] = wl2(q, q.eval(s))
     out["fourier/varf"] = dense(q.varf('cos(x) + y*y', 6, index_set="cube", tensorize=False).matrix)
     out["fourier/varfd"] = dense(q.varfd('1 + y', 6, [0, 1], index_set="cube", tensorize=False).matrix)
     out["fourier/integrate"] = np.array([q.integrate('cos(x)**2 * y*y', tensorize=False)])
