@@ -235,7 +235,7 @@ def workload_config(args, world):
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
-    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+    os.environ.pop("NCCL_DEBUG", None)   # NCCL prints its version banner on stdout at WARN/INFO: stdout is the JSON line only
     import torch
     import torch.distributed as dist
     from hermipy_b200 import core, _lib

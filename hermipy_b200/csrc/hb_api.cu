@@ -99,7 +99,7 @@ int cached_plan(hb_plan** out, int dim, const int* n_pts, int degree, const doub
 
 // staging buffers shared by the host-pointer entry points (one call at a time per process)
 std::mutex g_call_mutex;
-DevBuf g_in, g_out, g_aux[HB_MAX_FACTORS], g_auxi[HB_MAX_FACTORS];
+DevBuf g_in, g_out, g_stage, g_aux[HB_MAX_FACTORS], g_auxi[HB_MAX_FACTORS];
 
 // last sparse result
 DevBuf g_sp_indptr, g_sp_indices, g_sp_data, g_sp_rownnz;
@@ -107,9 +107,17 @@ long long g_sp_rows = 0, g_sp_nnz = 0;
 std::vector<long long> g_sp_indptr_host;
 
 int upload_grid(const hb_plan* pl, const double* f, int batch, double* dst) {
+    // flat host->device copy, then re-pitch on the device (a pitched H2D copy of short rows is 2.4x slower)
     const Axis& L = pl->ax[pl->dim - 1];
-    HB_CUDA(cudaMemcpy2DAsync(dst, (size_t)L.np * 8, f, (size_t)L.n * 8, (size_t)L.n * 8,
-                              (size_t)pl->grid_rows * batch, cudaMemcpyHostToDevice, 0));
+    const size_t n_grid = (size_t)pl->grid_rows * L.n * batch;
+    if (L.np == L.n) {
+        HB_CUDA(cudaMemcpyAsync(dst, f, n_grid * 8, cudaMemcpyHostToDevice, 0));
+        return HB_OK;
+    }
+    HB_TRY(g_stage.ensure(n_grid * 8));
+    HB_CUDA(cudaMemcpyAsync(g_stage.p, f, n_grid * 8, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpy2DAsync(dst, (size_t)L.np * 8, g_stage.p, (size_t)L.n * 8, (size_t)L.n * 8,
+                              (size_t)pl->grid_rows * batch, cudaMemcpyDeviceToDevice, 0));
     return HB_OK;
 }
 
@@ -253,6 +261,7 @@ int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const d
     const long long in_dev = forward ? pl->grid_size : cstride, out_dev = forward ? cstride : pl->grid_size;
     HB_TRY(g_in.ensure((size_t)batch * in_dev * 8));
     HB_TRY(g_out.ensure((size_t)batch * out_dev * 8));
+    if (forward && L.np != L.n) HB_TRY(g_stage.ensure((size_t)batch * n_grid * 8));
     // chunks of >= 2 MB of grid data, at most kMaxChunks
     const double grid_mb = (double)pl->grid_size * 8e-6;
     int n_chunks = (int)std::min<double>(Pipeline::kMaxChunks, std::max(1.0, batch * grid_mb / 2.0));
@@ -262,9 +271,18 @@ int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const d
         const int nb = std::min(per, batch - b0);
         double* d_in = g_in.d() + (size_t)b0 * in_dev;
         double* d_out = g_out.d() + (size_t)b0 * out_dev;
-        if (forward) {   // host rows of n doubles -> device rows padded to an even count (16-byte TMA rows)
-            HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)L.np * 8, f + (size_t)b0 * n_grid, (size_t)L.n * 8, (size_t)L.n * 8,
-                                      (size_t)pl->grid_rows * nb, cudaMemcpyHostToDevice, g_pipe.in));
+        if (forward && L.np == L.n) {
+            HB_CUDA(cudaMemcpyAsync(d_in, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8, cudaMemcpyHostToDevice, g_pipe.in));
+        } else if (forward) {
+            // host rows of n doubles -> device rows padded to an even count (16-byte TMA rows).  A pitched
+            // host->device copy runs at 23 GB/s on this PCIe 5 x16 link against 55 GB/s for a flat one
+            // (tools/pcie_probe.cu), so the rows cross the bus contiguously and are re-pitched on the device.
+            double* d_flat = g_stage.d() + (size_t)b0 * n_grid;
+            HB_CUDA(cudaMemcpyAsync(d_flat, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8, cudaMemcpyHostToDevice, g_pipe.in));
+            HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
+            HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.uploaded[c], 0));
+            HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)L.np * 8, d_flat, (size_t)L.n * 8, (size_t)L.n * 8,
+                                      (size_t)pl->grid_rows * nb, cudaMemcpyDeviceToDevice, g_pipe.compute));
         } else {
             HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)cstride * 8, f + (size_t)b0 * pl->n_polys, (size_t)pl->n_polys * 8,
                                       (size_t)pl->n_polys * 8, nb, cudaMemcpyHostToDevice, g_pipe.in));
