@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 C2 = dict(n=401, degree=200, batch=17, index_set="cube")
 C5 = dict(n_rule=2001, degree=1000, batch=65536)
 C4 = dict(n=256, degree=255)
+C3 = dict(n_rule=801, degree=400)
 
 
 def gauss_hermite(n):
@@ -422,6 +423,9 @@ def run_ours(args):
     if not args.skip_configs:
         configs["c5"] = bench_c5(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, dgemm_burst)
         configs["c4"] = bench_c4(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, dgemm_burst)
+        if not args.skip_varf:
+            torch.cuda.empty_cache()
+            configs["c3"] = bench_c3(torch, Plan, world, rank, flush, barrier, max_over_ranks, dgemm_burst)
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
@@ -464,6 +468,50 @@ def bench_c5(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, pea
     return {"workload": "65536 x 1-D forward+inverse, degree 1000, %d nodes (w>0, |x|<=50 subset of the 2001-point rule)" % n,
             "scaling": "strong", "ms": ms, "gpts": 2.0 * C5["batch"] * n / ms * 1e-6, "tflops": flops / ms * 1e-9,
             "frac_of_dgemm_peak_per_gpu": flops / ms * 1e-9 / (peak * world), "collective": "none (batch shard)"}
+
+
+def bench_c3(torch, Plan, world, rank, flush, barrier, max_over_ranks, peak):
+    """BASELINE configs[2]: dense 2-D varf at degree 400 per axis, quadrature Gram form (two-stage FP64 tensor-core
+    contraction) of a dense non-polynomial f.  One GPU: the triangle set (80 601^2 doubles = 52 GB).  N >= 2 GPUs:
+    the cube set (160 801^2 = 207 GB), row-sharded, never gathered (each rank keeps its row block)."""
+    from hermipy_b200.dist import split_range
+    x, w = gauss_hermite(C3["n_rule"])
+    keep = w > 0                                  # outer weights underflow in double precision
+    x, w = x[keep], w[keep]
+    n = len(x)
+    set_name = "triangle" if world == 1 else "cube"
+    plan = Plan(C3["degree"], [x, x], [w, w], index_set=set_name)
+    npol = plan.n_polys
+    lo, hi = split_range(npol, world, rank)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    fE = plan.pack_grid(np.exp(-3 * bistable(X, Y) / 10)[None])[0]
+    free = torch.cuda.mem_get_info()[0]
+    need = 8.0 * (hi - lo) * npol
+    if need > free - 6e9:
+        return {"workload": "2-D varf degree 400 (%s)" % set_name, "skipped": "row block of %.0f GB does not fit (%.0f GB free)"
+                % (need * 1e-9, free * 1e-9)}
+    out = torch.empty((hi - lo, npol), dtype=torch.float64, device="cuda")
+    reps = 2
+    run = lambda: plan.varf(fE, "gram", out, row_begin=lo, row_end=hi)
+    ms = max_over_ranks(time_steps(torch, run, reps, 1, flush, barrier)) / reps
+    # a full matrix is computed as its m0 <= n0 half and mirrored (flops n |I|^2); a row block computes every
+    # owned entry (2 n rows |I|)
+    flops = float(n) * float(npol) ** 2 if world == 1 else 2.0 * n * float(npol) ** 2
+    finite = bool(torch.isfinite(out[:: max(1, (hi - lo) // 64)]).all().item())
+    sym = None
+    if world == 1:
+        k = 4096
+        sym = float((out[:k, :k] - out[:k, :k].T).abs().max().item())
+    res = {"workload": "2-D Galerkin varf assembly, degree %d per axis, %s set: %d x %d dense (%.0f GB)%s, Gram form of a "
+                       "dense f on %d x %d nodes (w > 0 subset of the %d-point rule)"
+                       % (C3["degree"], set_name, npol, npol, 8e-9 * npol ** 2,
+                          "" if world == 1 else ", row-sharded over %d GPUs" % world, n, n, C3["n_rule"]),
+           "scaling": "strong", "assembly_ms": ms, "algorithmic_tflop": flops * 1e-12,
+           "achieved_tflops": flops / ms * 1e-9, "frac_of_dgemm_peak_per_gpu": flops / ms * 1e-9 / (peak * world),
+           "finite": finite, "symmetry_max_abs_leading_4096": sym, "collective": "none (row blocks stay on their rank)"}
+    del out
+    torch.cuda.empty_cache()
+    return res
 
 
 def bench_c4(torch, Plan, world, rank, flush, barrier, max_over_ranks, K, W, peak):

@@ -63,6 +63,44 @@ int launch_basis_tables(const double* x, const double* w, int n, int P, int four
     return launch_status();
 }
 
+// Weighted basis psi_k(x_i) = sqrt(w_i) * phi_k(x_i), the operand of the Gram-form varf.  The recurrence is
+// linear, so it is simply seeded with sqrt(w_i) instead of 1: psi is bounded (|psi| < 1 for a Gauss-Hermite
+// rule) where phi alone reaches 1e159 at degree 400 and overflows beyond degree ~780, and the pair products
+// psi_m psi_n = w phi_m phi_n never leave the double range (SURVEY.md findings 4 and 7).  Nodes whose weight
+// underflowed to 0 contribute 0, as in the weighted table of the transform.
+__global__ void psi_table_kernel(const double* __restrict__ x, const double* __restrict__ w, int n, int P, int fourier,
+                                 double* __restrict__ psi, long long ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double xi = x[i], s = sqrt(w[i]);
+    double* row = psi + (long long)i * ld;
+    if (fourier) {
+        row[0] = s / sqrt(2 * M_PI);
+        for (int k = 1; 2 * k < P; k++) {
+            row[2 * k] = s * (cos(k * xi) / sqrt(M_PI));
+            row[2 * k - 1] = s * (sin(k * xi) / sqrt(M_PI));
+        }
+        return;
+    }
+    double vm = s, v = xi * s;
+    row[0] = vm;
+    if (P > 1) row[1] = v;
+    for (int k = 1; k + 1 < P; k++) {
+        const double sk1 = sqrt((double)(k + 1));
+        const double a = __ddiv_rn(1.0, sk1), b = __ddiv_rn(sqrt((double)k), sk1);
+        const double nv = __dsub_rn(__dmul_rn(__dmul_rn(a, xi), v), __dmul_rn(b, vm));
+        vm = v;
+        v = nv;
+        row[k + 1] = v;
+    }
+}
+
+int launch_psi_table(const double* x, const double* w, int n, int P, int fourier, double* psi, long long ld,
+                     cudaStream_t s) {
+    psi_table_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, n, P, fourier, psi, ld);
+    return launch_status();
+}
+
 // Products of pairs of basis functions on the nodes, the operand of the Gram-form varf:
 //   psi2[x][m*Pp + n] = scale_x * phi_m(x) * phi_n(x),  scale_x = w_x (left/outer table) or 1.
 __global__ void pair_table_kernel(const double* __restrict__ plain, long long ld_ik, const double* __restrict__ w,

@@ -419,12 +419,18 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
         set_error("HB_VARF_GRAM supports dim <= 2 (got %d)", pl->dim);
         return HB_ERR_INVALID;
     }
+    // pair products are formed from psi = sqrt(w) phi (overflow-free), not from w * phi * phi
+    for (Axis& A : pl->ax) {
+        if (A.psi.p) continue;
+        HB_TRY(A.psi.ensure_zero((size_t)A.n * A.Pp * 8, st));
+        HB_TRY(launch_psi_table(A.x.d(), A.w.d(), A.n, A.P, A.fourier, A.psi.d(), A.Pp, st));
+    }
     if (pl->dim == 1) {
         const Axis& A = pl->ax[0];
         const size_t bytes = (size_t)A.n * A.P * A.Pp * 8;
         if (pl->pair[0].bytes < bytes) {
             HB_TRY(pl->pair[0].ensure(bytes));
-            HB_TRY(launch_pair_table(A.plain.d(), A.Pp, A.w.d(), A.n, A.P, A.Pp, pl->pair[0].d(), st));
+            HB_TRY(launch_pair_table(A.psi.d(), A.Pp, nullptr, A.n, A.P, A.Pp, pl->pair[0].d(), st));
         }
         const long long ncol = (long long)A.P * A.Pp;
         HB_TRY(pl->tmp.ensure(ncol * 8));
@@ -445,7 +451,7 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
         const Axis& A = pl->ax[a];
         const int nb = blocks8(A.P);
         HB_TRY(pl->pairB[a].ensure((size_t)A.n * nb * nb * 64 * 8));
-        HB_TRY(launch_blocked_pair_table(0, A.plain.d(), A.Pp, 0, A.w.d(), A.n, A.P, nb, pl->pairB[a].d(), st));
+        HB_TRY(launch_blocked_pair_table(0, A.psi.d(), A.Pp, 0, nullptr, A.n, A.P, nb, pl->pairB[a].d(), st));
         pl->pairB_ok[a] = true;
     }
     const Axis &A0 = pl->ax[0], &A1 = pl->ax[1];

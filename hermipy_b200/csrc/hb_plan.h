@@ -48,6 +48,7 @@ struct Axis {
     DevBuf x, w;
     DevBuf plain, wgt;    // [n][Pp]   phi_k(x_i), w_i*phi_k(x_i)
     DevBuf plainT, wgtT;  // [P][np]
+    DevBuf psi;           // [n][Pp]   sqrt(w_i)*phi_k(x_i), built on first Gram-form varf
 };
 
 }  // namespace hb
