@@ -92,7 +92,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.C = a.C; p.ldc = a.ldc; p.strideC = a.strideC;
     p.epi = a.epi; p.lut = a.lut;
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
-    p.row_begin = a.row_begin; p.row_end = a.row_end; p.tri_degree = a.tri_degree; p.symmetric = a.symmetric; p.lut_mode = a.lut_mode;
+    p.row_begin = a.row_begin; p.row_end = a.row_end; p.symmetric = a.symmetric;
+    p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkrange = a.blkrange;
     { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     p.alpha = a.alpha;
     p.block_rows = a.block_rows;

@@ -38,14 +38,22 @@ struct GemmParams {
     long long ldc;      // row pitch of C (EPI_STORE) / of the output matrix (EPI_VARF2D)
     long long strideC;  // batch stride of C / of the scattered output (EPI_LUT)
     int epi;
-    const int* lut;     // EPI_LUT: M*N entries; EPI_VARF2D: P0*P1 entries (lex (m0,m1) -> position or -1)
-    int P0, Pp0;        // EPI_VARF2D: basis count of axis 0 and its number of 8-blocks (GEMM row = blocked pair (m0,n0))
-    int P1, Pp1;        // EPI_VARF2D: same for axis 1 (GEMM col = blocked pair (m1,n1))
-    int symmetric;      // EPI_VARF2D: compute only pairs with m0 <= n0 and mirror them (A is symmetric)
-    int debug;          // developer switch (HB_VARF_DEBUG): bit0 drops direct stores, bit1 drops mirror stores
-    int lut_mode;       // EPI_VARF2D: 0 = positions from lut, 1 = cube closed form, 2 = triangle closed form
-    int row_begin, row_end;  // EPI_VARF2D: owned output rows [row_begin,row_end) (row sharding)
-    int tri_degree;     // EPI_VARF2D: >=0 -> skip tiles with m0+m1 > tri_degree (triangle-like sets)
+    const int* lut;     // EPI_LUT: M*N entries (padded lexicographic box -> position in the index set, or -1)
+    // EPI_VARF2D.  GEMM row = blocked pair (m0,n0) of axis-0 indices, GEMM column = blocked pair (m1,n1) of axis-1
+    // indices, pairs laid out in 8x8 blocks: p(i,j) = ((i>>3)*nb + (j>>3))*64 + (i&7)*8 + (j&7).  The entry lands at
+    // A[idx(m0,m1)][idx(n0,n1)].  Positions come from per-block tables of the 2-D index set (built once per plan):
+    //   blkpos  [(ba*Pp1 + bb)*64 + (a&7)*8 + (b&7)] = idx(a, b) for a in block ba of axis 0, b in block bb of axis 1
+    //                                                  (-1 outside the set or beyond the basis);
+    //   blkperm [(ba*Pp1 + bb)*64 + s]               = the 64 entries of the block sorted by position (invalid last);
+    //   blkrange[ba*Pp1 + bb]                        = {smallest, largest} valid position of the block, {0,-1} if none.
+    const int* blkpos;
+    const unsigned char* blkperm;
+    const int2* blkrange;
+    int P0, Pp0;        // basis count of axis 0 and its number of 8-blocks
+    int P1, Pp1;        // same for axis 1
+    int symmetric;      // compute only pairs with m0 <= n0 and mirror them (A is symmetric); full row range only
+    int debug;          // developer switch (HB_VARF_DEBUG): bit0 drops direct stores, bit1 mirror stores, bit2 both loops
+    int row_begin, row_end;  // owned output rows [row_begin,row_end) (row sharding)
     double alpha;       // result scale
     int tiles_m, tiles_n;    // grid is linear: blockIdx.x = b*tiles_m*tiles_n + (grouped tile order, see the kernel)
     int group_m;             // tile rows per rasterisation group (>= 1)
@@ -56,18 +64,6 @@ struct GemmParams {
     int block_rows;          // 0 = off
     double* blocks[GEMM_MAX_BLOCKS];
 };
-
-// Position of the multi-index (a, b) in the 2-D index set (reference order, iterators.cpp:106-321): closed
-// forms for the max-norm shell order (cube) and the graded order (triangle) keep dependent loads out of
-// the scatter epilogue; the other sets go through the look-up table.
-__device__ __forceinline__ int pair_position(const GemmParams& p, int a, int b) {
-    if (p.lut_mode == 1) return b >= a ? b * b + b + a : a * a + b;
-    if (p.lut_mode == 2) {
-        const int g = a + b;
-        return g <= p.tri_degree ? g * (g + 1) / 2 + a : -1;
-    }
-    return p.lut[a * p.P1 + b];
-}
 
 constexpr int GEMM_BK = 16;  // doubles per k-tile = one 128-byte swizzle span
 
@@ -108,27 +104,20 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if constexpr (EPI == EPI_VARF2D) {
-        // Tile-level skipping.  GEMM row = blocked pair (m0, n0), column = blocked pair (m1, n1); the entry
-        // lands at output row lut[m0,m1], column lut[n0,n1].  A tile is a few 8x8 blocks on each side:
-        // it is needed if some (row block, column block) combination is.
-        const int rb_lo = m_base >> 6, rb_hi = (min(m_base + BM, p.M) - 1) >> 6;
-        const int cb_lo = n_base >> 6, cb_hi = (min(n_base + BN, p.N) - 1) >> 6;
+        // Tile-level skipping: a tile is one 8x8 row block (bm0,bn0) by BN/64 column blocks (bm1,bn1).  It is
+        // needed if, for some column block, the output-row block (bm0,bm1) holds an owned row and the
+        // output-column block (bn0,bn1) holds any position of the set (total-degree and sparse sets leave whole
+        // blocks empty), and -- in symmetric mode -- if it lies in the upper half bm0 <= bn0.
+        static_assert(BM == 64 && BN % 64 == 0 && A_MMAJOR, "the varf epilogue works on 8x8-blocked pair tables");
+        const int rb = m_base >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
         bool needed = false;
-        for (int rb = rb_lo; rb <= rb_hi && !needed; rb++) {
-            const int bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
-            if (p.symmetric && bm0 > bn0) continue;              // mirrored from the (bn0, bm0) block
-            for (int cb = cb_lo; cb <= cb_hi && !needed; cb++) {
+        if (!(p.symmetric && bm0 > bn0)) {
+            for (int cbl = 0; cbl < BN / 64 && !needed; cbl++) {
+                const int cb = (n_base >> 6) + cbl;
+                if (cb * 64 >= p.N) break;
                 const int bm1 = cb / p.Pp1, bn1 = cb - bm1 * p.Pp1;
-                // total-degree sets keep only m0+m1 <= degree and n0+n1 <= degree: the smallest values decide
-                if (p.tri_degree >= 0 && (8 * (bm0 + bm1) > p.tri_degree || 8 * (bn0 + bn1) > p.tri_degree)) continue;
-                if (p.row_begin <= 0 && p.row_end >= 0x7fffffff) { needed = true; break; }
-                // row sharding: some (m0, m1) of the block pair must map to an owned output row
-                for (int i = 0; i < 8 && !needed; i++)
-                    for (int j = 0; j < 8; j++) {
-                        const int a = 8 * bm0 + i, c = 8 * bm1 + j;
-                        const int r = (a < p.P0 && c < p.P1) ? pair_position(p, a, c) : -1;
-                        if (r >= p.row_begin && r < p.row_end) { needed = true; break; }
-                    }
+                const int2 rr = p.blkrange[bm0 * p.Pp1 + bm1], cr = p.blkrange[bn0 * p.Pp1 + bn1];
+                needed = rr.y >= rr.x && cr.y >= cr.x && rr.y >= p.row_begin && rr.x < p.row_end;
             }
         }
         if (!needed) return;
@@ -237,70 +226,92 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
     }
 
     // ---------------- epilogue ----------------
-    if constexpr (BM == 64 && BN == 128 && A_MMAJOR) {
-        if constexpr (EPI == EPI_VARF2D) {
-            // Coalesced scatter through shared memory.  The tile is one 8x8 block of (m0,n0) pairs by two
-            // 8x8 blocks of (m1,n1) pairs.  Output runs are contiguous along n1 or n0 (direct entry
-            // A[idx(m0,m1)][idx(n0,n1)]) and along m1 or m0 (mirrored entry), never along a register
-            // fragment, so the accumulators are staged in the (now idle) pipeline buffers and written
-            // out 8 consecutive entries at a time.
-            constexpr int SP = BN + 2;   // staging pitch in doubles
-            double* S = reinterpret_cast<double*>(smem_gen);
-            asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");   // all warps done with the stages
+    if constexpr (EPI == EPI_VARF2D) {
+        // Table-driven coalesced scatter.  The accumulators are staged in the (now idle) pipeline buffers as
+        // S[(m0l,n0l)][(m1l,n1l)]; the positions of the 64 (m0l,m1l) row combinations and of the 64 (n0l,n1l)
+        // column combinations of every column block are read once from the per-block tables.  Direct entries
+        // A[r][c]: one warp per output row r, lanes walk the 64 columns in the order of their positions c, so
+        // that consecutive lanes hit consecutive addresses whatever the enumeration of the index set is (runs of
+        // 8 for the cube's shell order, anti-diagonal runs for the triangle).  Mirrored entries A[c][r]
+        // (symmetric mode, m0 < n0): the same with rows and columns exchanged.
+        constexpr int SP = BN + 2;   // staging pitch in doubles
+        constexpr int NCB = BN / 64;
+        double* S = reinterpret_cast<double*>(smem_gen);
+        int* s_rowpos = reinterpret_cast<int*>(smem_gen + 64 * SP * 8);   // [NCB][64]
+        int* s_colpos = s_rowpos + NCB * 64;                              // [NCB][64]
+        unsigned char* s_rowperm = reinterpret_cast<unsigned char*>(s_colpos + NCB * 64);   // [NCB][64]
+        unsigned char* s_colperm = s_rowperm + NCB * 64;
+        static_assert(64 * SP * 8 + NCB * 64 * 10 <= STAGES * STAGE_BYTES, "staging area");
+        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");   // all warps done with the stages
 #pragma unroll
-            for (int mi = 0; mi < MI; mi++) {
-                const int im = wm * MI + mi;
-                const int rl = 16 * (im >> 1) + 4 * (im & 1) + cm;
+        for (int mi = 0; mi < MI; mi++) {
+            const int im = wm * MI + mi;
+            const int rl = 16 * (im >> 1) + 4 * (im & 1) + cm;
 #pragma unroll
-                for (int nj = 0; nj < NJ; nj++) {
-                    const int jn = wn * NJ + nj;
-                    const int cl = 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
-                    *reinterpret_cast<double2*>(S + rl * SP + cl) =
-                        make_double2(acc[mi][nj][0] * p.alpha, acc[mi][nj][1] * p.alpha);
+            for (int nj = 0; nj < NJ; nj++) {
+                const int jn = wn * NJ + nj;
+                const int cl = 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
+                *reinterpret_cast<double2*>(S + rl * SP + cl) =
+                    make_double2(acc[mi][nj][0] * p.alpha, acc[mi][nj][1] * p.alpha);
+            }
+        }
+        const int rb = m_base >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
+        for (int e = threadIdx.x; e < NCB * 64; e += NCW * 32) {
+            const int cbl = e >> 6, cb = (n_base >> 6) + cbl;
+            int rp = -1, cp = -1, rperm = e & 63, cperm = e & 63;
+            if (cb * 64 < p.N) {
+                const int bm1 = cb / p.Pp1, bn1 = cb - bm1 * p.Pp1;
+                const int rblk = (bm0 * p.Pp1 + bm1) * 64 + (e & 63), cblk = (bn0 * p.Pp1 + bn1) * 64 + (e & 63);
+                rp = __ldg(p.blkpos + rblk);
+                cp = __ldg(p.blkpos + cblk);
+                rperm = __ldg(p.blkperm + rblk);
+                cperm = __ldg(p.blkperm + cblk);
+            }
+            s_rowpos[e] = rp; s_colpos[e] = cp;
+            s_rowperm[e] = (unsigned char)rperm; s_colperm[e] = (unsigned char)cperm;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+        if (p.debug & 4) return;
+        const bool diag = (bm0 == bn0);
+        // ---- direct entries A[idx(m0,m1)][idx(n0,n1)] = S[(m0l,n0l)][(m1l,n1l)] ----
+        for (int cbl = 0; cbl < NCB; cbl++) {
+            const double* Sc = S + cbl * 64;
+            for (int er = warp; er < 64; er += NCW) {          // er = m0l*8 + m1l
+                const int r = s_rowpos[cbl * 64 + er];
+                if (r < p.row_begin || r >= p.row_end) continue;    // also drops r = -1
+                const int i = er >> 3, k = er & 7;
+                double* orow = p.C + (long long)(r - p.row_begin) * p.ldc;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int ec = s_colperm[cbl * 64 + lane + 32 * h];   // ec = n0l*8 + n1l
+                    const int c = s_colpos[cbl * 64 + ec];
+                    const int j = ec >> 3, l = ec & 7;
+                    if (c < 0 || (p.symmetric && diag && i > j)) continue;
+                    if (!(p.debug & 1)) orow[c] = Sc[(i * 8 + j) * SP + k * 8 + l];
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
-            const int rb = m_base >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
-            const int f8 = lane & 7, s4 = lane >> 3;     // fast index (8 consecutive outputs), slow index (4)
-            const bool row_interior = 8 * bm0 + 8 <= p.P0 && 8 * bn0 + 8 <= p.P0;
-            if (p.debug & 4) return;
-            // pass 0: direct entries A[idx(m0,m1)][idx(n0,n1)]; pass 1: mirrored entries (symmetric mode,
-            // off-diagonal part).  Everything that does not depend on the lane is hoisted per column block.
-            const int n_pass = (p.symmetric && bm0 <= bn0) ? 2 : 1;
-            for (int pass = 0; pass < n_pass; pass++) {
-                for (int cbl = 0; cbl < 2; cbl++) {
-                    const int cb = (n_base >> 6) + cbl;
-                    if (cb * 64 >= p.N) break;
-                    const int bm1 = cb / p.Pp1, bn1 = cb - bm1 * p.Pp1;
-                    const bool interior = row_interior && 8 * bm1 + 8 <= p.P1 && 8 * bn1 + 8 <= p.P1;
-                    // which of the two patch indices runs along consecutive output entries
-                    const bool swap = pass == 0 ? (bn1 > bn0) : (bm1 > bm0);
-                    const double* Sc = S + cbl * 64;
-#pragma unroll 4
-                    for (int v = warp; v < 128; v += NCW) {
-                        const int l0 = v >> 4, l1 = (v >> 1) & 7;
-                        const int fa = swap ? s4 + 4 * (v & 1) : f8;     // index paired with l1's axis
-                        const int fb = swap ? f8 : s4 + 4 * (v & 1);     // index paired with l0's axis
-                        // pass 0: (m0l, m1l) = (l0, l1) fixed, (n0l, n1l) = (fb, fa); pass 1: the roles swap
-                        const int m0l = pass == 0 ? l0 : fb, m1l = pass == 0 ? l1 : fa;
-                        const int n0l = pass == 0 ? fb : l0, n1l = pass == 0 ? fa : l1;
-                        const int m0 = 8 * bm0 + m0l, n0 = 8 * bn0 + n0l, m1 = 8 * bm1 + m1l, n1 = 8 * bn1 + n1l;
-                        if (!interior && (m0 >= p.P0 || n0 >= p.P0 || m1 >= p.P1 || n1 >= p.P1)) continue;
-                        if (p.symmetric && (pass ? m0 >= n0 : m0 > n0)) continue;
-                        const int r_out = pair_position(p, m0, m1), c_out = pair_position(p, n0, n1);
-                        if (r_out < 0 || c_out < 0) continue;
-                        const double val = Sc[(m0l * 8 + n0l) * SP + m1l * 8 + n1l];
-                        if (pass == 0) {
-                            if (r_out >= p.row_begin && r_out < p.row_end && !(p.debug & 1))
-                                p.C[(long long)(r_out - p.row_begin) * p.ldc + c_out] = val;
-                        } else if (!(p.debug & 2)) {
-                            p.C[(long long)c_out * p.ldc + r_out] = val;
-                        }
+        }
+        // ---- mirrored entries A[idx(n0,n1)][idx(m0,m1)] for m0 < n0 ----
+        if (p.symmetric) {
+            for (int cbl = 0; cbl < NCB; cbl++) {
+                const double* Sc = S + cbl * 64;
+                for (int ec = warp; ec < 64; ec += NCW) {
+                    const int c = s_colpos[cbl * 64 + ec];
+                    if (c < 0) continue;
+                    const int j = ec >> 3, l = ec & 7;
+                    double* orow = p.C + (long long)c * p.ldc;
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int er = s_rowperm[cbl * 64 + lane + 32 * h];
+                        const int r = s_rowpos[cbl * 64 + er];
+                        const int i = er >> 3, k = er & 7;
+                        if (r < 0 || (diag && i >= j)) continue;
+                        if (!(p.debug & 2)) orow[r] = Sc[(i * 8 + j) * SP + k * 8 + l];
                     }
                 }
             }
-            return;
         }
+        return;
     }
     if constexpr (EPI == EPI_LUT) {
         // Scatter through the look-up table (last stage of a d-dim forward transform).  The table entries
@@ -352,30 +363,6 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
                 } else {
                     dst[0] = v0;
                     if (has1) dst[1] = v1;
-                }
-            } else if constexpr (EPI == EPI_VARF2D) {
-                const int rb = row >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
-                const int m0 = 8 * bm0 + ((row >> 3) & 7), n0 = 8 * bn0 + (row & 7);
-                if (m0 >= p.P0 || n0 >= p.P0 || (p.symmetric && m0 > n0)) continue;
-                const int cb = col >> 6, bm1 = cb / p.Pp1, bn1 = cb - bm1 * p.Pp1;
-                const int m1 = 8 * bm1 + ((col >> 3) & 7), n1 = 8 * bn1 + (col & 7);   // col is even: col+1 -> n1+1
-                if (m1 >= p.P1 || n1 >= p.P1) continue;
-                const int r_out = pair_position(p, m0, m1);
-                if (r_out < 0) continue;
-                const int c0 = pair_position(p, n0, n1);
-                const int c1 = (has1 && n1 + 1 < p.P1) ? pair_position(p, n0, n1 + 1) : -1;
-                if (r_out >= p.row_begin && r_out < p.row_end) {
-                    double* orow = p.C + (long long)(r_out - p.row_begin) * p.ldc;
-                    if (c1 == c0 + 1 && c0 >= 0 && ((reinterpret_cast<uintptr_t>(orow + c0) & 15) == 0)) {
-                        *reinterpret_cast<double2*>(orow + c0) = make_double2(v0, v1);   // one 16-byte store
-                    } else {
-                        if (c0 >= 0) orow[c0] = v0;
-                        if (c1 >= 0) orow[c1] = v1;
-                    }
-                }
-                if (p.symmetric && m0 < n0) {   // mirror: A[idx(n0,n1)][idx(m0,m1)] (full row range only)
-                    if (c0 >= 0) p.C[(long long)c0 * p.ldc + r_out] = v0;
-                    if (c1 >= 0) p.C[(long long)c1 * p.ldc + r_out] = v1;
                 }
             }
         }

@@ -19,7 +19,11 @@ struct GemmArgs {
     long long ldc = 0, strideC = 0;
     int epi = 0;
     const int* lut = nullptr;
-    int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, tri_degree = -1, symmetric = 0, lut_mode = 0;
+    // varf scatter epilogue (see GemmParams in hb_gemm.cuh)
+    const int* blkpos = nullptr;
+    const unsigned char* blkperm = nullptr;
+    const int2* blkrange = nullptr;
+    int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, symmetric = 0;
     double alpha = 1.0;
     int block_rows = 0;              // EPI_STORE: rows [i*block_rows, (i+1)*block_rows) -> blocks[i] (C unused)
     double* blocks[16] = {nullptr};

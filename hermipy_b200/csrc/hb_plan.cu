@@ -366,9 +366,36 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
         HB_TRY(pl->midx.ensure(m.size() * 4));
         HB_CUDA(cudaMemcpyAsync(pl->midx.p, m.data(), m.size() * 4, cudaMemcpyHostToDevice, st));
         if (pl->dim == 2) {
-            HB_TRY(pl->lut2d.ensure(pl->iset->lex_to_pos.size() * 4));
-            HB_CUDA(cudaMemcpyAsync(pl->lut2d.p, pl->iset->lex_to_pos.data(), pl->iset->lex_to_pos.size() * 4,
-                                    cudaMemcpyHostToDevice, st));
+            // Per-block position tables of the 2-D index set for the scatter epilogue of the dense varf
+            // (see GemmParams): positions, the order of the 64 entries of a block by position, and the range.
+            const int P0 = pl->ax[0].P, P1 = pl->ax[1].P, nb0 = (P0 + 7) / 8, nb1 = (P1 + 7) / 8;
+            std::vector<int> pos((size_t)nb0 * nb1 * 64, -1);
+            std::vector<unsigned char> perm((size_t)nb0 * nb1 * 64);
+            std::vector<int> range((size_t)nb0 * nb1 * 2);
+            for (int ba = 0; ba < nb0; ba++)
+                for (int bb = 0; bb < nb1; bb++) {
+                    const size_t base = ((size_t)ba * nb1 + bb) * 64;
+                    int lo = 0x7fffffff, hi = -1;
+                    for (int e = 0; e < 64; e++) {
+                        const int a = 8 * ba + (e >> 3), b = 8 * bb + (e & 7);
+                        const int v = (a < P0 && b < P1) ? pl->iset->lex_to_pos[(size_t)a * P1 + b] : -1;
+                        pos[base + e] = v;
+                        if (v >= 0) { lo = std::min(lo, v); hi = std::max(hi, v); }
+                        perm[base + e] = (unsigned char)e;
+                    }
+                    // invalid entries (-1) sort last: compare as unsigned
+                    std::sort(perm.begin() + base, perm.begin() + base + 64, [&](unsigned char x, unsigned char y) {
+                        return (unsigned)pos[base + x] < (unsigned)pos[base + y];
+                    });
+                    range[((size_t)ba * nb1 + bb) * 2] = hi >= 0 ? lo : 0;
+                    range[((size_t)ba * nb1 + bb) * 2 + 1] = hi;
+                }
+            HB_TRY(pl->blkpos.ensure(pos.size() * 4));
+            HB_TRY(pl->blkperm.ensure(perm.size()));
+            HB_TRY(pl->blkrange.ensure(range.size() * 4));
+            HB_CUDA(cudaMemcpyAsync(pl->blkpos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, st));
+            HB_CUDA(cudaMemcpyAsync(pl->blkperm.p, perm.data(), perm.size(), cudaMemcpyHostToDevice, st));
+            HB_CUDA(cudaMemcpyAsync(pl->blkrange.p, range.data(), range.size() * 4, cudaMemcpyHostToDevice, st));
         }
         HB_CUDA(cudaStreamSynchronize(st));
     }
@@ -401,13 +428,14 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.A = Ltab; g2.lda = nrow; g2.a_mmajor = true;
     g2.B = pl->G.d(); g2.ldb = ncol;
     g2.C = d_out; g2.ldc = ldo;
-    g2.epi = EPI_VARF2D; g2.lut = pl->lut2d.i();
+    g2.epi = EPI_VARF2D;
+    g2.blkpos = pl->blkpos.i();
+    g2.blkperm = static_cast<const unsigned char*>(pl->blkperm.p);
+    g2.blkrange = static_cast<const int2*>(pl->blkrange.p);
     g2.P0 = P0; g2.Pp0 = nb0; g2.P1 = P1; g2.Pp1 = nb1;
     const bool full = (row_begin == 0 && row_end == pl->n_polys);
     g2.row_begin = (int)row_begin; g2.row_end = full ? 0x7fffffff : (int)row_end;
     g2.symmetric = full ? 1 : 0;
-    g2.tri_degree = (pl->set == SET_TRIANGLE) ? pl->degree : -1;
-    g2.lut_mode = (pl->set == SET_CUBE) ? 1 : (pl->set == SET_TRIANGLE ? 2 : 0);
     g2.group_m = 16;   // 16 row tiles (3.3 MB of the left table at C2) stay in L2 while the right table streams
     g2.cfg = 2;   // 64 x 128 tiles, two CTAs per SM: one 8x8 row block per tile, epilogues overlap main loops
     return timed_gemm(pl, g2, 22, st);
