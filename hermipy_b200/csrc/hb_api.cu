@@ -148,6 +148,8 @@ extern "C" {
 const char* hb_last_error(void) { return hb::last_error(); }
 const char* hb_version(void) { return "hermite_b200 0.1 (sm_100a)"; }
 long long hb_launch_count(int reset) { return hb::launch_count(reset); }
+// developer hook (not in the public header): device buffer of 2 + 5*capacity int64 words, [1] = capacity
+void hb_debug_trace(void* dev) { hb::gemm_set_trace(static_cast<long long*>(dev)); }
 
 int hb_device_count(int* count) {
     int n = 0;

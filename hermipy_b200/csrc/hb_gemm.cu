@@ -82,6 +82,10 @@ static int pick_cfg(const GemmArgs& a) {
     return best_i;
 }
 
+static long long* g_trace = nullptr;
+void gemm_set_trace(long long* dev) { g_trace = dev; }
+long long* gemm_get_trace() { return g_trace; }
+
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return HB_OK;
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
@@ -94,6 +98,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.row_begin = a.row_begin; p.row_end = a.row_end; p.symmetric = a.symmetric;
     p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkrange = a.blkrange;
+    p.trace = g_trace;
     { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     p.alpha = a.alpha;
     p.block_rows = a.block_rows;

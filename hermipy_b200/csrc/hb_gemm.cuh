@@ -54,6 +54,7 @@ struct GemmParams {
     int symmetric;      // compute only pairs with m0 <= n0 and mirror them (A is symmetric); full row range only
     int debug;          // developer switch (HB_VARF_DEBUG): bit0 drops direct stores, bit1 mirror stores, bit2 both loops
     int row_begin, row_end;  // owned output rows [row_begin,row_end) (row sharding)
+    long long* trace;   // developer timeline (hb_debug_trace): [0] = record counter, [1] = capacity, then 5 words per CTA
     double alpha;       // result scale
     int tiles_m, tiles_n;    // grid is linear: blockIdx.x = b*tiles_m*tiles_n + (grouped tile order, see the kernel)
     int group_m;             // tile rows per rasterisation group (>= 1)
@@ -64,6 +65,12 @@ struct GemmParams {
     int block_rows;          // 0 = off
     double* blocks[GEMM_MAX_BLOCKS];
 };
+
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int GEMM_BK = 16;  // doubles per k-tile = one 128-byte swizzle span
 
@@ -122,6 +129,8 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
         }
         if (!needed) return;
     }
+    long long t_start = 0, t_main = 0;
+    if constexpr (EPI == EPI_VARF2D) { if (p.trace && threadIdx.x == 0) t_start = global_ns(); }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
 
     // ---------------- epilogue ----------------
     if constexpr (EPI == EPI_VARF2D) {
+        if (p.trace && threadIdx.x == 0) t_main = global_ns();
         // Table-driven coalesced scatter.  The accumulators are staged in the (now idle) pipeline buffers as
         // S[(m0l,n0l)][(m1l,n1l)]; the positions of the 64 (m0l,m1l) row combinations and of the 64 (n0l,n1l)
         // column combinations of every column block are read once from the per-block tables.  Direct entries
@@ -309,6 +319,15 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
                         if (!(p.debug & 2)) orow[r] = Sc[(i * 8 + j) * SP + k * 8 + l];
                     }
                 }
+            }
+        }
+        if (p.trace && threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const long long slot = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
+            if (slot < p.trace[1]) {
+                long long* rec = p.trace + 2 + 5 * slot;
+                rec[0] = blockIdx.x; rec[1] = smid; rec[2] = t_start; rec[3] = t_main; rec[4] = global_ns();
             }
         }
         return;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
+#include <vector>
 
 #include "../../include/hermite_b200.h"
 
@@ -32,5 +33,12 @@ struct GemmArgs {
 };
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream);
+void gemm_set_trace(long long* dev);   // developer timeline of the varf stage-2 kernel (nullptr = off)
+long long* gemm_get_trace();
+
+// Stage 2 of the dense 2-D varf as a persistent ping-pong kernel (hb_varf_gemm.cu): `a` as for gemm_launch with
+// epi = EPI_VARF2D; the tile list (pairs tile_m, tile_n) comes from varf_tile_list.
+int varf_tile_list(const GemmArgs& a, const std::vector<int>& blkrange, std::vector<int>& out);
+int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cudaStream_t stream);   // developer timeline of the varf stage-2 kernel (nullptr = off)
 
 }  // namespace hb

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "hb_gemm.cuh"
 #include "hb_kernels.h"
@@ -396,6 +397,7 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
             HB_CUDA(cudaMemcpyAsync(pl->blkpos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, st));
             HB_CUDA(cudaMemcpyAsync(pl->blkperm.p, perm.data(), perm.size(), cudaMemcpyHostToDevice, st));
             HB_CUDA(cudaMemcpyAsync(pl->blkrange.p, range.data(), range.size() * 4, cudaMemcpyHostToDevice, st));
+            pl->h_blkrange = range;
         }
         HB_CUDA(cudaStreamSynchronize(st));
     }
@@ -437,8 +439,36 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.row_begin = (int)row_begin; g2.row_end = full ? 0x7fffffff : (int)row_end;
     g2.symmetric = full ? 1 : 0;
     g2.group_m = 16;   // 16 row tiles (3.3 MB of the left table at C2) stay in L2 while the right table streams
-    g2.cfg = 2;   // 64 x 128 tiles, two CTAs per SM: one 8x8 row block per tile, epilogues overlap main loops
-    return timed_gemm(pl, g2, 22, st);
+    g2.cfg = 2;   // 64 x 128 tiles: one 8x8 row block per tile
+    static const bool pingpong = [] { const char* e = getenv("HB_VARF_PINGPONG"); return !(e && e[0] == '0'); }();
+    if (!pingpong) return timed_gemm(pl, g2, 22, st);   // generic kernel, two CTAs per SM (developer comparison)
+    // persistent ping-pong kernel over the list of needed tiles (cached per row range)
+    const long long key[3] = {row_begin, row_end, g2.symmetric};
+    if (key[0] != pl->tiles_key[0] || key[1] != pl->tiles_key[1] || key[2] != pl->tiles_key[2]) {
+        std::vector<int> list;
+        HB_TRY(varf_tile_list(g2, pl->h_blkrange, list));
+        pl->n_tiles = (int)(list.size() / 2);
+        HB_TRY(pl->tiles.ensure(std::max<size_t>(list.size(), 2) * 4));
+        if (!list.empty()) {
+            HB_CUDA(cudaMemcpyAsync(pl->tiles.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
+            HB_CUDA(cudaStreamSynchronize(st));   // `list` goes out of scope
+        }
+        pl->tiles_key[0] = key[0]; pl->tiles_key[1] = key[1]; pl->tiles_key[2] = key[2];
+    }
+    if (!pl->timing) return varf_stage2_launch(g2, static_cast<const int2*>(pl->tiles.p), pl->n_tiles, st);
+    if (pl->n_timed >= (int)pl->timed.size()) {
+        hb_plan::Timed t;
+        HB_CUDA(cudaEventCreate(&t.e0));
+        HB_CUDA(cudaEventCreate(&t.e1));
+        pl->timed.push_back(t);
+    }
+    hb_plan::Timed& t = pl->timed[pl->n_timed++];
+    t.tag = 22;
+    t.flops = 2.0 * g2.M * (double)g2.N * g2.K;
+    HB_CUDA(cudaEventRecord(t.e0, st));
+    const int rc = varf_stage2_launch(g2, static_cast<const int2*>(pl->tiles.p), pl->n_tiles, st);
+    HB_CUDA(cudaEventRecord(t.e1, st));
+    return rc;
 }
 
 static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ldo, long long row_begin,

@@ -69,6 +69,10 @@ struct hb_plan {
     hb::DevBuf pairB[2], TB[2];     // blocked pair tables (dim 2 dense varf): Gram / triple products per axis
     bool pairB_ok[2] = {false, false}, TB_ok[2] = {false, false};
     std::vector<double> h_Hf;
+    std::vector<int> h_blkrange;      // host copy of blkrange (tile lists of the stage-2 kernel)
+    hb::DevBuf tiles;                 // needed tiles of the last (row range, symmetric) request
+    long long tiles_key[3] = {-1, -1, -1};
+    int n_tiles = 0;
     int last_n_kept = 0, last_path = 0;
     // optional device timing (CUDA events on the launch stream) of every GEMM launch of the last call
     struct Timed { cudaEvent_t e0 = nullptr, e1 = nullptr; int tag = 0; double flops = 0; };
