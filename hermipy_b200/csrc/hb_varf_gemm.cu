@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(384, 1)
             s_rowperm[e] = (unsigned char)rperm; s_colperm[e] = (unsigned char)cperm;
         }
 
-        long long t_tile = 0, t_main0 = 0, t_main1 = 0, t_stage = 0;
+        long long t_tile = 0, t_main0 = 0, t_main1 = 0, t_stage = 0, t_staged = 0, t_direct = 0;
         if (p.trace && gt == 0) t_tile = global_ns();
         // ---- keep the two groups half a tile apart ----
         // prog[q] = 2 * (main loops finished by group q) + (1 once the current one is past its midpoint).  Tile n
@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(384, 1)
             }
         }
         group_sync(g);
+        if (p.trace && gt == 0) t_staged = global_ns();
         const bool diag = (bm0 == bn0);
         // direct entries A[idx(m0,m1)][idx(n0,n1)] = S[(m0l,n0l)][(m1l,n1l)]: one warp per output row, lanes walk the
         // 64 columns of the block in position order (coalesced whatever the enumeration of the set is).  What a
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(384, 1)
                     if (c[h] >= 0 && !(p.symmetric && diag && i > jj[h])) orow[c[h]] = Srow[soff[h]];
             }
         }
+        if (p.trace && gt == 0) t_direct = global_ns();
         // mirrored entries A[idx(n0,n1)][idx(m0,m1)] for m0 < n0 (symmetric mode: full row range)
         if (p.symmetric) {
             for (int cbl = 0; cbl < 2; cbl++) {
@@ -282,12 +284,12 @@ __global__ void __launch_bounds__(384, 1)
         if (gt == 0) {
             __threadfence_block();
             st_volatile(flags + 3, 0);
-            if (p.trace) {   // developer timeline: 8 words per tile
+            if (p.trace) {   // developer timeline: 10 words per tile
                 const long long slot = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
                 if (slot < p.trace[1]) {
-                    long long* rec = p.trace + 2 + 8 * slot;
+                    long long* rec = p.trace + 2 + 10 * slot;
                     rec[0] = ti; rec[1] = blockIdx.x * 2 + g; rec[2] = t_tile; rec[3] = t_main0; rec[4] = t_main1;
-                    rec[5] = t_stage; rec[6] = global_ns(); rec[7] = 0;
+                    rec[5] = t_stage; rec[6] = global_ns(); rec[7] = t_staged; rec[8] = t_direct; rec[9] = 0;
                 }
             }
         }

@@ -15,16 +15,17 @@ out = torch.empty((pl.n_polys, pl.n_polys), dtype=torch.float64, device="cuda")
 fE = pl.pack_grid(np.exp(-3 * V / 10)[None])[0]
 pl.varf(fE, "gram", out); torch.cuda.synchronize()
 cap = 200000
-tr = torch.zeros(2 + 8 * cap, dtype=torch.int64, device="cuda"); tr[1] = cap
+tr = torch.zeros(2 + 10 * cap, dtype=torch.int64, device="cuda"); tr[1] = cap
 lib.hb_debug_trace(C.c_void_p(tr.data_ptr()))
 pl.varf(fE, "gram", out); torch.cuda.synchronize()
 lib.hb_debug_trace(None)
-t = tr.cpu().numpy(); n = int(min(t[0], cap)); rec = t[2:2 + 8 * n].reshape(n, 8)
+t = tr.cpu().numpy(); n = int(min(t[0], cap)); rec = t[2:2 + 10 * n].reshape(n, 10)
 print("tiles", n)
 t0 = rec[:, 2].min()
 us = lambda a: a * 1e-3
 wait, main, hand, epi = us(rec[:, 3] - rec[:, 2]), us(rec[:, 4] - rec[:, 3]), us(rec[:, 5] - rec[:, 4]), us(rec[:, 6] - rec[:, 5])
-for name, v in (("wait for turn", wait), ("main loop", main), ("wait for staging", hand), ("stage+scatter", epi)):
+stg, dire, mirr = us(rec[:, 7] - rec[:, 5]), us(rec[:, 8] - rec[:, 7]), us(rec[:, 6] - rec[:, 8])
+for name, v in (("wait for turn", wait), ("main loop", main), ("wait for staging", hand), ("stage+scatter", epi), ("  staging", stg), ("  direct pass", dire), ("  mirror pass", mirr)):
     print("%-18s us: mean %.1f p10 %.1f p50 %.1f p90 %.1f max %.1f" % (name, v.mean(), *np.percentile(v, [10, 50, 90]), v.max()))
 print("kernel span ms %.2f" % ((rec[:, 6].max() - t0) * 1e-6))
 ends = {}
