@@ -79,8 +79,22 @@ constexpr int gemm_smem_bytes() {
     return STAGES * (BM + BN) * GEMM_BK * 8 + 1024 /*alignment slack*/ + 2 * STAGES * 8;
 }
 
+// Register budget.  A CTA is NCW consumer warps plus one producer WARP GROUP (4 warps, one of them active), so
+// that `setmaxnreg` can move registers between the roles: the register file is handed out per warp group, and a
+// (NCW + 1)-warp CTA is charged for NCW + 4 warps anyway.  With 8 consumer warps (1 CTA/SM) every thread starts
+// with 168 registers, with 4 consumer warps and 2 CTAs/SM with 128; the producer group drops to 40 and the
+// consumers grow to 232 / 216, enough for the 128 accumulator registers of a 32 x 64 warp tile plus fragments
+// (at 168 ptxas spills and shuffles accumulators through extra moves).  4 consumer warps at 1 CTA/SM already
+// start with 255 registers.
+template <int NCW, int MIN_CTAS>
+struct GemmRegs {
+    static constexpr bool kRealloc = (NCW == 8 && MIN_CTAS == 1) || (NCW == 4 && MIN_CTAS == 2);
+    static constexpr int kConsumer = (NCW == 8) ? 232 : 216;
+    static constexpr int kProducer = 40;
+};
+
 template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool A_MMAJOR, int MIN_CTAS, int EPI>
-__global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
+__global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
@@ -144,9 +158,11 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
 
     const int KT = (p.K + GEMM_BK - 1) / GEMM_BK;
 
-    if (warp == NCW) {
-        // ---------------- TMA producer (one elected lane) ----------------
-        if (lane == 0) {
+    using Regs = GemmRegs<NCW, MIN_CTAS>;
+    if (warp >= NCW) {
+        if constexpr (Regs::kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::kProducer));
+        // ---------------- TMA producer (one elected lane of the first warp of the producer group) ----------------
+        if (warp == NCW && lane == 0) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
             for (int kt = 0; kt < KT; kt++) {
@@ -172,6 +188,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 1) * 32, MIN_CTAS)
     }
 
     // ---------------- consumers: DMMA ----------------
+    if constexpr (Regs::kRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::kConsumer));
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int g = lane >> 2, t = lane & 3;
     const int rm = 2 * (g & 3) + (g >> 2);                          // rowmap(g)

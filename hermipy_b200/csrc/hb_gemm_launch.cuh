@@ -56,7 +56,7 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
             return HB_ERR_CUDA;
         attr_set = true;
     }
-    kern<<<(unsigned)n_cta, (WMc * WNc + 1) * 32, smem, stream>>>(tmA, tmB, p);
+    kern<<<(unsigned)n_cta, (WMc * WNc + 4) * 32, smem, stream>>>(tmA, tmB, p);
     return launch_status();
 }
 
