@@ -52,6 +52,8 @@ struct GemmParams {
     int P0, Pp0;        // basis count of axis 0 and its number of 8-blocks
     int P1, Pp1;        // same for axis 1
     int symmetric;      // compute only pairs with m0 <= n0 and mirror them (A is symmetric); full row range only
+    int b_koff_odd;     // > 0: row tiles whose block pair (bm0,bn0) has odd parity read B from k = b_koff_odd on
+    int nb_even0;       //      (parity of a block of axis 0: its index >= nb_even0), persistent kernel only
     int debug;          // developer switch (HB_VARF_DEBUG): bit0 drops direct stores, bit1 mirror stores, bit2 both loops
     int row_begin, row_end;  // owned output rows [row_begin,row_end) (row sharding)
     long long* trace;   // developer timeline (hb_debug_trace): [0] = record counter, [1] = capacity, then 5 words per CTA

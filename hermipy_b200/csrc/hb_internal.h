@@ -25,6 +25,7 @@ struct GemmArgs {
     const unsigned char* blkperm = nullptr;
     const int2* blkrange = nullptr;
     int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, symmetric = 0;
+    int b_koff_odd = 0, nb_even0 = 0;   // parity-halved contraction (0 = off): see varf_dense_2d in hb_plan.cu
     double alpha = 1.0;
     int block_rows = 0;              // EPI_STORE: rows [i*block_rows, (i+1)*block_rows) -> blocks[i] (C unused)
     double* blocks[16] = {nullptr};

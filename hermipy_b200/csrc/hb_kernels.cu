@@ -127,19 +127,22 @@ int launch_pair_table(const double* plain, long long ld_ik, const double* w, int
 // Blocked pair tables for the two-stage dense varf (dim 2).  Pairs (i, j) of basis indices are laid out
 // in 8x8 blocks, p(i,j) = ((i>>3)*nb + (j>>3))*64 + (i&7)*8 + (j&7), nb = ceil(P/8), so that a 64-row GEMM
 // tile is exactly one block: skipping by symmetry (i <= j blocks only) and by total degree then works
-// at a granularity of 8 instead of the tile width.  Entries with i >= P or j >= P are zero.
+// at a granularity of 8 instead of the tile width.  Entries of padding slots are zero.
 //   mode 0: out[x][p] = w_x * phi_i(x) * phi_j(x)      (Gram form; src = phi[x][k] with pitch ld, w may be null)
 //   mode 1: out[k][p] = T[k][i][j]                     (reference algebra; src = T with plane/pitch)
+// `slots` maps the 8*nb slots of an axis to basis indices (-1 = padding).  For a Hermite axis the even indices
+// come first and the odd ones start on a block boundary, so every 8x8 block has one parity of i + j.
 __global__ void blocked_pair_table_kernel(int mode, const double* __restrict__ src, long long ld, long long plane,
-                                          const double* __restrict__ w, int P, int nb, double* __restrict__ out) {
+                                          const double* __restrict__ w, const int* __restrict__ slots, int nb,
+                                          double* __restrict__ out) {
     const int x = blockIdx.y;
     const long long np = (long long)nb * nb * 64;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
     const int blk = (int)(p >> 6), bi = blk / nb, bj = blk - bi * nb;
-    const int i = 8 * bi + (int)((p >> 3) & 7), j = 8 * bj + (int)(p & 7);
+    const int i = slots[8 * bi + (int)((p >> 3) & 7)], j = slots[8 * bj + (int)(p & 7)];   // -1: padding slot
     double v = 0.0;
-    if (i < P && j < P) {
+    if (i >= 0 && j >= 0) {
         if (mode == 0) {
             v = src[(long long)x * ld + i] * src[(long long)x * ld + j];
             if (w) v = (w[x] == 0.0) ? 0.0 : v * w[x];
@@ -151,9 +154,31 @@ __global__ void blocked_pair_table_kernel(int mode, const double* __restrict__ s
 }
 
 int launch_blocked_pair_table(int mode, const double* src, long long ld, long long plane, const double* w, int rows,
-                              int P, int nb, double* out, cudaStream_t s) {
+                              const int* slots, int nb, double* out, cudaStream_t s) {
     dim3 grid(cdiv((long long)nb * nb * 64, 256), rows);
-    blocked_pair_table_kernel<<<grid, 256, 0, s>>>(mode, src, ld, plane, w, P, nb, out);
+    blocked_pair_table_kernel<<<grid, 256, 0, s>>>(mode, src, ld, plane, w, slots, nb, out);
+    return launch_status();
+}
+
+// Even / odd parts of a grid function along its first axis, for a symmetric node set (x_i = -x_{n-1-i}):
+//   out[h][c]        = f[lo+h][c] + f[n-1-lo-h][c]      (h < nh; the middle node of an odd rule is taken once)
+//   out[seg + h][c]  = f[lo+h][c] - f[n-1-lo-h][c]      (0 for the middle node)
+// with lo = n - nh the first non-negative node.  Rows nh..seg-1 of the even segment are left untouched (zero).
+__global__ void parity_split_kernel(const double* __restrict__ f, int n, int nh, int seg, long long pitch,
+                                    double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nh * pitch) return;
+    const int h = (int)(idx / pitch);
+    const long long c = idx - (long long)h * pitch;
+    const int xp = n - nh + h, xm = n - 1 - xp;
+    const double a = f[(long long)xp * pitch + c];
+    const double b = (xm == xp) ? 0.0 : f[(long long)xm * pitch + c];
+    out[(long long)h * pitch + c] = a + b;
+    out[(long long)(seg + h) * pitch + c] = (xm == xp) ? 0.0 : a - b;
+}
+
+int launch_parity_split(const double* f, int n, int nh, int seg, long long pitch, double* out, cudaStream_t s) {
+    parity_split_kernel<<<cdiv((long long)nh * pitch, 256), 256, 0, s>>>(f, n, nh, seg, pitch, out);
     return launch_status();
 }
 

@@ -15,7 +15,8 @@ int launch_pair_table(const double* plain, long long ld_ik, const double* w, int
                       cudaStream_t s);
 int launch_triple_products(int N, int Pp, double* T, cudaStream_t s);
 int launch_blocked_pair_table(int mode, const double* src, long long ld, long long plane, const double* w, int rows,
-                              int P, int nb, double* out, cudaStream_t s);
+                              const int* slots, int nb, double* out, cudaStream_t s);
+int launch_parity_split(const double* f, int n, int nh, int seg, long long pitch, double* out, cudaStream_t s);
 int launch_repack_rows(const double* src, long long src_ld, double* dst, long long dst_ld, long long rows, int cols,
                        cudaStream_t s);
 int launch_gather_lut(const double* src, long long src_stride, const int* lut, double* dst, long long dst_stride,

@@ -145,6 +145,23 @@ int plan_create(hb_plan** out, int dim, const int* n_pts, int degree, const doub
         HB_TRY(A.wgtT.ensure_zero((size_t)A.P * A.np * 8, st));
         HB_TRY(launch_basis_tables(A.x.d(), A.w.d(), A.n, A.P, A.fourier, A.plain.d(), A.wgt.d(), A.Pp,
                                    A.plainT.d(), A.wgtT.d(), A.np, st));
+        // slots of the blocked pair tables (dense varf); parity-sorted on Hermite axes
+        auto add_group = [&](int first, int step) {
+            int count = 0;
+            for (int k = first; k < A.P; k += step) { A.slots.push_back(k); count++; }
+            while (A.slots.size() % 8) A.slots.push_back(-1);
+            return (count + 7) / 8;
+        };
+        if (A.fourier) {
+            A.nb_even = add_group(0, 1);
+        } else {
+            A.nb_even = add_group(0, 2);
+            add_group(1, 2);
+        }
+        A.nb = (int)A.slots.size() / 8;
+        A.symmetric_nodes = !A.fourier;
+        for (int i = 0; i < A.n && A.symmetric_nodes; i++)
+            A.symmetric_nodes = A.h_x[i] == -A.h_x[A.n - 1 - i] && A.h_w[i] == A.h_w[A.n - 1 - i];
     }
     pl->grid_rows = 1;
     pl->box_rows = 1;
@@ -369,7 +386,12 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
         if (pl->dim == 2) {
             // Per-block position tables of the 2-D index set for the scatter epilogue of the dense varf
             // (see GemmParams): positions, the order of the 64 entries of a block by position, and the range.
-            const int P0 = pl->ax[0].P, P1 = pl->ax[1].P, nb0 = (P0 + 7) / 8, nb1 = (P1 + 7) / 8;
+            const int P1 = pl->ax[1].P, nb0 = pl->ax[0].nb, nb1 = pl->ax[1].nb;
+            for (int a = 0; a < 2; a++) {
+                Axis& A = pl->ax[a];
+                HB_TRY(A.d_slots.ensure(A.slots.size() * 4));
+                HB_CUDA(cudaMemcpyAsync(A.d_slots.p, A.slots.data(), A.slots.size() * 4, cudaMemcpyHostToDevice, st));
+            }
             std::vector<int> pos((size_t)nb0 * nb1 * 64, -1);
             std::vector<unsigned char> perm((size_t)nb0 * nb1 * 64);
             std::vector<int> range((size_t)nb0 * nb1 * 2);
@@ -378,8 +400,8 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
                     const size_t base = ((size_t)ba * nb1 + bb) * 64;
                     int lo = 0x7fffffff, hi = -1;
                     for (int e = 0; e < 64; e++) {
-                        const int a = 8 * ba + (e >> 3), b = 8 * bb + (e & 7);
-                        const int v = (a < P0 && b < P1) ? pl->iset->lex_to_pos[(size_t)a * P1 + b] : -1;
+                        const int a = pl->ax[0].slots[8 * ba + (e >> 3)], b = pl->ax[1].slots[8 * bb + (e & 7)];
+                        const int v = (a >= 0 && b >= 0) ? pl->iset->lex_to_pos[(size_t)a * P1 + b] : -1;
                         pos[base + e] = v;
                         if (v >= 0) { lo = std::min(lo, v); hi = std::max(hi, v); }
                         perm[base + e] = (unsigned char)e;
@@ -410,17 +432,20 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
 // with p = blocked pair (m0,n0) of axis 0 and q = blocked pair (m1,n1) of axis 1.  When the whole matrix
 // is requested only the blocks with m0 <= n0 are computed and mirrored (A is symmetric, bit for bit:
 // the tables are symmetric in (i,j) and every dot product runs over k in the same order).
-static inline int blocks8(int P) { return (P + 7) / 8; }
 
+// `parity_seg` > 0: the contraction over k0 is halved by parity (symmetric nodes, Gram form): `coef` holds the
+// even part of f in rows [0, K0) and the odd part in rows [parity_seg, parity_seg + K0); a row tile whose block
+// pair has even m0 + n0 reads the first segment of G, an odd one the second.
 static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int K0, int K1, const double* Ltab,
                          const double* Rtab, double* d_out, long long ldo, long long row_begin, long long row_end,
-                         cudaStream_t st) {
+                         int parity_seg, cudaStream_t st) {
     const int P0 = pl->ax[0].P, P1 = pl->ax[1].P;
-    const int nb0 = blocks8(P0), nb1 = blocks8(P1);
+    const int nb0 = pl->ax[0].nb, nb1 = pl->ax[1].nb;
+    const int rows1 = parity_seg > 0 ? parity_seg + K0 : K0;   // rows of the stage-1 product
     const long long nrow = (long long)nb0 * nb0 * 64, ncol = (long long)nb1 * nb1 * 64;
-    HB_TRY(pl->G.ensure((size_t)K0 * ncol * 8));
+    HB_TRY(pl->G.ensure((size_t)rows1 * ncol * 8));
     GemmArgs g1;
-    g1.M = K0; g1.K = K1; g1.N = (int)ncol;
+    g1.M = rows1; g1.K = K1; g1.N = (int)ncol;
     g1.A = coef; g1.lda = ld_coef;
     g1.B = Rtab; g1.ldb = ncol;
     g1.C = pl->G.d(); g1.ldc = ncol;
@@ -435,20 +460,24 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.blkperm = static_cast<const unsigned char*>(pl->blkperm.p);
     g2.blkrange = static_cast<const int2*>(pl->blkrange.p);
     g2.P0 = P0; g2.Pp0 = nb0; g2.P1 = P1; g2.Pp1 = nb1;
+    g2.b_koff_odd = parity_seg; g2.nb_even0 = pl->ax[0].nb_even;
     const bool full = (row_begin == 0 && row_end == pl->n_polys);
     g2.row_begin = (int)row_begin; g2.row_end = full ? 0x7fffffff : (int)row_end;
     g2.symmetric = full ? 1 : 0;
     g2.group_m = 16;   // 16 row tiles (3.3 MB of the left table at C2) stay in L2 while the right table streams
     g2.cfg = 2;   // 64 x 128 tiles: one 8x8 row block per tile
     static const bool pingpong = [] { const char* e = getenv("HB_VARF_PINGPONG"); return !(e && e[0] == '0'); }();
-    if (!pingpong) return timed_gemm(pl, g2, 22, st);   // generic kernel, two CTAs per SM (developer comparison)
+    if (!pingpong) {   // generic kernel, two CTAs per SM (developer comparison); it has no parity split
+        if (parity_seg > 0) { set_error("HB_VARF_PINGPONG=0 needs HB_VARF_PARITY=0"); return HB_ERR_INVALID; }
+        return timed_gemm(pl, g2, 22, st);
+    }
     // persistent ping-pong kernel over the list of needed tiles (cached per row range)
     const long long key[3] = {row_begin, row_end, g2.symmetric};
     if (key[0] != pl->tiles_key[0] || key[1] != pl->tiles_key[1] || key[2] != pl->tiles_key[2]) {
         std::vector<int> list;
         HB_TRY(varf_tile_list(g2, pl->h_blkrange, list));
         pl->n_tiles = (int)(list.size() / 2);
-        HB_TRY(pl->tiles.ensure(std::max<size_t>(list.size(), 2) * 4));
+        HB_TRY(pl->tiles.ensure((list.size() + 2) * 4));   // + one int2 slot: the tile counter of the kernel
         if (!list.empty()) {
             HB_CUDA(cudaMemcpyAsync(pl->tiles.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
             HB_CUDA(cudaStreamSynchronize(st));   // `list` goes out of scope
@@ -504,17 +533,33 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
                                       r1 - r0, cudaMemcpyDeviceToDevice, st));
         return HB_OK;
     }
+    // Parity: psi_k(-x) = (-1)^k psi_k(x) holds bit for bit when the nodes and weights of axis 0 are symmetric,
+    // so L[-x][(m0,n0)] = (-1)^(m0+n0) L[x][(m0,n0)] and the contraction over x0 only needs the non-negative
+    // nodes, against the even or the odd part of f (chosen per row tile, whose 8x8 block has one parity):
+    // half the flops of the dominant stage.
+    static const bool parity_ok = [] { const char* e = getenv("HB_VARF_PARITY"); return !(e && e[0] == '0'); }();
+    static const bool pingpong = [] { const char* e = getenv("HB_VARF_PINGPONG"); return !(e && e[0] == '0'); }();
+    Axis &A0 = pl->ax[0], &A1 = pl->ax[1];
+    const bool parity = parity_ok && pingpong && A0.symmetric_nodes && A0.n >= 2;
+    const int nh = (A0.n + 1) / 2;                       // nodes x >= 0: rows n - nh .. n - 1
     for (int a = 0; a < 2; a++) {
         if (pl->pairB_ok[a]) continue;
-        const Axis& A = pl->ax[a];
-        const int nb = blocks8(A.P);
-        HB_TRY(pl->pairB[a].ensure((size_t)A.n * nb * nb * 64 * 8));
-        HB_TRY(launch_blocked_pair_table(0, A.psi.d(), A.Pp, 0, nullptr, A.n, A.P, nb, pl->pairB[a].d(), st));
+        Axis& A = pl->ax[a];
+        const bool half = (a == 0 && parity);
+        const int rows = half ? nh : A.n, first = half ? A.n - nh : 0;
+        HB_TRY(pl->pairB[a].ensure((size_t)rows * A.nb * A.nb * 64 * 8));
+        HB_TRY(launch_blocked_pair_table(0, A.psi.d() + (size_t)first * A.Pp, A.Pp, 0, nullptr, rows, A.d_slots.i(),
+                                         A.nb, pl->pairB[a].d(), st));
         pl->pairB_ok[a] = true;
     }
-    const Axis &A0 = pl->ax[0], &A1 = pl->ax[1];
-    return varf_dense_2d(pl, d_f, A1.np, A0.n, A1.n, pl->pairB[0].d(), pl->pairB[1].d(), d_out, ldo, row_begin,
-                         row_end, st);
+    if (!parity)
+        return varf_dense_2d(pl, d_f, A1.np, A0.n, A1.n, pl->pairB[0].d(), pl->pairB[1].d(), d_out, ldo, row_begin,
+                             row_end, 0, st);
+    const int seg = (nh + 15) & ~15;                     // the odd segment starts on a k-tile boundary
+    HB_TRY(pl->fsplit.ensure_zero((size_t)(seg + nh) * A1.np * 8, st));
+    HB_TRY(launch_parity_split(d_f, A0.n, nh, seg, A1.np, pl->fsplit.d(), st));
+    return varf_dense_2d(pl, pl->fsplit.d(), A1.np, nh, A1.n, pl->pairB[0].d(), pl->pairB[1].d(), d_out, ldo, row_begin,
+                         row_end, seg, st);
 }
 
 // The reference's algebra (varf.cpp:164-269).
@@ -572,15 +617,16 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
         for (int a = 0; a < 2; a++) {
             if (pl->TB_ok[a]) continue;
             if (a == 1 && pl->ax[1].fourier == pl->ax[0].fourier && pl->ax[1].P == pl->ax[0].P) continue;  // shares TB[0]
-            const int nb = blocks8(pl->ax[a].P);
+            const int nb = pl->ax[a].nb;
             const double* T = pl->ax[a].fourier ? pl->Tf.d() : pl->T.d();
             HB_TRY(pl->TB[a].ensure((size_t)(2 * N + 1) * nb * nb * 64 * 8));
-            HB_TRY(launch_blocked_pair_table(1, T, pl->TPp, plane, nullptr, 2 * N + 1, pl->ax[a].P, nb, pl->TB[a].d(), st));
+            HB_TRY(launch_blocked_pair_table(1, T, pl->TPp, plane, nullptr, 2 * N + 1, pl->ax[a].d_slots.i(), nb,
+                                             pl->TB[a].d(), st));
             pl->TB_ok[a] = true;
         }
         const double* T0 = pl->TB[0].d();
         const double* T1 = pl->TB_ok[1] ? pl->TB[1].d() : pl->TB[0].d();
-        return varf_dense_2d(pl, pl->Hc.d(), ldc, E0, E1, T0, T1, d_out, ldo, row_begin, row_end, st);
+        return varf_dense_2d(pl, pl->Hc.d(), ldc, E0, E1, T0, T1, d_out, ldo, row_begin, row_end, 0, st);
     }
     HB_TRY(pl->kept_alpha.ensure(std::max<size_t>(kept_alpha.size(), 1) * 4));
     HB_TRY(pl->kept_val.ensure(std::max<size_t>(kept_val.size(), 1) * 8));

@@ -49,6 +49,12 @@ struct Axis {
     DevBuf plain, wgt;    // [n][Pp]   phi_k(x_i), w_i*phi_k(x_i)
     DevBuf plainT, wgtT;  // [P][np]
     DevBuf psi;           // [n][Pp]   sqrt(w_i)*phi_k(x_i), built on first Gram-form varf
+    // dense 2-D varf: slots of the 8x8-blocked pair tables (slot -> basis index, -1 padding).  Hermite axes list
+    // the even indices first and start the odd ones on a block boundary: `nb_even` blocks of even indices.
+    std::vector<int> slots;
+    DevBuf d_slots;
+    int nb = 0, nb_even = 0;
+    bool symmetric_nodes = false;   // x_i == -x_{n-1-i} and w_i == w_{n-1-i} bit for bit (non-Fourier axis)
 };
 
 }  // namespace hb
@@ -67,6 +73,7 @@ struct hb_plan {
     hb::DevBuf T, Tf;           // triple products [2N+1][N+1][TPp] (Hermite / Fourier)
     hb::DevBuf midx, blkpos, blkperm, blkrange, Hf, Hc, G, kept_alpha, kept_val, pair[2], tmp;
     hb::DevBuf pairB[2], TB[2];     // blocked pair tables (dim 2 dense varf): Gram / triple products per axis
+    hb::DevBuf fsplit;              // even / odd parts of f along axis 0 (parity-halved Gram contraction)
     bool pairB_ok[2] = {false, false}, TB_ok[2] = {false, false};
     std::vector<double> h_Hf;
     std::vector<int> h_blkrange;      // host copy of blkrange (tile lists of the stage-2 kernel)

@@ -16,8 +16,8 @@
 //
 // Tiles are 64 x 128 (one 8x8 block of (m0,n0) pairs by two 8x8 blocks of (m1,n1) pairs) with K = number of
 // nodes (Gram form) or 2N+1 (reference algebra); only needed tiles (owned rows, upper half in symmetric mode,
-// non-empty blocks of the index set) are listed by the host, in an L2-friendly order, and dealt round-robin to
-// the 2 x gridDim groups.  Shared memory: 3-stage TMA ring per group (2 x 72 KB), one staging buffer for the
+// non-empty blocks of the index set) are listed by the host, in an L2-friendly order, and drawn dynamically by
+// the 2 x gridDim groups from a global counter.  Shared memory: 3-stage TMA ring per group (2 x 72 KB), one staging buffer for the
 // epilogue (65 KB) guarded by a flag, position tables of the current tile.
 #include <cstdlib>
 
@@ -47,7 +47,8 @@ __device__ __forceinline__ void group_sync(int g) {   // the 128 consumer thread
 
 __global__ void __launch_bounds__(384, 1)
     varf2d_pingpong_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                           const GemmParams p, const int2* __restrict__ tiles, int n_tiles) {
+                           const GemmParams p, const int2* __restrict__ tiles, int n_tiles,
+                           int* __restrict__ counter) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(384, 1)
     const uint32_t table_off = staging_off + PP_STAGING_BYTES;
     const uint32_t bar_off = table_off + 2 * PP_TABLE_BYTES;
     const uint32_t flag_off = bar_off + 2 * 2 * PP_STAGES * 8;
-    int* flags = reinterpret_cast<int*>(smem_gen + flag_off);   // [1], [2] progress of group 0, 1; [3] staging busy
+    int* flags = reinterpret_cast<int*>(smem_gen + flag_off);   // [1], [2] progress of group 0, 1; [3] staging busy;
+                                                                // [4+2g], [5+2g] tile queue of group g; [8+g] tiles published
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KT = (p.K + GEMM_BK - 1) / GEMM_BK;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(384, 1)
                 mbar_init(smem_base + bar_off + 8 * (g * 2 * PP_STAGES + s), 1);                          // full
                 mbar_init(smem_base + bar_off + 8 * (g * 2 * PP_STAGES + PP_STAGES + s), PP_GROUP_WARPS);  // empty
             }
-        flags[0] = 0; flags[1] = 0; flags[2] = 0; flags[3] = 0;
+        for (int i = 0; i < 16; i++) flags[i] = 0;
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -76,7 +78,6 @@ __global__ void __launch_bounds__(384, 1)
     const int g = warp >= 8 ? warp - 8 : warp >> 2;            // group of this warp
     const uint32_t ring = smem_base + g * PP_RING_BYTES;
     const uint32_t full0 = smem_base + bar_off + 8 * (g * 2 * PP_STAGES), empty0 = full0 + 8 * PP_STAGES;
-    const int first = 2 * blockIdx.x + g, step = 2 * gridDim.x;
 
     // Register budget: 384 threads start with 168 registers each; the producer warp group (warps 8-11, two of
     // them idle) gives most of its share back and the two consumer groups grow to 232, which holds the 128
@@ -89,9 +90,18 @@ __global__ void __launch_bounds__(384, 1)
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
             int it = 0;
-            for (int ti = first; ti < n_tiles; ti += step) {
+            for (int n = 0;; n++) {
+                // tiles are handed out dynamically: the consumer group publishes the index of its next tile one
+                // tile ahead (see below), so the producer runs on across tile boundaries
+                while (ld_volatile(flags + 8 + g) < n + 1) {
+                }
+                const int ti = ld_volatile(flags + 4 + 2 * g + (n & 1));
+                if (ti >= n_tiles) break;
                 const int2 tile = tiles[ti];
                 const int m_base = tile.x * PP_BM, n_base = tile.y * PP_BN;
+                // parity-halved contraction: odd (m0 + n0) row blocks read the odd segment of B
+                const int pb0 = tile.x / p.Pp0, pb1 = tile.x - pb0 * p.Pp0;
+                const int kb = ((pb0 >= p.nb_even0) != (pb1 >= p.nb_even0)) ? p.b_koff_odd : 0;
                 for (int kt = 0; kt < KT; kt++, it++) {
                     const int s = it % PP_STAGES;
                     if (it >= PP_STAGES) mbar_wait(empty0 + 8 * s, ((it / PP_STAGES) - 1) & 1);
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(384, 1)
 #pragma unroll
                     for (int q = 0; q < PP_BM / 16; q++) tma_load_3d(sA + q * 2048, &tmA, full, m_base + 16 * q, k0, 0);
 #pragma unroll
-                    for (int q = 0; q < PP_BN / 16; q++) tma_load_3d(sB + q * 2048, &tmB, full, n_base + 16 * q, k0, 0);
+                    for (int q = 0; q < PP_BN / 16; q++) tma_load_3d(sB + q * 2048, &tmB, full, n_base + 16 * q, kb + k0, 0);
                 }
             }
         }
@@ -134,8 +144,24 @@ __global__ void __launch_bounds__(384, 1)
     unsigned char* s_colperm = s_rowperm + 128;
     const int gt = threadIdx.x & 127;                           // thread index inside the group
 
+    // Dynamic tile scheduling (the tiles differ in scatter cost and the memory system is the bottleneck, so a
+    // static deal leaves some SMs 20 % behind): thread 0 of the group draws tile indices from a global counter,
+    // one tile ahead, and publishes them to the group and to its producer warp through a two-slot queue.
+    if (gt == 0) {
+        flags[4 + 2 * g] = atomicAdd(counter, 1);
+        __threadfence_block();
+        st_volatile(flags + 8 + g, 1);
+    }
     int it = 0, n_done = 0;
-    for (int ti = first; ti < n_tiles; ti += step) {
+    for (int n = 0;; n++) {
+        group_sync(g);                                          // slot n & 1 is published; slot (n+1) & 1 is free
+        const int ti = ld_volatile(flags + 4 + 2 * g + (n & 1));
+        if (ti >= n_tiles) break;
+        if (gt == 0) {
+            flags[4 + 2 * g + ((n + 1) & 1)] = atomicAdd(counter, 1);
+            __threadfence_block();
+            st_volatile(flags + 8 + g, n + 2);
+        }
         const int2 tile = tiles[ti];
         const int n_base = tile.y * PP_BN;
         const int bm0 = tile.x / p.Pp0, bn0 = tile.x - bm0 * p.Pp0;
@@ -250,7 +276,7 @@ __global__ void __launch_bounds__(384, 1)
                 const double* Srow = Sc + i * 8 * PP_SP + k * 8;
 #pragma unroll
                 for (int h = 0; h < 2; h++)
-                    if (c[h] >= 0 && !(p.symmetric && diag && i > jj[h])) orow[c[h]] = Srow[soff[h]];
+                    if (c[h] >= 0 && !(p.symmetric && diag && i > jj[h]) && !(p.debug & 1)) orow[c[h]] = Srow[soff[h]];
             }
         }
         if (p.trace && gt == 0) t_direct = global_ns();
@@ -276,7 +302,7 @@ __global__ void __launch_bounds__(384, 1)
                     const double* Scol = Sc + j * PP_SP + l;
 #pragma unroll
                     for (int h = 0; h < 2; h++)
-                        if (r[h] >= 0 && !(diag && ii[h] >= j)) orow[r[h]] = Scol[soff[h]];
+                        if (r[h] >= 0 && !(diag && ii[h] >= j) && !(p.debug & 2)) orow[r[h]] = Scol[soff[h]];
                 }
             }
         }
@@ -299,7 +325,12 @@ __global__ void __launch_bounds__(384, 1)
 
 }  // namespace
 
-// List of needed tiles in the order they should run: groups of `group_m` tile rows, tile row fastest.
+// List of needed tiles in the order they are handed out: groups of `group_m` tile rows, tile row fastest inside a
+// group.  Adjacent tile rows are adjacent n0 blocks, whose 64-byte runs are neighbours in the output rows, and a
+// group of 16 row tiles (3.3 MB of the left table at C2) stays in L2 while the right table streams.  Orders binned
+// by output super-blocks, streaming stores and L2 eviction hints were all measured and were no better: with both
+// the direct and the mirrored half written, the scatter of 64-byte runs over a 13 GB matrix sustains ~0.7 TB/s
+// and is what bounds the kernel once parity has halved the flops (compute alone: 12.2 ms at C2 cube).
 int varf_tile_list(const GemmArgs& a, const std::vector<int>& blkrange, std::vector<int>& out) {
     const int tiles_m = (a.M + PP_BM - 1) / PP_BM, tiles_n = (a.N + PP_BN - 1) / PP_BN;
     const int gm = a.group_m > 0 ? a.group_m : 1;
@@ -332,7 +363,8 @@ int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cuda
         return HB_ERR_ALIGN;
     CUtensorMap tmA, tmB;
     HB_TRY(make_map(&tmA, a.A, a.M, a.K, 1, a.lda, (uint64_t)a.lda * a.K, 16, GEMM_BK));
-    HB_TRY(make_map(&tmB, a.B, a.N, a.K, 1, a.ldb, (uint64_t)a.ldb * a.K, 16, GEMM_BK));
+    const int b_rows = a.b_koff_odd > 0 ? a.b_koff_odd + a.K : a.K;   // B holds two k-segments when the parity split is on
+    HB_TRY(make_map(&tmB, a.B, a.N, b_rows, 1, a.ldb, (uint64_t)a.ldb * b_rows, 16, GEMM_BK));
     GemmParams p = {};
     p.M = a.M; p.N = a.N; p.K = a.K; p.batch = 1;
     p.C = a.C; p.ldc = a.ldc;
@@ -340,8 +372,10 @@ int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cuda
     p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkrange = a.blkrange;
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.symmetric = a.symmetric; p.row_begin = a.row_begin; p.row_end = a.row_end;
+    p.b_koff_odd = a.b_koff_odd; p.nb_even0 = a.nb_even0;
     p.alpha = a.alpha;
     p.trace = gemm_get_trace();
+    { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }   // developer switch: bit0 / bit1 drop the direct / mirrored stores
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(varf2d_pingpong_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM) != cudaSuccess)
@@ -352,7 +386,9 @@ int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cuda
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(sms, (n_tiles + 1) / 2);
-    varf2d_pingpong_kernel<<<grid, 384, PP_SMEM, stream>>>(tmA, tmB, p, d_tiles, n_tiles);
+    int* counter = reinterpret_cast<int*>(const_cast<int2*>(d_tiles) + n_tiles);   // one spare entry after the list
+    HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+    varf2d_pingpong_kernel<<<grid, 384, PP_SMEM, stream>>>(tmA, tmB, p, d_tiles, n_tiles, counter);
     return launch_status();
 }
 

@@ -288,3 +288,36 @@ def test_varf_row_blocks_equal_full_matrix(index_set, mode):
         assert part.shape == (hi - lo, n)
         assert np.array_equal(part, full[lo:hi]), (lo, hi)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("n", [60, 61])
+@pytest.mark.parametrize("index_set", ["triangle", "cube", "rectangle", "cross"])
+def test_varf_gram_parity_halved_contraction(core, ref, n, index_set):
+    """Bit-symmetric nodes and weights (hermipy_b200.lib.hermegauss) switch the Gram contraction over x0 to the
+    non-negative nodes against the even / odd parts of f; f here has no symmetry of its own.  Odd and even n
+    (with and without the node x = 0)."""
+    from hermipy_b200 import lib
+    x, w = lib.hermegauss(n)
+    assert np.array_equal(x, -x[::-1]) and np.array_equal(w, w[::-1])
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    V = X ** 4 / 4 - X ** 3 / 3 + X * Y / 2 + Y ** 3 - Y + 0.7
+    degree = 19
+    G = core.varf(degree, V, [x, x], [w, w], index_set=index_set, mode="gram")
+    R = ref.varf(degree, V.ravel(), [x, x], [w, w], index_set=index_set)
+    assert rel_err(G, R) < TOL
+    assert np.array_equal(G, G.T)
+    # a dense non-polynomial f: against the plain quadrature sum in 80-bit arithmetic
+    f = np.exp(-(X ** 2 + Y ** 2) / 9) * (1 + np.sin(X + 0.3 * Y))
+    G = core.varf(degree, f, [x, x], [w, w], index_set="cube", mode="gram")
+    xl, wl = x.astype(np.longdouble), w.astype(np.longdouble)
+    phi = np.zeros((n, degree + 1), dtype=np.longdouble)
+    phi[:, 0], phi[:, 1] = 1, xl
+    for k in range(1, degree):
+        phi[:, k + 1] = (xl * phi[:, k] - np.sqrt(np.longdouble(k)) * phi[:, k - 1]) / np.sqrt(np.longdouble(k + 1))
+    idx = core.iterator_list_indices(2, degree, index_set="cube")
+    rng = np.random.default_rng(n)
+    fl = f.astype(np.longdouble)
+    for r, c in zip(rng.integers(0, len(idx), 40), rng.integers(0, len(idx), 40)):
+        (m0, m1), (n0, n1) = idx[r], idx[c]
+        exact = float((wl * phi[:, m0] * phi[:, n0]) @ fl @ (wl * phi[:, m1] * phi[:, n1]))
+        assert abs(G[r, c] - exact) < 1e-13 * max(1.0, np.abs(G).max()), (r, c)
