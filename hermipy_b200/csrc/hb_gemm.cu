@@ -116,7 +116,8 @@ static int tuned_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
     static const bool enabled = [] { const char* e = getenv("HB_GEMM_AUTOTUNE"); return !(e && e[0] == '0'); }();
     if (!enabled || t[order[0]] > 150.0 || a.block_rows > 0 || a.epi == EPI_VARF2D) return order[0];
     const TuneKey key{a.M, a.N, a.K, a.batch,
-                      (a.a_mmajor ? 1 : 0) | (a.epi << 1) | ((a.strideA == 0) << 4) | ((a.strideB == 0) << 5)};
+                      (a.a_mmajor ? 1 : 0) | (a.epi << 1) | ((a.strideA == 0) << 4) | ((a.strideB == 0) << 5) |
+                          ((a.col_stride > 1) << 6)};
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     auto it = g_tuned.find(key);
     if (it != g_tuned.end()) return it->second;
@@ -168,6 +169,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     p.alpha = a.alpha;
     p.block_rows = a.block_rows;
+    p.col_stride = a.col_stride > 0 ? a.col_stride : 1; p.col_offset = a.col_offset;
     for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.blocks[i] = a.blocks[i];
     if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) return HB_ERR_INVALID;
     int cfg = a.cfg;

@@ -65,6 +65,7 @@ struct GemmParams {
     // The block pointers may be peer-GPU addresses (NVLink P2P): this is how a GEMM's epilogue performs
     // the all-to-all of the sharded transform.
     int block_rows;          // 0 = off
+    int col_stride, col_offset;   // EPI_STORE: column c is stored at col_offset + c * col_stride (1, 0 = plain)
     double* blocks[GEMM_MAX_BLOCKS];
 };
 
@@ -395,7 +396,14 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
             const bool has1 = (col + 1 < p.N);
             if constexpr (EPI == EPI_STORE) {
                 double* dst = (p.block_rows ? p.blocks[row / p.block_rows] + (long long)(row % p.block_rows) * p.ldc
-                                            : p.C + (long long)row * p.ldc) + (long long)b * p.strideC + col;
+                                            : p.C + (long long)row * p.ldc) + (long long)b * p.strideC;
+                if (p.col_stride != 1) {   // interleaved output (even / odd coefficients of the parity transform)
+                    dst += p.col_offset + (long long)col * p.col_stride;
+                    dst[0] = v0;
+                    if (has1) dst[p.col_stride] = v1;
+                    continue;
+                }
+                dst += col;
                 if (has1 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
                     *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
                 } else {

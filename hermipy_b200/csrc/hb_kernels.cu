@@ -174,7 +174,7 @@ __global__ void parity_split_kernel(const double* __restrict__ f, int n, int nh,
     const double a = f[(long long)xp * pitch + c];
     const double b = (xm == xp) ? 0.0 : f[(long long)xm * pitch + c];
     out[(long long)h * pitch + c] = a + b;
-    out[(long long)(seg + h) * pitch + c] = (xm == xp) ? 0.0 : a - b;
+    out[(long long)(seg + h) * pitch + c] = (xm == xp) ? a * 0.0 : a - b;   // keeps a NaN / inf of f visible, as 0 * f
 }
 
 int launch_parity_split(const double* f, int n, int nh, int seg, long long pitch, double* out, cudaStream_t s) {
@@ -236,6 +236,74 @@ int launch_triple_products(int N, int Pp, double* T, cudaStream_t s) {
     if (cudaMemsetAsync(T, 0, bytes, s) != cudaSuccess) return HB_ERR_CUDA;
     const int smem = 3 * (2 * N + 3) * 8;
     triple_products_kernel<<<N + 1, 256, smem, s>>>(N, Pp, T);
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parity helpers of the 1-D transform on a symmetric node set (x_i = -x_{n-1-i}, w_i = w_{n-1-i}): phi_k(-x) =
+// (-1)^k phi_k(x), so even coefficients only see the even part of f and odd ones the odd part, both contracted
+// over the nh = ceil(n/2) non-negative nodes lo .. n-1 (lo = n - nh; the node x = 0 of an odd rule is taken once).
+//   split : fe[b][h] = f[b][lo+h] + f[b][n-1-lo-h],  fo[b][h] = f[b][lo+h] - f[b][n-1-lo-h]
+//   merge : f[b][lo+h] = ge[b][h] + go[b][h],        f[b][n-1-lo-h] = ge[b][h] - go[b][h]
+__global__ void rows_parity_split_kernel(const double* __restrict__ f, long long f_stride, int n, int nh,
+                                         double* __restrict__ fe, double* __restrict__ fo, long long h_stride,
+                                         long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long b = idx / nh;
+    const int h = (int)(idx - b * nh);
+    const int xp = n - nh + h, xm = n - 1 - xp;
+    const double a = f[b * f_stride + xp];
+    const double c = (xm == xp) ? 0.0 : f[b * f_stride + xm];
+    fe[b * h_stride + h] = a + c;
+    fo[b * h_stride + h] = (xm == xp) ? a * 0.0 : a - c;   // 0 at the node x = 0, NaN if f is not finite there (as 0 * f)
+}
+
+__global__ void rows_parity_merge_kernel(const double* __restrict__ ge, const double* __restrict__ go,
+                                         long long h_stride, int n, int nh, double* __restrict__ f,
+                                         long long f_stride, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long b = idx / nh;
+    const int h = (int)(idx - b * nh);
+    const int xp = n - nh + h, xm = n - 1 - xp;
+    const double e = ge[b * h_stride + h], o = go[b * h_stride + h];
+    f[b * f_stride + xp] = e + o;
+    if (xm != xp) f[b * f_stride + xm] = e - o;
+}
+
+// dst[r][c] = src[(r0 + r*rs)*src_ld + c0 + c*cs] for r < rows, c < cols; pad columns up to dst_ld are zeroed
+__global__ void strided_copy_kernel(const double* __restrict__ src, long long src_ld, int r0, int rs, int c0, int cs,
+                                    double* __restrict__ dst, long long dst_ld, long long rows, int cols,
+                                    long long src_bstride, long long dst_bstride) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * dst_ld) return;
+    const long long r = idx / dst_ld;
+    const int c = (int)(idx - r * dst_ld);
+    const double* sb = src + blockIdx.y * src_bstride;
+    dst[blockIdx.y * dst_bstride + idx] = (c < cols) ? sb[(r0 + r * rs) * src_ld + c0 + (long long)c * cs] : 0.0;
+}
+
+int launch_rows_parity_split(const double* f, long long f_stride, int n, int nh, double* fe, double* fo,
+                             long long h_stride, int batch, cudaStream_t s) {
+    const long long total = (long long)batch * nh;
+    rows_parity_split_kernel<<<cdiv(total, 256), 256, 0, s>>>(f, f_stride, n, nh, fe, fo, h_stride, total);
+    return launch_status();
+}
+
+int launch_rows_parity_merge(const double* ge, const double* go, long long h_stride, int n, int nh, double* f,
+                             long long f_stride, int batch, cudaStream_t s) {
+    const long long total = (long long)batch * nh;
+    rows_parity_merge_kernel<<<cdiv(total, 256), 256, 0, s>>>(ge, go, h_stride, n, nh, f, f_stride, total);
+    return launch_status();
+}
+
+int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int c0, int cs, double* dst,
+                        long long dst_ld, long long rows, int cols, int batch, long long src_bstride,
+                        long long dst_bstride, cudaStream_t s) {
+    dim3 grid(cdiv(rows * dst_ld, 256), batch);
+    strided_copy_kernel<<<grid, 256, 0, s>>>(src, src_ld, r0, rs, c0, cs, dst, dst_ld, rows, cols, src_bstride,
+                                             dst_bstride);
     return launch_status();
 }
 

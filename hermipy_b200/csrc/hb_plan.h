@@ -66,6 +66,9 @@ struct hb_plan {
     long long n_polys = 0, grid_rows = 0 /* n_0..n_{d-2} */, grid_size = 0, box_rows = 0, box_size = 0;
     hb::DevBuf lut_box;  // int32[box_size]: padded lexicographic box -> position in the set, -1 absent
     hb::DevBuf ws[2];
+    // 1-D transform on a symmetric node set: per-parity tables (built on first use) and work buffers
+    hb::DevBuf parWe, parWo, parPe, parPo, parA, parB;
+    bool par_tables = false;
     hb::DevBuf nodes_cat;  // all axes' nodes, concatenated (discretize)
     // --- varf state (lazy) ---
     hb_plan* plan2 = nullptr;   // transform plan at degree 2*degree (Hf), owned

@@ -374,6 +374,7 @@ int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cuda
     p.symmetric = a.symmetric; p.row_begin = a.row_begin; p.row_end = a.row_end;
     p.b_koff_odd = a.b_koff_odd; p.nb_even0 = a.nb_even0;
     p.alpha = a.alpha;
+    p.col_stride = 1;
     p.trace = gemm_get_trace();
     { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }   // developer switch: bit0 / bit1 drop the direct / mirrored stores
     static bool attr_set = false;
