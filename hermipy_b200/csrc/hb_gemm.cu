@@ -170,6 +170,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.alpha = a.alpha;
     p.block_rows = a.block_rows;
     p.col_stride = a.col_stride > 0 ? a.col_stride : 1; p.col_offset = a.col_offset;
+    p.row_stride = a.row_stride > 0 ? a.row_stride : 1; p.row_offset = a.row_offset;
     for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.blocks[i] = a.blocks[i];
     if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) return HB_ERR_INVALID;
     int cfg = a.cfg;

@@ -66,6 +66,7 @@ struct GemmParams {
     // the all-to-all of the sharded transform.
     int block_rows;          // 0 = off
     int col_stride, col_offset;   // EPI_STORE: column c is stored at col_offset + c * col_stride (1, 0 = plain)
+    int row_stride, row_offset;   // EPI_LUT: GEMM row r is row row_offset + r * row_stride of the look-up table
     double* blocks[GEMM_MAX_BLOCKS];
 };
 
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
             const int im = wm * MI + mi;
             const int row = m_base + (A_MMAJOR ? (16 * (im >> 1) + 4 * (im & 1) + cm) : (wm * WM + 8 * mi + rm));
             if (row >= p.M) continue;
-            const int* __restrict__ lrow = p.lut + (long long)row * p.N;
+            const int* __restrict__ lrow = p.lut + (long long)(p.row_offset + row * p.row_stride) * p.N;
             int2 idx[NJ];
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {

@@ -30,6 +30,7 @@ struct GemmArgs {
     int block_rows = 0;              // EPI_STORE: rows [i*block_rows, (i+1)*block_rows) -> blocks[i] (C unused)
     double* blocks[16] = {nullptr};
     int col_stride = 1, col_offset = 0;   // EPI_STORE: column c goes to col_offset + c*col_stride
+    int row_stride = 1, row_offset = 0;   // EPI_LUT: GEMM row r uses look-up-table row row_offset + r*row_stride
     int group_m = 1;                 // tile rows per rasterisation group (L2 locality of big GEMMs)
     int cfg = -1;  // -1 auto (cost model), else index into the tile-configuration table of hb_gemm.cu
 };

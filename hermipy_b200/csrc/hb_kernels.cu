@@ -260,7 +260,7 @@ __global__ void rows_parity_split_kernel(const double* __restrict__ f, long long
 }
 
 __global__ void rows_parity_merge_kernel(const double* __restrict__ ge, const double* __restrict__ go,
-                                         long long h_stride, int n, int nh, double* __restrict__ f,
+                                         long long h_stride, int n, int nh, int n_pad, double* __restrict__ f,
                                          long long f_stride, long long total) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -270,6 +270,8 @@ __global__ void rows_parity_merge_kernel(const double* __restrict__ ge, const do
     const double e = ge[b * h_stride + h], o = go[b * h_stride + h];
     f[b * f_stride + xp] = e + o;
     if (xm != xp) f[b * f_stride + xm] = e - o;
+    if (h == 0)
+        for (int c = n; c < n_pad; c++) f[b * f_stride + c] = 0.0;   // pad columns of the row (16-byte pitch)
 }
 
 // dst[r][c] = src[(r0 + r*rs)*src_ld + c0 + c*cs] for r < rows, c < cols; pad columns up to dst_ld are zeroed
@@ -284,6 +286,54 @@ __global__ void strided_copy_kernel(const double* __restrict__ src, long long sr
     dst[blockIdx.y * dst_bstride + idx] = (c < cols) ? sb[(r0 + r * rs) * src_ld + c0 + (long long)c * cs] : 0.0;
 }
 
+// The same along a middle axis: in[p][x][c] (x < n, c < cols, batch entries in_stride apart) ->
+//   be[p][h][c] = in[p][lo+h][c] + in[p][n-1-lo-h][c],  bo[p][h][c] = in[p][lo+h][c] - in[p][n-1-lo-h][c]
+// and back: out[p][lo+h][c] = ge + go, out[p][n-1-lo-h][c] = ge - go (out batch entries out_stride apart).
+__global__ void axis_parity_split_kernel(const double* __restrict__ in, long long in_stride, int n, int nh,
+                                         long long cols, double* __restrict__ be, double* __restrict__ bo,
+                                         long long per_batch) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_batch) return;
+    const int h = (int)(idx / cols);
+    const long long c = idx - (long long)h * cols;
+    const int xp = n - nh + h, xm = n - 1 - xp;
+    const double* src = in + blockIdx.y * in_stride;
+    const double a = src[(long long)xp * cols + c];
+    const double b = (xm == xp) ? 0.0 : src[(long long)xm * cols + c];
+    be[blockIdx.y * per_batch + idx] = a + b;
+    bo[blockIdx.y * per_batch + idx] = (xm == xp) ? a * 0.0 : a - b;
+}
+
+__global__ void axis_parity_merge_kernel(const double* __restrict__ ge, const double* __restrict__ go, int n, int nh,
+                                         long long cols, double* __restrict__ out, long long out_stride,
+                                         long long per_batch) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_batch) return;
+    const int h = (int)(idx / cols);
+    const long long c = idx - (long long)h * cols;
+    const int xp = n - nh + h, xm = n - 1 - xp;
+    const double e = ge[blockIdx.y * per_batch + idx], o = go[blockIdx.y * per_batch + idx];
+    double* dst = out + blockIdx.y * out_stride;
+    dst[(long long)xp * cols + c] = e + o;
+    if (xm != xp) dst[(long long)xm * cols + c] = e - o;
+}
+
+int launch_axis_parity_split(const double* in, long long in_stride, int n, int nh, long long cols, int batch,
+                             double* be, double* bo, cudaStream_t s) {
+    const long long per_batch = (long long)nh * cols;
+    dim3 grid(cdiv(per_batch, 256), batch);
+    axis_parity_split_kernel<<<grid, 256, 0, s>>>(in, in_stride, n, nh, cols, be, bo, per_batch);
+    return launch_status();
+}
+
+int launch_axis_parity_merge(const double* ge, const double* go, int n, int nh, long long cols, int batch, double* out,
+                             long long out_stride, cudaStream_t s) {
+    const long long per_batch = (long long)nh * cols;
+    dim3 grid(cdiv(per_batch, 256), batch);
+    axis_parity_merge_kernel<<<grid, 256, 0, s>>>(ge, go, n, nh, cols, out, out_stride, per_batch);
+    return launch_status();
+}
+
 int launch_rows_parity_split(const double* f, long long f_stride, int n, int nh, double* fe, double* fo,
                              long long h_stride, int batch, cudaStream_t s) {
     const long long total = (long long)batch * nh;
@@ -291,10 +341,10 @@ int launch_rows_parity_split(const double* f, long long f_stride, int n, int nh,
     return launch_status();
 }
 
-int launch_rows_parity_merge(const double* ge, const double* go, long long h_stride, int n, int nh, double* f,
-                             long long f_stride, int batch, cudaStream_t s) {
+int launch_rows_parity_merge(const double* ge, const double* go, long long h_stride, int n, int nh, int n_pad,
+                             double* f, long long f_stride, int batch, cudaStream_t s) {
     const long long total = (long long)batch * nh;
-    rows_parity_merge_kernel<<<cdiv(total, 256), 256, 0, s>>>(ge, go, h_stride, n, nh, f, f_stride, total);
+    rows_parity_merge_kernel<<<cdiv(total, 256), 256, 0, s>>>(ge, go, h_stride, n, nh, n_pad, f, f_stride, total);
     return launch_status();
 }
 

@@ -16,10 +16,14 @@ int launch_pair_table(const double* plain, long long ld_ik, const double* w, int
 int launch_triple_products(int N, int Pp, double* T, cudaStream_t s);
 int launch_blocked_pair_table(int mode, const double* src, long long ld, long long plane, const double* w, int rows,
                               const int* slots, int nb, double* out, cudaStream_t s);
+int launch_axis_parity_split(const double* in, long long in_stride, int n, int nh, long long cols, int batch,
+                             double* be, double* bo, cudaStream_t s);
+int launch_axis_parity_merge(const double* ge, const double* go, int n, int nh, long long cols, int batch, double* out,
+                             long long out_stride, cudaStream_t s);
 int launch_rows_parity_split(const double* f, long long f_stride, int n, int nh, double* fe, double* fo,
                              long long h_stride, int batch, cudaStream_t s);
-int launch_rows_parity_merge(const double* ge, const double* go, long long h_stride, int n, int nh, double* f,
-                             long long f_stride, int batch, cudaStream_t s);
+int launch_rows_parity_merge(const double* ge, const double* go, long long h_stride, int n, int nh, int n_pad,
+                             double* f, long long f_stride, int batch, cudaStream_t s);
 int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int c0, int cs, double* dst,
                         long long dst_ld, long long rows, int cols, int batch, long long src_bstride,
                         long long dst_bstride, cudaStream_t s);

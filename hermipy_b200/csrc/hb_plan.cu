@@ -194,10 +194,16 @@ int plan_create(hb_plan** out, int dim, const int* n_pts, int degree, const doub
 // non-negative nodes: two GEMMs of a quarter of the size each instead of one -- half the flops.  The even / odd
 // results are interleaved by the store epilogue (column stride 2); the inverse mirrors it (de-interleave, two
 // GEMMs, butterfly).  The extra passes move 8 (n + P) bytes per function each way, against 2 n P flops saved.
-static bool parity_1d(const hb_plan* pl) {
-    static const bool on = [] { const char* e = getenv("HB_TRANSFORM_PARITY"); return !(e && e[0] == '0'); }();
-    const Axis& A = pl->ax[0];
-    return on && pl->dim == 1 && A.symmetric_nodes && A.n >= 4 && A.P >= 4;
+// HB_TRANSFORM_PARITY: 0 = off, 2 = on for every stage, unset / 1 = on where the stage is large enough for the
+// extra split / merge passes (one read + one write of the operand) to pay off.  Read on every call (tests toggle it).
+static int parity_mode() {
+    const char* e = getenv("HB_TRANSFORM_PARITY");
+    return e && e[0] ? atoi(e) : 1;
+}
+static bool parity_stage(const Axis& A, double stage_flops) {
+    const int mode = parity_mode();
+    if (mode == 0 || !A.symmetric_nodes || A.n < 4 || A.P < 4) return false;
+    return mode == 2 || stage_flops >= 4e9;
 }
 
 struct Parity1D { int nh, nhp, lo, Pe, Po, Pep, Pop; };
@@ -208,70 +214,76 @@ static Parity1D parity_dims(const Axis& A) {
     return d;
 }
 
-static int ensure_parity_tables(hb_plan* pl, cudaStream_t st) {
-    if (pl->par_tables) return HB_OK;
-    const Axis& A = pl->ax[0];
+static int ensure_parity_tables(Axis& A, cudaStream_t st) {
+    if (A.par_tables) return HB_OK;
     const Parity1D d = parity_dims(A);
-    // forward operands [node h][coefficient]: rows lo + h of w*phi, every second column
-    HB_TRY(pl->parWe.ensure((size_t)d.nh * d.Pep * 8));
-    HB_TRY(pl->parWo.ensure((size_t)d.nh * d.Pop * 8));
-    HB_TRY(launch_strided_copy(A.wgt.d(), A.Pp, d.lo, 1, 0, 2, pl->parWe.d(), d.Pep, d.nh, d.Pe, 1, 0, 0, st));
-    HB_TRY(launch_strided_copy(A.wgt.d(), A.Pp, d.lo, 1, 1, 2, pl->parWo.d(), d.Pop, d.nh, d.Po, 1, 0, 0, st));
-    // inverse operands [coefficient][node h]: every second row of phi^T, columns lo + h
-    HB_TRY(pl->parPe.ensure((size_t)d.Pe * d.nhp * 8));
-    HB_TRY(pl->parPo.ensure((size_t)d.Po * d.nhp * 8));
-    HB_TRY(launch_strided_copy(A.plainT.d(), A.np, 0, 2, d.lo, 1, pl->parPe.d(), d.nhp, d.Pe, d.nh, 1, 0, 0, st));
-    HB_TRY(launch_strided_copy(A.plainT.d(), A.np, 1, 2, d.lo, 1, pl->parPo.d(), d.nhp, d.Po, d.nh, 1, 0, 0, st));
-    pl->par_tables = true;
+    HB_TRY(A.pWe.ensure((size_t)d.nh * d.Pep * 8));
+    HB_TRY(A.pWo.ensure((size_t)d.nh * d.Pop * 8));
+    HB_TRY(A.pPhiE.ensure((size_t)d.nh * d.Pep * 8));
+    HB_TRY(A.pPhiO.ensure((size_t)d.nh * d.Pop * 8));
+    HB_TRY(A.pWeT.ensure((size_t)d.Pe * d.nhp * 8));
+    HB_TRY(A.pWoT.ensure((size_t)d.Po * d.nhp * 8));
+    HB_TRY(A.pPe.ensure((size_t)d.Pe * d.nhp * 8));
+    HB_TRY(A.pPo.ensure((size_t)d.Po * d.nhp * 8));
+    // [node h][basis]: rows lo + h, every second column
+    HB_TRY(launch_strided_copy(A.wgt.d(), A.Pp, d.lo, 1, 0, 2, A.pWe.d(), d.Pep, d.nh, d.Pe, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(A.wgt.d(), A.Pp, d.lo, 1, 1, 2, A.pWo.d(), d.Pop, d.nh, d.Po, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(A.plain.d(), A.Pp, d.lo, 1, 0, 2, A.pPhiE.d(), d.Pep, d.nh, d.Pe, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(A.plain.d(), A.Pp, d.lo, 1, 1, 2, A.pPhiO.d(), d.Pop, d.nh, d.Po, 1, 0, 0, st));
+    // [basis][node h]: every second row, columns lo + h
+    HB_TRY(launch_strided_copy(A.wgtT.d(), A.np, 0, 2, d.lo, 1, A.pWeT.d(), d.nhp, d.Pe, d.nh, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(A.wgtT.d(), A.np, 1, 2, d.lo, 1, A.pWoT.d(), d.nhp, d.Po, d.nh, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(A.plainT.d(), A.np, 0, 2, d.lo, 1, A.pPe.d(), d.nhp, d.Pe, d.nh, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(A.plainT.d(), A.np, 1, 2, d.lo, 1, A.pPo.d(), d.nhp, d.Po, d.nh, 1, 0, 0, st));
+    A.par_tables = true;
     return HB_OK;
 }
 
-static int forward_1d_parity(hb_plan* pl, const double* d_f, long long f_stride, int batch, double* d_coef,
-                             long long coef_stride, cudaStream_t st) {
-    const Axis& A = pl->ax[0];
+// Contraction of the LAST grid axis of `rows` rows (pitch f_pitch) into interleaved even / odd coefficients
+// (out row pitch out_pitch): split + two half-size GEMMs.  This is the whole forward transform when dim == 1.
+static int forward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_f, long long f_pitch, long long rows,
+                                    double* d_out, long long out_pitch, int tag, cudaStream_t st) {
     const Parity1D d = parity_dims(A);
-    HB_TRY(ensure_parity_tables(pl, st));
-    HB_TRY(pl->parA.ensure((size_t)batch * d.nhp * 8));
-    HB_TRY(pl->parB.ensure((size_t)batch * d.nhp * 8));
-    HB_TRY(launch_rows_parity_split(d_f, f_stride, A.n, d.nh, pl->parA.d(), pl->parB.d(), d.nhp, batch, st));
-    pl->n_timed = 0;
+    HB_TRY(ensure_parity_tables(A, st));
+    HB_TRY(pl->parA.ensure((size_t)rows * d.nhp * 8));
+    HB_TRY(pl->parB.ensure((size_t)rows * d.nhp * 8));
+    HB_TRY(launch_rows_parity_split(d_f, f_pitch, A.n, d.nh, pl->parA.d(), pl->parB.d(), d.nhp, (int)rows, st));
     for (int par = 0; par < 2; par++) {
         GemmArgs g;
-        g.M = batch; g.K = d.nh; g.N = par ? d.Po : d.Pe;
+        g.M = (int)rows; g.K = d.nh; g.N = par ? d.Po : d.Pe;
         g.A = par ? pl->parB.d() : pl->parA.d(); g.lda = d.nhp;
-        g.B = par ? pl->parWo.d() : pl->parWe.d(); g.ldb = par ? d.Pop : d.Pep;
-        g.C = d_coef; g.ldc = coef_stride;
+        g.B = par ? A.pWo.d() : A.pWe.d(); g.ldb = par ? d.Pop : d.Pep;
+        g.C = d_out; g.ldc = out_pitch;
         g.col_stride = 2; g.col_offset = par;
-        HB_TRY(timed_gemm(pl, g, 1, st));
+        HB_TRY(timed_gemm(pl, g, tag, st));
     }
     return HB_OK;
 }
 
-static int backward_1d_parity(hb_plan* pl, const double* d_coef, long long coef_stride, int batch, double* d_f,
-                              long long f_stride, cudaStream_t st) {
-    const Axis& A = pl->ax[0];
+// Inverse of it: rows of interleaved coefficients (pitch c_pitch) -> grid rows (pitch f_pitch).
+static int backward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_coef, long long c_pitch, long long rows,
+                                     double* d_f, long long f_pitch, int tag, cudaStream_t st) {
     const Parity1D d = parity_dims(A);
-    HB_TRY(ensure_parity_tables(pl, st));
-    // work buffers: de-interleaved coefficients [batch][Pep | Pop], then the two half-grids [batch][nhp] x 2
+    HB_TRY(ensure_parity_tables(A, st));
     const size_t cw = (size_t)d.Pep + d.Pop;
-    HB_TRY(pl->parA.ensure((size_t)batch * cw * 8));
-    HB_TRY(pl->parB.ensure((size_t)batch * 2 * d.nhp * 8));
+    HB_TRY(pl->parA.ensure((size_t)rows * cw * 8));
+    HB_TRY(pl->parB.ensure((size_t)rows * 2 * d.nhp * 8));
     double* ce = pl->parA.d();
-    double* co = ce + (size_t)batch * d.Pep;
+    double* co = ce + (size_t)rows * d.Pep;
     double* ge = pl->parB.d();
-    double* go = ge + (size_t)batch * d.nhp;
-    HB_TRY(launch_strided_copy(d_coef, coef_stride, 0, 1, 0, 2, ce, d.Pep, batch, d.Pe, 1, 0, 0, st));
-    HB_TRY(launch_strided_copy(d_coef, coef_stride, 0, 1, 1, 2, co, d.Pop, batch, d.Po, 1, 0, 0, st));
-    pl->n_timed = 0;
+    double* go = ge + (size_t)rows * d.nhp;
+    HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 0, 2, ce, d.Pep, rows, d.Pe, 1, 0, 0, st));
+    HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 1, 2, co, d.Pop, rows, d.Po, 1, 0, 0, st));
     for (int par = 0; par < 2; par++) {
         GemmArgs g;
-        g.M = batch; g.K = par ? d.Po : d.Pe; g.N = d.nh;
+        g.M = (int)rows; g.K = par ? d.Po : d.Pe; g.N = d.nh;
         g.A = par ? co : ce; g.lda = par ? d.Pop : d.Pep;
-        g.B = par ? pl->parPo.d() : pl->parPe.d(); g.ldb = d.nhp;
+        g.B = par ? A.pPo.d() : A.pPe.d(); g.ldb = d.nhp;
         g.C = par ? go : ge; g.ldc = d.nhp;
-        HB_TRY(timed_gemm(pl, g, 11, st));
+        HB_TRY(timed_gemm(pl, g, tag, st));
     }
-    return launch_rows_parity_merge(ge, go, d.nhp, A.n, d.nh, d_f, f_stride, batch, st);
+    return launch_rows_parity_merge(ge, go, d.nhp, A.n, d.nh, (int)std::min<long long>(A.np, f_pitch), d_f, f_pitch,
+                                    (int)rows, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -281,7 +293,10 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
                  long long coef_stride, cudaStream_t st) {
     if (batch <= 0) return HB_OK;
     const int d = pl->dim;
-    if (d == 1 && parity_1d(pl)) return forward_1d_parity(pl, d_f, f_stride, batch, d_coef, coef_stride, st);
+    if (d == 1 && parity_stage(pl->ax[0], 2.0 * batch * pl->ax[0].n * pl->ax[0].P)) {
+        pl->n_timed = 0;
+        return forward_last_axis_parity(pl, pl->ax[0], d_f, f_stride, batch, d_coef, coef_stride, 1, st);
+    }
     if (d == 1) {
         const Axis& A = pl->ax[0];
         GemmArgs g;
@@ -293,7 +308,7 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         pl->n_timed = 0;
         return timed_gemm(pl, g, 1, st);
     }
-    const Axis& L = pl->ax[d - 1];
+    Axis& L = pl->ax[d - 1];
     long long cols = L.Pp;
     const long long rows1 = pl->grid_rows;
     // workspace: largest intermediate
@@ -308,7 +323,13 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
     }
     HB_TRY(pl->ws[0].ensure(need * 8));
     if (d > 2) HB_TRY(pl->ws[1].ensure(need * 8));
-    {
+    pl->n_timed = 0;
+    const bool flat = (f_stride == rows1 * L.np || batch == 1);
+    if (flat && parity_stage(L, 2.0 * batch * rows1 * L.n * L.P)) {
+        if (L.Pp != L.P)   // the pad column of the interleaved output is not written by the half GEMMs
+            HB_CUDA(cudaMemsetAsync(pl->ws[0].p, 0, (size_t)batch * rows1 * cols * 8, st));
+        HB_TRY(forward_last_axis_parity(pl, L, d_f, L.np, batch * rows1, pl->ws[0].d(), cols, d, st));
+    } else {
         GemmArgs g;
         g.K = L.n; g.N = L.Pp;
         g.A = d_f; g.lda = L.np;
@@ -319,14 +340,40 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         }
         g.B = L.wgt.d(); g.ldb = L.Pp; g.strideB = 0;
         g.C = pl->ws[0].d(); g.ldc = cols;
-        pl->n_timed = 0;
         HB_TRY(timed_gemm(pl, g, d, st));
     }
     int cur = 0;
     long long prefix = (long long)batch * rows1;
     for (int a = d - 2; a >= 0; a--) {
-        const Axis& A = pl->ax[a];
+        Axis& A = pl->ax[a];
         prefix /= A.n;
+        if (parity_stage(A, 2.0 * prefix * A.P * A.n * cols)) {
+            // even / odd parts of the operand along x_a, then out[2 me + par][cols] = W_par^T[me][h] * B_par[h][cols]:
+            // the two results interleave row-wise (row pitch 2 * cols; look-up-table rows for the last stage)
+            const Parity1D q = parity_dims(A);
+            HB_TRY(ensure_parity_tables(A, st));
+            const size_t half = (size_t)prefix * q.nh * cols;
+            HB_TRY(pl->parA.ensure(half * 8));
+            HB_TRY(pl->parB.ensure(half * 8));
+            HB_TRY(launch_axis_parity_split(pl->ws[cur].d(), (long long)A.n * cols, A.n, q.nh, cols, (int)prefix,
+                                            pl->parA.d(), pl->parB.d(), st));
+            for (int par = 0; par < 2; par++) {
+                GemmArgs g;
+                g.M = par ? q.Po : q.Pe; g.K = q.nh; g.N = (int)cols; g.batch = (int)prefix;
+                g.A = par ? A.pWoT.d() : A.pWeT.d(); g.lda = q.nhp; g.strideA = 0;
+                g.B = par ? pl->parB.d() : pl->parA.d(); g.ldb = cols; g.strideB = (long long)q.nh * cols;
+                if (a == 0) {
+                    g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = pl->lut_box.i();
+                    g.row_stride = 2; g.row_offset = par;
+                } else {
+                    g.C = pl->ws[cur ^ 1].d() + (size_t)par * cols; g.ldc = 2 * cols; g.strideC = (long long)A.P * cols;
+                }
+                HB_TRY(timed_gemm(pl, g, 1 + a, st));
+            }
+            cols *= A.P;
+            cur ^= 1;
+            continue;
+        }
         GemmArgs g;
         g.M = A.P; g.K = A.n; g.N = (int)cols; g.batch = (int)prefix;
         g.A = A.wgtT.d(); g.lda = A.np; g.strideA = 0;
@@ -348,7 +395,10 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
                   long long f_stride, cudaStream_t st) {
     if (batch <= 0) return HB_OK;
     const int d = pl->dim;
-    if (d == 1 && parity_1d(pl)) return backward_1d_parity(pl, d_coef, coef_stride, batch, d_f, f_stride, st);
+    if (d == 1 && parity_stage(pl->ax[0], 2.0 * batch * pl->ax[0].n * pl->ax[0].P)) {
+        pl->n_timed = 0;
+        return backward_last_axis_parity(pl, pl->ax[0], d_coef, coef_stride, batch, d_f, f_stride, 11, st);
+    }
     if (d == 1) {
         const Axis& A = pl->ax[0];
         GemmArgs g;
@@ -359,7 +409,7 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
         pl->n_timed = 0;
         return timed_gemm(pl, g, 11, st);
     }
-    const Axis& L = pl->ax[d - 1];
+    Axis& L = pl->ax[d - 1];
     size_t need = (size_t)batch * pl->box_size;
     {
         long long c = L.np, prefix = (long long)batch * pl->box_rows;
@@ -375,20 +425,45 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
     // coefficients in set order -> zero-padded lexicographic box
     HB_TRY(launch_gather_lut(d_coef, coef_stride, pl->lut_box.i(), pl->ws[0].d(), pl->box_size, pl->box_size, batch, st));
     long long cols = L.np;
-    {
+    pl->n_timed = 0;
+    if (parity_stage(L, 2.0 * batch * pl->box_rows * L.n * L.P)) {
+        HB_TRY(backward_last_axis_parity(pl, L, pl->ws[0].d(), L.Pp, batch * pl->box_rows, pl->ws[1].d(), cols, 10 + d, st));
+    } else {
         GemmArgs g;
         g.M = (int)(batch * pl->box_rows); g.K = L.P; g.N = L.np;
         g.A = pl->ws[0].d(); g.lda = L.Pp;
         g.B = L.plainT.d(); g.ldb = L.np;
         g.C = pl->ws[1].d(); g.ldc = cols;
-        pl->n_timed = 0;
         HB_TRY(timed_gemm(pl, g, 10 + d, st));
     }
     int cur = 1;
     long long prefix = (long long)batch * pl->box_rows;
     for (int a = d - 2; a >= 0; a--) {
-        const Axis& A = pl->ax[a];
+        Axis& A = pl->ax[a];
         prefix /= A.P;
+        if (parity_stage(A, 2.0 * prefix * A.P * A.n * cols)) {
+            // g_par[h][cols] = Phi_par[h][me] * cur[2 me + par][cols] (operand rows taken with pitch 2 * cols), then the
+            // butterfly out[lo+h] = g_e + g_o, out[n-1-lo-h] = g_e - g_o
+            const Parity1D q = parity_dims(A);
+            HB_TRY(ensure_parity_tables(A, st));
+            const size_t half = (size_t)prefix * q.nh * cols;
+            HB_TRY(pl->parA.ensure(half * 8));
+            HB_TRY(pl->parB.ensure(half * 8));
+            for (int par = 0; par < 2; par++) {
+                GemmArgs g;
+                g.M = q.nh; g.K = par ? q.Po : q.Pe; g.N = (int)cols; g.batch = (int)prefix;
+                g.A = par ? A.pPhiO.d() : A.pPhiE.d(); g.lda = par ? q.Pop : q.Pep; g.strideA = 0;
+                g.B = pl->ws[cur].d() + (size_t)par * cols; g.ldb = 2 * cols; g.strideB = (long long)A.P * cols;
+                g.C = par ? pl->parB.d() : pl->parA.d(); g.ldc = cols; g.strideC = (long long)q.nh * cols;
+                HB_TRY(timed_gemm(pl, g, 11 + a, st));
+            }
+            double* out = (a == 0) ? d_f : pl->ws[cur ^ 1].d();
+            const long long out_stride = (a == 0) ? f_stride : (long long)A.n * cols;
+            HB_TRY(launch_axis_parity_merge(pl->parA.d(), pl->parB.d(), A.n, q.nh, cols, (int)prefix, out, out_stride, st));
+            cols *= A.n;
+            cur ^= 1;
+            continue;
+        }
         GemmArgs g;
         g.M = A.n; g.K = A.P; g.N = (int)cols; g.batch = (int)prefix;
         g.A = A.plain.d(); g.lda = A.Pp; g.strideA = 0;

@@ -55,6 +55,14 @@ struct Axis {
     DevBuf d_slots;
     int nb = 0, nb_even = 0;
     bool symmetric_nodes = false;   // x_i == -x_{n-1-i} and w_i == w_{n-1-i} bit for bit (non-Fourier axis)
+    // per-parity operand tables of the transform on a symmetric node set (built on first use), with nh = ceil(n/2)
+    // non-negative nodes lo + h and Pe even / Po odd basis functions:
+    //   pWe / pWo     [nh][Pe|Po]  w*phi        forward, this axis last  (B operand)
+    //   pWeT / pWoT   [Pe|Po][nh]  w*phi        forward, other axes      (A operand)
+    //   pPe / pPo     [Pe|Po][nh]  phi          inverse, this axis last  (B operand)
+    //   pPhiE / pPhiO [nh][Pe|Po]  phi          inverse, other axes      (A operand)
+    DevBuf pWe, pWo, pWeT, pWoT, pPe, pPo, pPhiE, pPhiO;
+    bool par_tables = false;
 };
 
 }  // namespace hb
@@ -66,9 +74,7 @@ struct hb_plan {
     long long n_polys = 0, grid_rows = 0 /* n_0..n_{d-2} */, grid_size = 0, box_rows = 0, box_size = 0;
     hb::DevBuf lut_box;  // int32[box_size]: padded lexicographic box -> position in the set, -1 absent
     hb::DevBuf ws[2];
-    // 1-D transform on a symmetric node set: per-parity tables (built on first use) and work buffers
-    hb::DevBuf parWe, parWo, parPe, parPo, parA, parB;
-    bool par_tables = false;
+    hb::DevBuf parA, parB;   // work buffers of the parity stages (even / odd halves)
     hb::DevBuf nodes_cat;  // all axes' nodes, concatenated (discretize)
     // --- varf state (lazy) ---
     hb_plan* plan2 = nullptr;   // transform plan at degree 2*degree (Hf), owned

@@ -321,3 +321,58 @@ def test_varf_gram_parity_halved_contraction(core, ref, n, index_set):
         (m0, m1), (n0, n1) = idx[r], idx[c]
         exact = float((wl * phi[:, m0] * phi[:, n0]) @ fl @ (wl * phi[:, m1] * phi[:, n1]))
         assert abs(G[r, c] - exact) < 1e-13 * max(1.0, np.abs(G).max()), (r, c)
+
+
+@pytest.fixture
+def force_transform_parity(monkeypatch):
+    """Small test problems stay below the size at which the even / odd split of the transform pays off; force it."""
+    monkeypatch.setenv("HB_TRANSFORM_PARITY", "2")
+
+
+@pytest.mark.parametrize("n,degree", [(41, 20), (40, 21), (201, 100), (64, 63)])
+def test_transform_1d_parity_split(core, ref, force_transform_parity, n, degree):
+    x, w = gauss_hermite(n)
+    assert np.array_equal(x, -x[::-1]) and np.array_equal(w, w[::-1])
+    f = np.exp(-x ** 2 / 8) * np.cos(3 * x + 0.4) + 0.1 * x          # no symmetry of its own
+    c = core.transform(degree, f, [x], [w], True)
+    assert rel_err(c, ref.transform(degree, f, [x], [w], True)) < TOL
+    back = core.transform(degree, c, [x], [w], False)
+    want = ref.transform(degree, c, [x], [w], False)
+    assert rel_err(back * np.sqrt(w), want * np.sqrt(w)) < TOL
+    batch = core.transform_batch(degree, np.stack([f, f[::-1], f ** 2]), [x], [w], True)
+    for row, g in zip(batch, (f, f[::-1], f ** 2)):
+        assert rel_err(row, ref.transform(degree, g, [x], [w], True)) < TOL
+
+
+@pytest.mark.parametrize("index_set", SETS)
+def test_transform_2d_parity_split(core, ref, force_transform_parity, index_set):
+    x, w = gauss_hermite(41)
+    y, v = gauss_hermite(36)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    f = np.exp(-(X ** 2 + X * Y + Y ** 2) / 10) * (1 + 0.3 * X - 0.2 * Y)
+    degree = 14
+    c = core.transform(degree, f, [x, y], [w, v], True, index_set=index_set)
+    assert rel_err(c, ref.transform(degree, f.ravel(), [x, y], [w, v], True, index_set=index_set)) < TOL
+    back = core.transform(degree, c, [x, y], [w, v], False, index_set=index_set)
+    want = ref.transform(degree, c, [x, y], [w, v], False, index_set=index_set)
+    sw = np.sqrt(np.outer(w, v)).ravel()
+    assert rel_err(back * sw, want * sw) < TOL
+
+
+@pytest.mark.parametrize("index_set", ["triangle", "cube", "rectangle"])
+def test_transform_3d_parity_split(core, ref, force_transform_parity, index_set):
+    x, w = gauss_hermite(15)
+    y, v = gauss_hermite(14)
+    z, u = gauss_hermite(13)
+    X, Y, Z = np.meshgrid(x, y, z, indexing="ij")
+    f = np.exp(-(X ** 2 + Y ** 2 + Z ** 2) / 8) * (1 + X * Y - Z + 0.5 * Y)
+    degree = 7
+    c = core.transform(degree, f, [x, y, z], [w, v, u], True, index_set=index_set)
+    assert rel_err(c, ref.transform(degree, f.ravel(), [x, y, z], [w, v, u], True, index_set=index_set)) < TOL
+    back = core.transform(degree, c, [x, y, z], [w, v, u], False, index_set=index_set)
+    want = ref.transform(degree, c, [x, y, z], [w, v, u], False, index_set=index_set)
+    sw = np.sqrt(np.einsum("i,j,k->ijk", w, v, u)).ravel()
+    assert rel_err(back * sw, want * sw) < TOL
+    # batch of two through the plan path with a function stride
+    both = core.transform_batch(degree, np.stack([f.ravel(), (f * X).ravel()]), [x, y, z], [w, v, u], True, index_set=index_set)
+    assert rel_err(both[1], ref.transform(degree, (f * X).ravel(), [x, y, z], [w, v, u], True, index_set=index_set)) < TOL
