@@ -325,18 +325,20 @@ __global__ void __launch_bounds__(384, 1)
 
 }  // namespace
 
-// List of needed tiles in the order they are handed out: groups of `group_m` tile rows, tile row fastest inside a
-// group.  Adjacent tile rows are adjacent n0 blocks, whose 64-byte runs are neighbours in the output rows, and a
-// group of 16 row tiles (3.3 MB of the left table at C2) stays in L2 while the right table streams.  Orders binned
-// by output super-blocks, streaming stores and L2 eviction hints were all measured and were no better: with both
-// the direct and the mirrored half written, the scatter of 64-byte runs over a 13 GB matrix sustains ~0.7 TB/s
-// and is what bounds the kernel once parity has halved the flops (compute alone: 12.2 ms at C2 cube).
+// List of needed tiles in the order they are handed out: row tiles in G x G squares of (bm0, bn0), and for every
+// column tile the whole square back to back, so that a square keeps its part of the left table in L2 while the
+// right table streams, and tiles whose 64-byte runs are neighbours in the output (adjacent n0 blocks for the direct
+// entries, adjacent m0 blocks for the mirrored ones) run close together in time.
+// What the order does NOT fix: the runs start on 16-byte but mostly not on 32-byte boundaries, and ncu shows 26 GB
+// read + 26 GB written for the 13 GB matrix of C2/cube (read-modify-write of partial sectors); squares of 2..13,
+// groups of 16 consecutive row tiles, orders binned by output super-blocks, streaming stores and L2 eviction hints
+// all land within 5 % of each other (15.6-16.7 ms).  The scatter pattern itself is dictated by the reference's
+// enumeration order; wider runs would need 128-row tiles (two n0 blocks per tile).
 int varf_tile_list(const GemmArgs& a, const std::vector<int>& blkrange, std::vector<int>& out) {
-    const int tiles_m = (a.M + PP_BM - 1) / PP_BM, tiles_n = (a.N + PP_BN - 1) / PP_BN;
-    const int gm = a.group_m > 0 ? a.group_m : 1;
+    const int tiles_n = (a.N + PP_BN - 1) / PP_BN;
+    static const int G = [] { const char* e = getenv("HB_VARF_GROUP"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
     out.clear();
-    auto needed = [&](int tm, int tn) {
-        const int bm0 = tm / a.Pp0, bn0 = tm - bm0 * a.Pp0;
+    auto needed = [&](int bm0, int bn0, int tn) {
         if (a.symmetric && bm0 > bn0) return false;
         for (int cbl = 0; cbl < PP_BN / 64; cbl++) {
             const int cb = tn * (PP_BN / 64) + cbl;
@@ -348,12 +350,12 @@ int varf_tile_list(const GemmArgs& a, const std::vector<int>& blkrange, std::vec
         }
         return false;
     };
-    for (int m0 = 0; m0 < tiles_m; m0 += gm) {
-        const int rows = std::min(gm, tiles_m - m0);
-        for (int tn = 0; tn < tiles_n; tn++)
-            for (int r = 0; r < rows; r++)
-                if (needed(m0 + r, tn)) { out.push_back(m0 + r); out.push_back(tn); }
-    }
+    for (int m0 = 0; m0 < a.Pp0; m0 += G)
+        for (int n0 = 0; n0 < a.Pp0; n0 += G)
+            for (int tn = 0; tn < tiles_n; tn++)
+                for (int i = m0; i < std::min(m0 + G, a.Pp0); i++)
+                    for (int j = n0; j < std::min(n0 + G, a.Pp0); j++)
+                        if (needed(i, j, tn)) { out.push_back(i * a.Pp0 + j); out.push_back(tn); }
     return HB_OK;
 }
 
