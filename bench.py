@@ -419,9 +419,10 @@ def run_ours(args):
                             "achieved_tflops": flops2 / tl.get(22, np.nan) * 1e-9, "peak_tflops": dgemm_burst,
                             "frac": flops2 / tl.get(22, np.nan) * 1e-9 / dgemm_burst,
                             "survey_equivalent_tflops": survey_flops2 / tl.get(22, np.nan) * 1e-9,
-                            "note": "the scatter of 64-byte runs into the %.1f GB matrix (direct + mirrored half) "
-                                    "sustains ~0.7-0.9 TB/s and bounds the kernel; its compute alone takes 12.2 ms at "
-                                    "C2 cube" % (8e-9 * npol ** 2)},
+                            "note": "bound by the scatter of misaligned 64-byte runs into the %.1f GB matrix (direct + "
+                                    "mirrored half): ~0.8 TB/s, the rate tools/scatter_probe.cu measures for that "
+                                    "pattern; see DESIGN.md 4.3" % (8e-9 * npol ** 2),
+                            "scatter_tbs": 8e-12 * npol ** 2 / (tl.get(22, np.nan) * 1e-3)},
             }
             if args.check:
                 vplan.varf(fV, "gram", out)
