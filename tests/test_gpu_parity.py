@@ -376,3 +376,46 @@ def test_transform_3d_parity_split(core, ref, force_transform_parity, index_set)
     # batch of two through the plan path with a function stride
     both = core.transform_batch(degree, np.stack([f.ravel(), (f * X).ravel()]), [x, y, z], [w, v, u], True, index_set=index_set)
     assert rel_err(both[1], ref.transform(degree, (f * X).ravel(), [x, y, z], [w, v, u], True, index_set=index_set)) < TOL
+
+
+@pytest.mark.parametrize("index_set", ["triangle", "cube", "rectangle"])
+def test_varf_scatter_stays_inside_the_owned_block(index_set):
+    """Guard rows above and below and guard columns to the right of the output block keep their sentinel: the
+    table-driven scatter of the stage-2 kernel (direct and mirrored entries, full matrix and row blocks) writes
+    nothing outside rows [row_begin, row_end) x columns [0, n_polys)."""
+    import torch
+    from hermipy_b200.plan import Plan
+    x, w = gauss_hermite(45)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    f = np.exp(-(X ** 2 + Y ** 2) / 8) * (1 + np.sin(X - 0.5 * Y))
+    plan = Plan(18, [x, x], [w, w], index_set=index_set)
+    fd = plan.pack_grid(f[None])[0]
+    n, guard, pad = plan.n_polys, 3, 5
+    sentinel = -7.25
+    for lo, hi in ((0, n), (0, n // 2), (n // 3, n - 7)):
+        buf = torch.full((hi - lo + 2 * guard, n + pad), sentinel, dtype=torch.float64, device="cuda")
+        view = buf[guard:guard + hi - lo, :n]
+        plan.varf(fd, "gram", out=view, row_begin=lo, row_end=hi)
+        torch.cuda.synchronize()
+        host = buf.cpu().numpy()
+        assert (host[:guard] == sentinel).all() and (host[guard + hi - lo:] == sentinel).all()
+        assert (host[:, n:] == sentinel).all()
+        assert (host[guard:guard + hi - lo, :n] != sentinel).all()     # every owned entry was written
+
+
+def test_transform_batch_respects_strides_and_padding(force_transform_parity):
+    """Plan API with padded batch strides: nothing is written past a function's own coefficient / grid row."""
+    import torch
+    from hermipy_b200.plan import Plan
+    x, w = gauss_hermite(37)
+    plan = Plan(20, [x], [w])
+    B, sentinel = 5, -3.5
+    f = torch.randn(B, plan.grid_size, dtype=torch.float64, device="cuda")
+    coef = torch.full((B, plan.coef_stride + 6), sentinel, dtype=torch.float64, device="cuda")
+    plan.forward(f, coef[:, :plan.coef_stride])
+    host = coef.cpu().numpy()
+    assert (host[:, plan.coef_stride:] == sentinel).all() and (host[:, :21] != sentinel).all()
+    grid = torch.full((B, plan.grid_size + 4), sentinel, dtype=torch.float64, device="cuda")
+    plan.backward(coef[:, :plan.coef_stride], grid[:, :plan.grid_size])
+    hg = grid.cpu().numpy()
+    assert (hg[:, plan.grid_size:] == sentinel).all() and (hg[:, :37] != sentinel).all()
