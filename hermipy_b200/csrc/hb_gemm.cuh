@@ -151,6 +151,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     if constexpr (EPI == EPI_VARF2D) { if (p.trace && threadIdx.x == 0) t_start = global_ns(); }
 
     if (threadIdx.x == 0) {
+        grid_launch_dependents();
         for (int s = 0; s < STAGES; s++) {
             mbar_init(bar_base + 8 * s, 1);
             mbar_init(bar_base + 8 * (STAGES + s), NCW);
@@ -162,6 +163,11 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
 
     const int KT = (p.K + GEMM_BK - 1) / GEMM_BK;
 
+    // Everything above (CTA launch, barrier setup) overlaps the tail of the previous kernel of the stream when
+    // this one was launched programmatically; operands are only read from here on.  Every warp blocks here (a
+    // hardware wait): consumer warps spinning on their mbarriers instead would steal issue slots from the
+    // kernel that is still running.
+    grid_dependency_wait();
     using Regs = GemmRegs<NCW, MIN_CTAS>;
     if (warp >= NCW) {
         if constexpr (Regs::kRealloc) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Regs::kProducer));
@@ -169,6 +175,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         if (warp == NCW && lane == 0) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
+
             for (int kt = 0; kt < KT; kt++) {
                 const int s = kt % STAGES;
                 if (kt >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((kt / STAGES) - 1) & 1);

@@ -1,6 +1,8 @@
 // Host-side launch template of the DMMA/TMA GEMM, shared by the translation units that instantiate the
 // kernel (hb_gemm_inst_*.cu: one per (epilogue, A layout) so that they compile in parallel).
 #pragma once
+#include <cstdlib>
+
 #include "hb_gemm.cuh"
 #include "hb_internal.h"
 #include "hb_plan.h"
@@ -56,7 +58,23 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
             return HB_ERR_CUDA;
         attr_set = true;
     }
-    kern<<<(unsigned)n_cta, (WMc * WNc + 4) * 32, smem, stream>>>(tmA, tmB, p);
+    // Programmatic dependent launch (opt-in, HB_GEMM_PDL=1): the CTA launch and barrier setup of this kernel overlap
+    // the tail of its predecessor in the stream (every warp blocks in griddepcontrol.wait before touching operands).
+    // Measured on B200: C4 1.63 -> 1.60 ms, but the C2 step of five 30-60 us kernels gets SLOWER (170 -> 191 us in a
+    // CUDA graph: the early CTAs take shared memory and registers from the kernel that is still running), so it is
+    // off by default.
+    static const bool pdl = [] { const char* e = getenv("HB_GEMM_PDL"); return e && e[0] == '1'; }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_cta);
+    cfg.blockDim = dim3((WMc * WNc + 4) * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p) != cudaSuccess) return launch_status();
     return launch_status();
 }
 

@@ -64,6 +64,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; `grid_dependency_wait` blocks until the predecessor has
+// completed and its memory is visible (a no-op for a normal launch), `grid_launch_dependents` lets the successor
+// be scheduled once every CTA of this grid has executed it.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // D(8x8) += A(8x4, row) * B(4x8, col), all FP64.  Lane l = 4*g + t holds A[g][t], B[t][g],
 // C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
