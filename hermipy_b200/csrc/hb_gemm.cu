@@ -163,7 +163,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.epi = a.epi; p.lut = a.lut;
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.row_begin = a.row_begin; p.row_end = a.row_end; p.symmetric = a.symmetric;
-    p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkrange = a.blkrange;
+    p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkperm2 = a.blkperm2; p.blkrange = a.blkrange;
     p.b_koff_odd = 0; p.nb_even0 = 0;
     p.trace = g_trace;
     { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }

@@ -48,6 +48,7 @@ struct GemmParams {
     //   blkrange[ba*Pp1 + bb]                        = {smallest, largest} valid position of the block, {0,-1} if none.
     const int* blkpos;
     const unsigned char* blkperm;
+    const unsigned char* blkperm2;   // persistent kernel: joint order of the 128 column entries of a column tile, per bn0
     const int2* blkrange;
     int P0, Pp0;        // basis count of axis 0 and its number of 8-blocks
     int P1, Pp1;        // same for axis 1

@@ -23,6 +23,7 @@ struct GemmArgs {
     // varf scatter epilogue (see GemmParams in hb_gemm.cuh)
     const int* blkpos = nullptr;
     const unsigned char* blkperm = nullptr;
+    const unsigned char* blkperm2 = nullptr;   // [(bn0 * tiles_n + tile_n) * 128 + s]: joint order of a column tile's entries
     const int2* blkrange = nullptr;
     int P0 = 0, Pp0 = 0, P1 = 0, Pp1 = 0, row_begin = 0, row_end = 0, symmetric = 0;
     int b_koff_odd = 0, nb_even0 = 0;   // parity-halved contraction (0 = off): see varf_dense_2d in hb_plan.cu

@@ -576,6 +576,29 @@ static int ensure_varf_tables(hb_plan* pl, cudaStream_t st) {
                     range[((size_t)ba * nb1 + bb) * 2] = hi >= 0 ? lo : 0;
                     range[((size_t)ba * nb1 + bb) * 2 + 1] = hi;
                 }
+            // joint order of the 128 column entries of a column tile (two adjacent column blocks) for every bn0:
+            // entry = cbl * 64 + slot, sorted by output position, so that runs continue across the two blocks
+            // (16-entry runs where the enumeration is consecutive along n1)
+            const int tiles_n = (nb1 * nb1 + 1) / 2;
+            std::vector<unsigned char> perm2((size_t)nb0 * tiles_n * 128);
+            for (int bn0 = 0; bn0 < nb0; bn0++)
+                for (int tn = 0; tn < tiles_n; tn++) {
+                    int key[128];
+                    unsigned char* dst = &perm2[((size_t)bn0 * tiles_n + tn) * 128];
+                    for (int e = 0; e < 128; e++) {
+                        const int cb = 2 * tn + (e >> 6);
+                        int v = -1;
+                        if (cb < nb1 * nb1) {
+                            const int bn1 = cb % nb1;
+                            v = pos[((size_t)bn0 * nb1 + bn1) * 64 + (e & 63)];
+                        }
+                        key[e] = v;
+                        dst[e] = (unsigned char)e;
+                    }
+                    std::sort(dst, dst + 128, [&](unsigned char x, unsigned char y) { return (unsigned)key[x] < (unsigned)key[y]; });
+                }
+            HB_TRY(pl->blkperm2.ensure(perm2.size()));
+            HB_CUDA(cudaMemcpyAsync(pl->blkperm2.p, perm2.data(), perm2.size(), cudaMemcpyHostToDevice, st));
             HB_TRY(pl->blkpos.ensure(pos.size() * 4));
             HB_TRY(pl->blkperm.ensure(perm.size()));
             HB_TRY(pl->blkrange.ensure(range.size() * 4));
@@ -621,6 +644,7 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.epi = EPI_VARF2D;
     g2.blkpos = pl->blkpos.i();
     g2.blkperm = static_cast<const unsigned char*>(pl->blkperm.p);
+    g2.blkperm2 = static_cast<const unsigned char*>(pl->blkperm2.p);
     g2.blkrange = static_cast<const int2*>(pl->blkrange.p);
     g2.P0 = P0; g2.Pp0 = nb0; g2.P1 = P1; g2.Pp1 = nb1;
     g2.b_koff_odd = parity_seg; g2.nb_even0 = pl->ax[0].nb_even;

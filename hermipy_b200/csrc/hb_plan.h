@@ -80,7 +80,7 @@ struct hb_plan {
     hb_plan* plan2 = nullptr;   // transform plan at degree 2*degree (Hf), owned
     int Tdeg = -1, TPp = 0;
     hb::DevBuf T, Tf;           // triple products [2N+1][N+1][TPp] (Hermite / Fourier)
-    hb::DevBuf midx, blkpos, blkperm, blkrange, Hf, Hc, G, kept_alpha, kept_val, pair[2], tmp;
+    hb::DevBuf midx, blkpos, blkperm, blkperm2, blkrange, Hf, Hc, G, kept_alpha, kept_val, pair[2], tmp;
     hb::DevBuf pairB[2], TB[2];     // blocked pair tables (dim 2 dense varf): Gram / triple products per axis
     hb::DevBuf fsplit;              // even / odd parts of f along axis 0 (parity-halved Gram contraction)
     bool pairB_ok[2] = {false, false}, TB_ok[2] = {false, false};

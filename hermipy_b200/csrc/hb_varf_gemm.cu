@@ -36,7 +36,7 @@ constexpr int PP_STAGE_BYTES = PP_A_BYTES + PP_B_BYTES;            // 24 KB
 constexpr int PP_RING_BYTES = PP_STAGES * PP_STAGE_BYTES;          // 72 KB per group
 constexpr int PP_SP = PP_BN + 2;                                   // staging pitch (doubles)
 constexpr int PP_STAGING_BYTES = PP_BM * PP_SP * 8;                // 65 KB
-constexpr int PP_TABLE_BYTES = 2 * (2 * 64 * 4 + 2 * 64);          // per group: row/col positions + permutations
+constexpr int PP_TABLE_BYTES = 2 * (2 * 64 * 4 + 2 * 64) + 128;    // per group: row/col positions, permutations, joint column order
 constexpr int PP_SMEM = 1024 + 2 * PP_RING_BYTES + PP_STAGING_BYTES + 2 * PP_TABLE_BYTES + 2 * 2 * PP_STAGES * 8 + 64;
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(384, 1)
     int* s_colpos = s_rowpos + 128;
     unsigned char* s_rowperm = reinterpret_cast<unsigned char*>(s_colpos + 128);
     unsigned char* s_colperm = s_rowperm + 128;
+    unsigned char* s_colperm2 = s_colperm + 128;   // joint order of both column blocks
     const int gt = threadIdx.x & 127;                           // thread index inside the group
+    const int tiles_n = (p.N + PP_BN - 1) / PP_BN;
 
     // Dynamic tile scheduling (the tiles differ in scatter cost and the memory system is the bottleneck, so a
     // static deal leaves some SMs 20 % behind): thread 0 of the group draws tile indices from a global counter,
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(384, 1)
             }
             s_rowpos[e] = rp; s_colpos[e] = cp;
             s_rowperm[e] = (unsigned char)rperm; s_colperm[e] = (unsigned char)cperm;
+            s_colperm2[e] = __ldg(p.blkperm2 + ((size_t)bn0 * tiles_n + tile.y) * 128 + e);
         }
 
         long long t_tile = 0, t_main0 = 0, t_main1 = 0, t_stage = 0, t_staged = 0, t_direct = 0;
@@ -254,29 +257,37 @@ __global__ void __launch_bounds__(384, 1)
         if (p.trace && gt == 0) t_staged = global_ns();
         const bool diag = (bm0 == bn0);
         // direct entries A[idx(m0,m1)][idx(n0,n1)] = S[(m0l,n0l)][(m1l,n1l)]: one warp per output row, lanes walk the
-        // 64 columns of the block in position order (coalesced whatever the enumeration of the set is).  What a
-        // lane needs about its two columns does not depend on the row and is read once per column block.
-        for (int cbl = 0; cbl < 2; cbl++) {
-            const double* Sc = S + cbl * 64;
-            int c[2], soff[2], jj[2];
+        // 128 columns of BOTH column blocks in position order (coalesced whatever the enumeration of the set is;
+        // where it is consecutive along n1 the runs continue across the two blocks: 16 entries = 128 bytes).  What
+        // a lane needs about its four columns does not depend on the row and is read once per tile.
+        {
+            // per lane: its four column entries (of 128, both column blocks, in position order)
+            int c[4], soff[4], jj[4], cb_[4];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int ec = s_colperm[cbl * 64 + lane + 32 * h];
-                c[h] = s_colpos[cbl * 64 + ec];
+            for (int h = 0; h < 4; h++) {
+                const int e = s_colperm2[lane + 32 * h];
+                const int ec = e & 63;
+                cb_[h] = e >> 6;
+                c[h] = s_colpos[e];
                 jj[h] = ec >> 3;
-                soff[h] = (ec >> 3) * PP_SP + (ec & 7);
+                soff[h] = (ec >> 3) * PP_SP + (e >> 6) * 64 + (ec & 7);
             }
 #pragma unroll 4
             for (int q = 0; q < 64 / PP_GROUP_WARPS; q++) {
                 const int er = w + PP_GROUP_WARPS * q;
-                const int r = s_rowpos[cbl * 64 + er];
-                if (r < p.row_begin || r >= p.row_end) continue;
                 const int i = er >> 3, k = er & 7;
-                double* orow = p.C + (long long)(r - p.row_begin) * p.ldc;
-                const double* Srow = Sc + i * 8 * PP_SP + k * 8;
+                const int r0 = s_rowpos[er], r1 = s_rowpos[64 + er];    // output row for column block 0 / 1
+                const bool ok0 = r0 >= p.row_begin && r0 < p.row_end, ok1 = r1 >= p.row_begin && r1 < p.row_end;
+                if (!ok0 && !ok1) continue;
+                double* row0 = p.C + (long long)(r0 - p.row_begin) * p.ldc;
+                double* row1 = p.C + (long long)(r1 - p.row_begin) * p.ldc;
+                const double* Srow = S + i * 8 * PP_SP + k * 8;
 #pragma unroll
-                for (int h = 0; h < 2; h++)
-                    if (c[h] >= 0 && !(p.symmetric && diag && i > jj[h]) && !(p.debug & 1)) orow[c[h]] = Srow[soff[h]];
+                for (int h = 0; h < 4; h++) {
+                    const bool ok = cb_[h] ? ok1 : ok0;
+                    if (ok && c[h] >= 0 && !(p.symmetric && diag && i > jj[h]) && !(p.debug & 1))
+                        (cb_[h] ? row1 : row0)[c[h]] = Srow[soff[h]];
+                }
             }
         }
         if (p.trace && gt == 0) t_direct = global_ns();
@@ -371,7 +382,7 @@ int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cuda
     p.M = a.M; p.N = a.N; p.K = a.K; p.batch = 1;
     p.C = a.C; p.ldc = a.ldc;
     p.epi = EPI_VARF2D;
-    p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkrange = a.blkrange;
+    p.blkpos = a.blkpos; p.blkperm = a.blkperm; p.blkperm2 = a.blkperm2; p.blkrange = a.blkrange;
     p.P0 = a.P0; p.Pp0 = a.Pp0; p.P1 = a.P1; p.Pp1 = a.Pp1;
     p.symmetric = a.symmetric; p.row_begin = a.row_begin; p.row_end = a.row_end;
     p.b_koff_odd = a.b_koff_odd; p.nb_even0 = a.nb_even0;
