@@ -239,10 +239,78 @@ static int ensure_parity_tables(Axis& A, cudaStream_t st) {
     return HB_OK;
 }
 
+// The coefficient box in which the axes of `mask` are parity-sorted: per sorted axis the index runs over the even
+// basis functions first and then the odd ones (on the last axis the odd block starts at the even offset Pep, so
+// that both blocks are 16-byte aligned; the pitch is Pep + Pop).  Returns the look-up table box cell -> position in
+// the index set (-1 for padding and for cells outside the set).
+static int sorted_box(hb_plan* pl, int mask, hb_plan::SortedBox** out, cudaStream_t st) {
+    auto it = pl->sorted_boxes.find(mask);
+    if (it != pl->sorted_boxes.end()) { *out = &it->second; return HB_OK; }
+    const int d = pl->dim;
+    std::vector<std::vector<int>> index(d);   // box coordinate -> basis index (-1 padding)
+    for (int a = 0; a < d; a++) {
+        const Axis& A = pl->ax[a];
+        const Parity1D q = parity_dims(A);
+        const bool last = (a == d - 1);
+        if (mask >> a & 1) {
+            for (int k = 0; k < q.Pe; k++) index[a].push_back(2 * k);
+            if (last) while ((int)index[a].size() < q.Pep) index[a].push_back(-1);
+            for (int k = 0; k < q.Po; k++) index[a].push_back(2 * k + 1);
+            if (last) while ((int)index[a].size() < q.Pep + q.Pop) index[a].push_back(-1);
+        } else {
+            for (int k = 0; k < A.P; k++) index[a].push_back(k);
+            if (last) while ((int)index[a].size() < A.Pp) index[a].push_back(-1);
+        }
+    }
+    long long total = 1;
+    for (int a = 0; a < d; a++) total *= (long long)index[a].size();
+    std::vector<int> lut((size_t)total, -1);
+    std::vector<int> coord(d, 0);
+    for (long long cell = 0; cell < total; cell++) {
+        long long lex = 0;
+        bool ok = true;
+        for (int a = 0; a < d; a++) {
+            const int k = index[a][coord[a]];
+            if (k < 0) { ok = false; break; }
+            lex = lex * pl->ax[a].P + k;
+        }
+        if (ok) lut[(size_t)cell] = pl->iset->lex_to_pos[(size_t)lex];
+        for (int a = d - 1; a >= 0; a--) {        // next cell, last axis fastest
+            if (++coord[a] < (int)index[a].size()) break;
+            coord[a] = 0;
+        }
+    }
+    hb_plan::SortedBox& box = pl->sorted_boxes[mask];
+    box.pitch = (long long)index[d - 1].size();
+    box.size = total;
+    HB_TRY(box.lut.ensure((size_t)total * 4));
+    HB_CUDA(cudaMemcpyAsync(box.lut.p, lut.data(), (size_t)total * 4, cudaMemcpyHostToDevice, st));
+    HB_CUDA(cudaStreamSynchronize(st));   // `lut` goes out of scope
+    *out = &box;
+    return HB_OK;
+}
+
+// Which axis contractions of a d-dimensional transform of `batch` functions are split by parity (bit a).
+static int parity_mask(const hb_plan* pl, int batch, bool flat_last) {
+    const int d = pl->dim;
+    int mask = 0;
+    // sum-factorised stage sizes of the forward transform (the inverse mirrors them)
+    long long prefix = (long long)batch * pl->grid_rows;
+    double cols = pl->ax[d - 1].P;
+    if (flat_last && parity_stage(pl->ax[d - 1], 2.0 * prefix * pl->ax[d - 1].n * pl->ax[d - 1].P)) mask |= 1 << (d - 1);
+    for (int a = d - 2; a >= 0; a--) {
+        const Axis& A = pl->ax[a];
+        prefix /= A.n;
+        if (parity_stage(A, 2.0 * prefix * A.P * A.n * cols)) mask |= 1 << a;
+        cols *= A.P;
+    }
+    return mask;
+}
+
 // Contraction of the LAST grid axis of `rows` rows (pitch f_pitch) into interleaved even / odd coefficients
 // (out row pitch out_pitch): split + two half-size GEMMs.  This is the whole forward transform when dim == 1.
 static int forward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_f, long long f_pitch, long long rows,
-                                    double* d_out, long long out_pitch, int tag, cudaStream_t st) {
+                                    double* d_out, long long out_pitch, int tag, cudaStream_t st, bool sorted = false) {
     const Parity1D d = parity_dims(A);
     HB_TRY(ensure_parity_tables(A, st));
     HB_TRY(pl->parA.ensure((size_t)rows * d.nhp * 8));
@@ -253,8 +321,12 @@ static int forward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_f, lon
         g.M = (int)rows; g.K = d.nh; g.N = par ? d.Po : d.Pe;
         g.A = par ? pl->parB.d() : pl->parA.d(); g.lda = d.nhp;
         g.B = par ? A.pWo.d() : A.pWe.d(); g.ldb = par ? d.Pop : d.Pep;
-        g.C = d_out; g.ldc = out_pitch;
-        g.col_stride = 2; g.col_offset = par;
+        g.ldc = out_pitch;
+        if (sorted) {   // [even block | odd block at Pep]: plain 16-byte stores
+            g.C = d_out + (par ? d.Pep : 0);
+        } else {        // natural order: even / odd coefficients interleave (1-D transform)
+            g.C = d_out; g.col_stride = 2; g.col_offset = par;
+        }
         HB_TRY(timed_gemm(pl, g, tag, st));
     }
     return HB_OK;
@@ -262,22 +334,28 @@ static int forward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_f, lon
 
 // Inverse of it: rows of interleaved coefficients (pitch c_pitch) -> grid rows (pitch f_pitch).
 static int backward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_coef, long long c_pitch, long long rows,
-                                     double* d_f, long long f_pitch, int tag, cudaStream_t st) {
+                                     double* d_f, long long f_pitch, int tag, cudaStream_t st, bool sorted = false) {
     const Parity1D d = parity_dims(A);
     HB_TRY(ensure_parity_tables(A, st));
     const size_t cw = (size_t)d.Pep + d.Pop;
-    HB_TRY(pl->parA.ensure((size_t)rows * cw * 8));
+    if (!sorted) HB_TRY(pl->parA.ensure((size_t)rows * cw * 8));
     HB_TRY(pl->parB.ensure((size_t)rows * 2 * d.nhp * 8));
-    double* ce = pl->parA.d();
-    double* co = ce + (size_t)rows * d.Pep;
+    const double* ce = pl->parA.d();
+    const double* co = ce + (size_t)rows * d.Pep;
+    long long lde = d.Pep, ldo = d.Pop;
     double* ge = pl->parB.d();
     double* go = ge + (size_t)rows * d.nhp;
-    HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 0, 2, ce, d.Pep, rows, d.Pe, 1, 0, 0, st));
-    HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 1, 2, co, d.Pop, rows, d.Po, 1, 0, 0, st));
+    if (sorted) {   // the rows already hold [even block | odd block at Pep]
+        ce = d_coef; co = d_coef + d.Pep; lde = ldo = c_pitch;
+    } else {        // natural order (1-D transform): de-interleave
+        HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 0, 2, pl->parA.d(), d.Pep, rows, d.Pe, 1, 0, 0, st));
+        HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 1, 2, pl->parA.d() + (size_t)rows * d.Pep, d.Pop, rows, d.Po,
+                                   1, 0, 0, st));
+    }
     for (int par = 0; par < 2; par++) {
         GemmArgs g;
         g.M = (int)rows; g.K = par ? d.Po : d.Pe; g.N = d.nh;
-        g.A = par ? co : ce; g.lda = par ? d.Pop : d.Pep;
+        g.A = par ? co : ce; g.lda = par ? ldo : lde;
         g.B = par ? A.pPo.d() : A.pPe.d(); g.ldb = d.nhp;
         g.C = par ? go : ge; g.ldc = d.nhp;
         HB_TRY(timed_gemm(pl, g, tag, st));
@@ -309,8 +387,19 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         return timed_gemm(pl, g, 1, st);
     }
     Axis& L = pl->ax[d - 1];
-    long long cols = L.Pp;
     const long long rows1 = pl->grid_rows;
+    const bool flat = (f_stride == rows1 * L.np || batch == 1);
+    // Axes whose contraction is split by parity keep their coefficient index parity-sorted in every intermediate
+    // and in the look-up table of the final scatter (see sorted_box).
+    const int mask = parity_mask(pl, batch, flat);
+    const int* lut = pl->lut_box.i();
+    long long cols = L.Pp;
+    if (mask) {
+        hb_plan::SortedBox* box = nullptr;
+        HB_TRY(sorted_box(pl, mask, &box, st));
+        lut = box->lut.i();
+        cols = box->pitch;
+    }
     // workspace: largest intermediate
     size_t need = (size_t)batch * rows1 * cols;
     {
@@ -324,16 +413,13 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
     HB_TRY(pl->ws[0].ensure(need * 8));
     if (d > 2) HB_TRY(pl->ws[1].ensure(need * 8));
     pl->n_timed = 0;
-    const bool flat = (f_stride == rows1 * L.np || batch == 1);
-    if (flat && parity_stage(L, 2.0 * batch * rows1 * L.n * L.P)) {
-        if (L.Pp != L.P)   // the pad column of the interleaved output is not written by the half GEMMs
-            HB_CUDA(cudaMemsetAsync(pl->ws[0].p, 0, (size_t)batch * rows1 * cols * 8, st));
-        HB_TRY(forward_last_axis_parity(pl, L, d_f, L.np, batch * rows1, pl->ws[0].d(), cols, d, st));
+    if (mask >> (d - 1) & 1) {
+        HB_TRY(forward_last_axis_parity(pl, L, d_f, L.np, batch * rows1, pl->ws[0].d(), cols, d, st, true));
     } else {
         GemmArgs g;
         g.K = L.n; g.N = L.Pp;
         g.A = d_f; g.lda = L.np;
-        if (f_stride == rows1 * L.np || batch == 1) {
+        if (flat) {
             g.M = (int)(batch * rows1); g.batch = 1;
         } else {
             g.M = (int)rows1; g.batch = batch; g.strideA = f_stride; g.strideC = rows1 * cols;
@@ -347,9 +433,9 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
     for (int a = d - 2; a >= 0; a--) {
         Axis& A = pl->ax[a];
         prefix /= A.n;
-        if (parity_stage(A, 2.0 * prefix * A.P * A.n * cols)) {
-            // even / odd parts of the operand along x_a, then out[2 me + par][cols] = W_par^T[me][h] * B_par[h][cols]:
-            // the two results interleave row-wise (row pitch 2 * cols; look-up-table rows for the last stage)
+        if (mask >> a & 1) {
+            // even / odd parts of the operand along x_a, then out[par block][cols] = W_par^T[m][h] * B_par[h][cols]:
+            // the even results fill rows [0, Pe), the odd ones rows [Pe, P) of the parity-sorted output
             const Parity1D q = parity_dims(A);
             HB_TRY(ensure_parity_tables(A, st));
             const size_t half = (size_t)prefix * q.nh * cols;
@@ -363,10 +449,11 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
                 g.A = par ? A.pWoT.d() : A.pWeT.d(); g.lda = q.nhp; g.strideA = 0;
                 g.B = par ? pl->parB.d() : pl->parA.d(); g.ldb = cols; g.strideB = (long long)q.nh * cols;
                 if (a == 0) {
-                    g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = pl->lut_box.i();
-                    g.row_stride = 2; g.row_offset = par;
+                    g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = lut;
+                    g.row_stride = 1; g.row_offset = par ? q.Pe : 0;
                 } else {
-                    g.C = pl->ws[cur ^ 1].d() + (size_t)par * cols; g.ldc = 2 * cols; g.strideC = (long long)A.P * cols;
+                    g.C = pl->ws[cur ^ 1].d() + (size_t)(par ? q.Pe : 0) * cols; g.ldc = cols;
+                    g.strideC = (long long)A.P * cols;
                 }
                 HB_TRY(timed_gemm(pl, g, 1 + a, st));
             }
@@ -379,7 +466,7 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         g.A = A.wgtT.d(); g.lda = A.np; g.strideA = 0;
         g.B = pl->ws[cur].d(); g.ldb = cols; g.strideB = (long long)A.n * cols;
         if (a == 0) {
-            g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = pl->lut_box.i();
+            g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = lut;
         } else {
             g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = (long long)A.P * cols;
         }
@@ -410,7 +497,17 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
         return timed_gemm(pl, g, 11, st);
     }
     Axis& L = pl->ax[d - 1];
-    size_t need = (size_t)batch * pl->box_size;
+    const int mask = parity_mask(pl, batch, true);
+    const int* lut = pl->lut_box.i();
+    long long box_pitch = L.Pp, box_size = pl->box_size;
+    if (mask) {
+        hb_plan::SortedBox* box = nullptr;
+        HB_TRY(sorted_box(pl, mask, &box, st));
+        lut = box->lut.i();
+        box_pitch = box->pitch;
+        box_size = box->size;
+    }
+    size_t need = (size_t)batch * box_size;
     {
         long long c = L.np, prefix = (long long)batch * pl->box_rows;
         need = std::max(need, (size_t)(prefix * c));
@@ -422,16 +519,17 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
     }
     HB_TRY(pl->ws[0].ensure(need * 8));
     HB_TRY(pl->ws[1].ensure(need * 8));
-    // coefficients in set order -> zero-padded lexicographic box
-    HB_TRY(launch_gather_lut(d_coef, coef_stride, pl->lut_box.i(), pl->ws[0].d(), pl->box_size, pl->box_size, batch, st));
+    // coefficients in set order -> zero-padded (parity-sorted) lexicographic box
+    HB_TRY(launch_gather_lut(d_coef, coef_stride, lut, pl->ws[0].d(), box_size, box_size, batch, st));
     long long cols = L.np;
     pl->n_timed = 0;
-    if (parity_stage(L, 2.0 * batch * pl->box_rows * L.n * L.P)) {
-        HB_TRY(backward_last_axis_parity(pl, L, pl->ws[0].d(), L.Pp, batch * pl->box_rows, pl->ws[1].d(), cols, 10 + d, st));
+    if (mask >> (d - 1) & 1) {
+        HB_TRY(backward_last_axis_parity(pl, L, pl->ws[0].d(), box_pitch, batch * pl->box_rows, pl->ws[1].d(), cols,
+                                         10 + d, st, true));
     } else {
         GemmArgs g;
         g.M = (int)(batch * pl->box_rows); g.K = L.P; g.N = L.np;
-        g.A = pl->ws[0].d(); g.lda = L.Pp;
+        g.A = pl->ws[0].d(); g.lda = box_pitch;
         g.B = L.plainT.d(); g.ldb = L.np;
         g.C = pl->ws[1].d(); g.ldc = cols;
         HB_TRY(timed_gemm(pl, g, 10 + d, st));
@@ -441,9 +539,9 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
     for (int a = d - 2; a >= 0; a--) {
         Axis& A = pl->ax[a];
         prefix /= A.P;
-        if (parity_stage(A, 2.0 * prefix * A.P * A.n * cols)) {
-            // g_par[h][cols] = Phi_par[h][me] * cur[2 me + par][cols] (operand rows taken with pitch 2 * cols), then the
-            // butterfly out[lo+h] = g_e + g_o, out[n-1-lo-h] = g_e - g_o
+        if (mask >> a & 1) {
+            // g_par[h][cols] = Phi_par[h][m] * cur[par block][cols] (even rows [0, Pe), odd rows [Pe, P) of the
+            // parity-sorted operand), then the butterfly out[lo+h] = g_e + g_o, out[n-1-lo-h] = g_e - g_o
             const Parity1D q = parity_dims(A);
             HB_TRY(ensure_parity_tables(A, st));
             const size_t half = (size_t)prefix * q.nh * cols;
@@ -453,7 +551,7 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
                 GemmArgs g;
                 g.M = q.nh; g.K = par ? q.Po : q.Pe; g.N = (int)cols; g.batch = (int)prefix;
                 g.A = par ? A.pPhiO.d() : A.pPhiE.d(); g.lda = par ? q.Pop : q.Pep; g.strideA = 0;
-                g.B = pl->ws[cur].d() + (size_t)par * cols; g.ldb = 2 * cols; g.strideB = (long long)A.P * cols;
+                g.B = pl->ws[cur].d() + (size_t)(par ? q.Pe : 0) * cols; g.ldb = cols; g.strideB = (long long)A.P * cols;
                 g.C = par ? pl->parB.d() : pl->parA.d(); g.ldc = cols; g.strideC = (long long)q.nh * cols;
                 HB_TRY(timed_gemm(pl, g, 11 + a, st));
             }

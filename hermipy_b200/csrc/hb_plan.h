@@ -1,5 +1,6 @@
 // Plan object: device-resident tables + workspace for one (grid, degree, index set) combination.
 #pragma once
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -73,6 +74,11 @@ struct hb_plan {
     std::vector<hb::Axis> ax;
     long long n_polys = 0, grid_rows = 0 /* n_0..n_{d-2} */, grid_size = 0, box_rows = 0, box_size = 0;
     hb::DevBuf lut_box;  // int32[box_size]: padded lexicographic box -> position in the set, -1 absent
+    // Parity-sorted boxes: when the contraction of axis a is split by parity, its coefficient index runs
+    // [even indices | odd indices] in every intermediate (the half GEMMs then write / read contiguous blocks);
+    // one look-up table per set of sorted axes (bit a of the key), built on first use.
+    struct SortedBox { hb::DevBuf lut; long long pitch = 0, size = 0; };
+    std::map<int, SortedBox> sorted_boxes;
     hb::DevBuf ws[2];
     hb::DevBuf parA, parB;   // work buffers of the parity stages (even / odd halves)
     hb::DevBuf nodes_cat;  // all axes' nodes, concatenated (discretize)
