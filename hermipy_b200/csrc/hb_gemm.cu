@@ -186,8 +186,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
 
 static int dispatch(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream) {
     if (a.epi == EPI_VARF2D) {
-        if (!a.a_mmajor) { set_error("gemm: the varf epilogue needs an M-contiguous A operand"); return HB_ERR_INVALID; }
-        return gemm_dispatch_varf_m(2, a, p, stream);
+        set_error("gemm: the varf scatter epilogue belongs to the persistent kernel (varf_stage2_launch)");
+        return HB_ERR_INVALID;
     }
     if (a.epi == EPI_LUT) {
         if (a.a_mmajor) { set_error("gemm: the look-up-table epilogue needs a K-contiguous A operand"); return HB_ERR_INVALID; }

@@ -26,8 +26,8 @@ namespace hb {
 enum EpilogueMode : int {
     EPI_STORE = 0,    // C[b][row*ldc + col] = v
     EPI_LUT = 1,      // out[b*strideC + lut[row*N + col]] = v   (lut < 0: dropped)
-    EPI_VARF2D = 2,   // row=(m0,n0), col=(m1,n1): out[(lut[m0*P+m1]-row_begin)*ldc + lut[n0*P+n1]] = v
-                      // pairs are indexed in 8x8 blocks: p(i,j) = ((i>>3)*nb + (j>>3))*64 + (i&7)*8 + (j&7)
+    EPI_VARF2D = 2,   // stage 2 of the dense 2-D varf: scatter A[idx(m0,m1)][idx(n0,n1)]; handled by the persistent
+                      // kernel of hb_varf_gemm.cu (this generic kernel has no instantiation for it)
 };
 
 constexpr int GEMM_MAX_BLOCKS = 16;
@@ -39,7 +39,7 @@ struct GemmParams {
     long long strideC;  // batch stride of C / of the scattered output (EPI_LUT)
     int epi;
     const int* lut;     // EPI_LUT: M*N entries (padded lexicographic box -> position in the index set, or -1)
-    // EPI_VARF2D.  GEMM row = blocked pair (m0,n0) of axis-0 indices, GEMM column = blocked pair (m1,n1) of axis-1
+    // EPI_VARF2D (persistent kernel, hb_varf_gemm.cu).  GEMM row = blocked pair (m0,n0) of axis-0 indices, GEMM column = blocked pair (m1,n1) of axis-1
     // indices, pairs laid out in 8x8 blocks: p(i,j) = ((i>>3)*nb + (j>>3))*64 + (i&7)*8 + (j&7).  The entry lands at
     // A[idx(m0,m1)][idx(n0,n1)].  Positions come from per-block tables of the 2-D index set (built once per plan):
     //   blkpos  [(ba*Pp1 + bb)*64 + (a&7)*8 + (b&7)] = idx(a, b) for a in block ba of axis 0, b in block bb of axis 1
@@ -128,28 +128,6 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     const int tile_n = t_grp / g_rows;
     const int m_base = tile_m * BM, n_base = tile_n * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if constexpr (EPI == EPI_VARF2D) {
-        // Tile-level skipping: a tile is one 8x8 row block (bm0,bn0) by BN/64 column blocks (bm1,bn1).  It is
-        // needed if, for some column block, the output-row block (bm0,bm1) holds an owned row and the
-        // output-column block (bn0,bn1) holds any position of the set (total-degree and sparse sets leave whole
-        // blocks empty), and -- in symmetric mode -- if it lies in the upper half bm0 <= bn0.
-        static_assert(BM == 64 && BN % 64 == 0 && A_MMAJOR, "the varf epilogue works on 8x8-blocked pair tables");
-        const int rb = m_base >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
-        bool needed = false;
-        if (!(p.symmetric && bm0 > bn0)) {
-            for (int cbl = 0; cbl < BN / 64 && !needed; cbl++) {
-                const int cb = (n_base >> 6) + cbl;
-                if (cb * 64 >= p.N) break;
-                const int bm1 = cb / p.Pp1, bn1 = cb - bm1 * p.Pp1;
-                const int2 rr = p.blkrange[bm0 * p.Pp1 + bm1], cr = p.blkrange[bn0 * p.Pp1 + bn1];
-                needed = rr.y >= rr.x && cr.y >= cr.x && rr.y >= p.row_begin && rr.x < p.row_end;
-            }
-        }
-        if (!needed) return;
-    }
-    long long t_start = 0, t_main = 0;
-    if constexpr (EPI == EPI_VARF2D) { if (p.trace && threadIdx.x == 0) t_start = global_ns(); }
 
     if (threadIdx.x == 0) {
         grid_launch_dependents();
@@ -264,103 +242,6 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     }
 
     // ---------------- epilogue ----------------
-    if constexpr (EPI == EPI_VARF2D) {
-        if (p.trace && threadIdx.x == 0) t_main = global_ns();
-        // Table-driven coalesced scatter.  The accumulators are staged in the (now idle) pipeline buffers as
-        // S[(m0l,n0l)][(m1l,n1l)]; the positions of the 64 (m0l,m1l) row combinations and of the 64 (n0l,n1l)
-        // column combinations of every column block are read once from the per-block tables.  Direct entries
-        // A[r][c]: one warp per output row r, lanes walk the 64 columns in the order of their positions c, so
-        // that consecutive lanes hit consecutive addresses whatever the enumeration of the index set is (runs of
-        // 8 for the cube's shell order, anti-diagonal runs for the triangle).  Mirrored entries A[c][r]
-        // (symmetric mode, m0 < n0): the same with rows and columns exchanged.
-        constexpr int SP = BN + 2;   // staging pitch in doubles
-        constexpr int NCB = BN / 64;
-        double* S = reinterpret_cast<double*>(smem_gen);
-        int* s_rowpos = reinterpret_cast<int*>(smem_gen + 64 * SP * 8);   // [NCB][64]
-        int* s_colpos = s_rowpos + NCB * 64;                              // [NCB][64]
-        unsigned char* s_rowperm = reinterpret_cast<unsigned char*>(s_colpos + NCB * 64);   // [NCB][64]
-        unsigned char* s_colperm = s_rowperm + NCB * 64;
-        static_assert(64 * SP * 8 + NCB * 64 * 10 <= STAGES * STAGE_BYTES, "staging area");
-        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");   // all warps done with the stages
-#pragma unroll
-        for (int mi = 0; mi < MI; mi++) {
-            const int im = wm * MI + mi;
-            const int rl = 16 * (im >> 1) + 4 * (im & 1) + cm;
-#pragma unroll
-            for (int nj = 0; nj < NJ; nj++) {
-                const int jn = wn * NJ + nj;
-                const int cl = 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
-                *reinterpret_cast<double2*>(S + rl * SP + cl) =
-                    make_double2(acc[mi][nj][0] * p.alpha, acc[mi][nj][1] * p.alpha);
-            }
-        }
-        const int rb = m_base >> 6, bm0 = rb / p.Pp0, bn0 = rb - bm0 * p.Pp0;
-        for (int e = threadIdx.x; e < NCB * 64; e += NCW * 32) {
-            const int cbl = e >> 6, cb = (n_base >> 6) + cbl;
-            int rp = -1, cp = -1, rperm = e & 63, cperm = e & 63;
-            if (cb * 64 < p.N) {
-                const int bm1 = cb / p.Pp1, bn1 = cb - bm1 * p.Pp1;
-                const int rblk = (bm0 * p.Pp1 + bm1) * 64 + (e & 63), cblk = (bn0 * p.Pp1 + bn1) * 64 + (e & 63);
-                rp = __ldg(p.blkpos + rblk);
-                cp = __ldg(p.blkpos + cblk);
-                rperm = __ldg(p.blkperm + rblk);
-                cperm = __ldg(p.blkperm + cblk);
-            }
-            s_rowpos[e] = rp; s_colpos[e] = cp;
-            s_rowperm[e] = (unsigned char)rperm; s_colperm[e] = (unsigned char)cperm;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
-        if (p.debug & 4) return;
-        const bool diag = (bm0 == bn0);
-        // ---- direct entries A[idx(m0,m1)][idx(n0,n1)] = S[(m0l,n0l)][(m1l,n1l)] ----
-        for (int cbl = 0; cbl < NCB; cbl++) {
-            const double* Sc = S + cbl * 64;
-            for (int er = warp; er < 64; er += NCW) {          // er = m0l*8 + m1l
-                const int r = s_rowpos[cbl * 64 + er];
-                if (r < p.row_begin || r >= p.row_end) continue;    // also drops r = -1
-                const int i = er >> 3, k = er & 7;
-                double* orow = p.C + (long long)(r - p.row_begin) * p.ldc;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int ec = s_colperm[cbl * 64 + lane + 32 * h];   // ec = n0l*8 + n1l
-                    const int c = s_colpos[cbl * 64 + ec];
-                    const int j = ec >> 3, l = ec & 7;
-                    if (c < 0 || (p.symmetric && diag && i > j)) continue;
-                    if (!(p.debug & 1)) orow[c] = Sc[(i * 8 + j) * SP + k * 8 + l];
-                }
-            }
-        }
-        // ---- mirrored entries A[idx(n0,n1)][idx(m0,m1)] for m0 < n0 ----
-        if (p.symmetric) {
-            for (int cbl = 0; cbl < NCB; cbl++) {
-                const double* Sc = S + cbl * 64;
-                for (int ec = warp; ec < 64; ec += NCW) {
-                    const int c = s_colpos[cbl * 64 + ec];
-                    if (c < 0) continue;
-                    const int j = ec >> 3, l = ec & 7;
-                    double* orow = p.C + (long long)c * p.ldc;
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int er = s_rowperm[cbl * 64 + lane + 32 * h];
-                        const int r = s_rowpos[cbl * 64 + er];
-                        const int i = er >> 3, k = er & 7;
-                        if (r < 0 || (diag && i >= j)) continue;
-                        if (!(p.debug & 2)) orow[r] = Sc[(i * 8 + j) * SP + k * 8 + l];
-                    }
-                }
-            }
-        }
-        if (p.trace && threadIdx.x == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            const long long slot = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(p.trace), 1ull);
-            if (slot < p.trace[1]) {
-                long long* rec = p.trace + 2 + 5 * slot;
-                rec[0] = blockIdx.x; rec[1] = smid; rec[2] = t_start; rec[3] = t_main; rec[4] = global_ns();
-            }
-        }
-        return;
-    }
     if constexpr (EPI == EPI_LUT) {
         // Scatter through the look-up table (last stage of a d-dim forward transform).  The table entries
         // of one accumulator row are fetched first (independent loads in flight together), then stored.

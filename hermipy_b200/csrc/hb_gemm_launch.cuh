@@ -85,6 +85,5 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
 int gemm_dispatch_store_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);  // A K-contiguous
 int gemm_dispatch_store_m(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);  // A M-contiguous
 int gemm_dispatch_lut_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);
-int gemm_dispatch_varf_m(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);   // cfg 2 only
 
 }  // namespace hb

@@ -749,13 +749,6 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     const bool full = (row_begin == 0 && row_end == pl->n_polys);
     g2.row_begin = (int)row_begin; g2.row_end = full ? 0x7fffffff : (int)row_end;
     g2.symmetric = full ? 1 : 0;
-    g2.group_m = 16;   // 16 row tiles (3.3 MB of the left table at C2) stay in L2 while the right table streams
-    g2.cfg = 2;   // 64 x 128 tiles: one 8x8 row block per tile
-    static const bool pingpong = [] { const char* e = getenv("HB_VARF_PINGPONG"); return !(e && e[0] == '0'); }();
-    if (!pingpong) {   // generic kernel, two CTAs per SM (developer comparison); it has no parity split
-        if (parity_seg > 0) { set_error("HB_VARF_PINGPONG=0 needs HB_VARF_PARITY=0"); return HB_ERR_INVALID; }
-        return timed_gemm(pl, g2, 22, st);
-    }
     // persistent ping-pong kernel over the list of needed tiles (cached per row range)
     const long long key[3] = {row_begin, row_end, g2.symmetric};
     if (key[0] != pl->tiles_key[0] || key[1] != pl->tiles_key[1] || key[2] != pl->tiles_key[2]) {
@@ -823,9 +816,8 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
     // nodes, against the even or the odd part of f (chosen per row tile, whose 8x8 block has one parity):
     // half the flops of the dominant stage.
     static const bool parity_ok = [] { const char* e = getenv("HB_VARF_PARITY"); return !(e && e[0] == '0'); }();
-    static const bool pingpong = [] { const char* e = getenv("HB_VARF_PINGPONG"); return !(e && e[0] == '0'); }();
     Axis &A0 = pl->ax[0], &A1 = pl->ax[1];
-    const bool parity = parity_ok && pingpong && A0.symmetric_nodes && A0.n >= 2;
+    const bool parity = parity_ok && A0.symmetric_nodes && A0.n >= 2;
     const int nh = (A0.n + 1) / 2;                       // nodes x >= 0: rows n - nh .. n - 1
     for (int a = 0; a < 2; a++) {
         if (pl->pairB_ok[a]) continue;
