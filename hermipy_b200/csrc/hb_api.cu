@@ -223,7 +223,7 @@ int hb_hermite_eval(const double* x, int n, int degree, double* out) {
 namespace hb {
 namespace {
 struct Pipeline {
-    static const int kMaxChunks = 8;
+    static const int kMaxChunks = 16;
     cudaStream_t in = nullptr, compute = nullptr, out = nullptr;
     cudaEvent_t uploaded[kMaxChunks] = {nullptr}, computed[kMaxChunks] = {nullptr};
     bool ok = false;
@@ -266,7 +266,9 @@ int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const d
     if (forward && L.np != L.n) HB_TRY(g_stage.ensure((size_t)batch * n_grid * 8));
     // chunks of >= 2 MB of grid data, at most kMaxChunks
     const double grid_mb = (double)pl->grid_size * 8e-6;
-    int n_chunks = (int)std::min<double>(Pipeline::kMaxChunks, std::max(1.0, batch * grid_mb / 2.0));
+    static const int max_chunks = [] { const char* e = getenv("HB_PIPE_CHUNKS"); const int v = e ? atoi(e) : 8;
+                                       return std::max(1, std::min(v, (int)Pipeline::kMaxChunks)); }();
+    int n_chunks = (int)std::min<double>(max_chunks, std::max(1.0, batch * grid_mb / 2.0));
     n_chunks = std::min(n_chunks, batch);
     const int per = (batch + n_chunks - 1) / n_chunks;
     for (int c = 0, b0 = 0; b0 < batch; c++, b0 += per) {
