@@ -424,6 +424,18 @@ def run_ours(args):
                                     "pattern; see DESIGN.md 4.3" % (8e-9 * npol ** 2),
                             "scatter_tbs": 8e-12 * npol ** 2 / (tl.get(22, np.nan) * 1e-3)},
             }
+            # consumer of the resident matrix: y = A x (hb_dev_matvec), HBM-bound at 8 |I|^2 bytes per product
+            from hermipy_b200.resident import device_matvec
+            xv = torch.randn(npol, dtype=torch.float64, device="cuda")
+            yv = torch.empty(npol, dtype=torch.float64, device="cuda")
+            ms_mv = max_over_ranks(time_steps(torch, lambda: device_matvec(out, xv, yv), 5, 2, flush, barrier)) / 5
+            mv_err = float(((yv - out @ xv).norm() / yv.norm()).item())
+            entry["matvec"] = {"kernel": "matvec_kernel (hb_dev_matvec)", "ms": ms_mv, "bound": "hbm",
+                               "algorithmic_bytes": 8.0 * npol ** 2, "achieved_gbs": 8.0 * npol ** 2 / ms_mv * 1e-6,
+                               "peak_gbs": peaks.get("hbm_gbs"),
+                               "frac": 8.0 * npol ** 2 / ms_mv * 1e-6 / peaks.get("hbm_gbs"),
+                               "rel_diff_vs_torch_mv": mv_err}
+            del xv, yv
             if args.check:
                 vplan.varf(fV, "gram", out)
                 entry["gram_vs_reference_algebra_rel_err_polynomial_f"] = float(((out - ref_poly).norm() / ref_poly.norm()).item())

@@ -83,6 +83,9 @@ SIGNATURES = {
     "hb_dev_dgemm_scatter": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong,
                                        C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p), C.c_int,
                                        C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]),
+    "hb_dev_matvec": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_dev_varfd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_size_t, C.c_int,
+                               C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "hb_plan_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_llp, c_llp, c_llp]),
     "hb_plan_varf_info": (C.c_int, [C.c_void_p, c_ip, c_ip]),
 }

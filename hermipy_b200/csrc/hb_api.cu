@@ -430,18 +430,17 @@ int hb_sparse_fetch(long long* indptr, int* indices, double* data) {
     return HB_OK;
 }
 
-int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_polys, int do_fourier,
-             const char* index_set, double* out) {
-    HB_TRY(check_device());
+// column map of varfd (varf.cpp:423-453): entry (i, j) = fac[j] * var[i][src[j]], src[j] = index(m_j -/+ e_dir)
+static int varfd_column_map(int dim, int degree, int direction, size_t n_polys, int do_fourier, const char* index_set,
+                            std::vector<int>& src, std::vector<double>& fac) {
     const int set = set_or_err(index_set);
     if (set < 0) return HB_ERR_INDEX_SET;
     auto s = get_index_set(set, dim, degree);
     if (!s || direction < 0 || direction >= dim) return HB_ERR_INVALID;
     if (n_polys != s->size) { set_error("varfd: matrix size %zu != n_polys %u", n_polys, s->size); return HB_ERR_INVALID; }
     const int n = (int)n_polys;
-    // column map (varf.cpp:423-453): entry (i, j) = factor(m_j) * var[i][index(m_j -/+ e_dir)]
-    std::vector<int> src(n, -1);
-    std::vector<double> fac(n, 0.0);
+    src.assign(n, -1);
+    fac.assign(n, 0.0);
     std::vector<uint32_t> m(dim);
     for (int j = 0; j < n; j++) {
         for (int a = 0; a < dim; a++) m[a] = s->list[(size_t)j * dim + a];
@@ -458,6 +457,16 @@ int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_pol
         }
         src[j] = s->position(m.data());
     }
+    return HB_OK;
+}
+
+int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_polys, int do_fourier,
+             const char* index_set, double* out) {
+    HB_TRY(check_device());
+    std::vector<int> src;
+    std::vector<double> fac;
+    HB_TRY(varfd_column_map(dim, degree, direction, n_polys, do_fourier, index_set, src, fac));
+    const int n = (int)n_polys;
     std::lock_guard<std::mutex> lock(g_call_mutex);
     HB_TRY(g_in.ensure(n_polys * n_polys * 8));
     HB_TRY(g_out.ensure(n_polys * n_polys * 8));
@@ -466,7 +475,7 @@ int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_pol
     HB_CUDA(cudaMemcpyAsync(g_in.p, var, n_polys * n_polys * 8, cudaMemcpyHostToDevice, 0));
     HB_CUDA(cudaMemcpyAsync(g_auxi[0].p, src.data(), (size_t)n * 4, cudaMemcpyHostToDevice, 0));
     HB_CUDA(cudaMemcpyAsync(g_aux[0].p, fac.data(), (size_t)n * 8, cudaMemcpyHostToDevice, 0));
-    HB_TRY(launch_varfd(g_in.d(), g_auxi[0].i(), g_aux[0].d(), g_out.d(), n, 0));
+    HB_TRY(launch_varfd(g_in.d(), n, g_auxi[0].i(), g_aux[0].d(), g_out.d(), n, n, n, 0));
     HB_CUDA(cudaMemcpyAsync(out, g_out.p, n_polys * n_polys * 8, cudaMemcpyDeviceToHost, 0));
     HB_CUDA(cudaStreamSynchronize(0));
     return HB_OK;
@@ -733,6 +742,33 @@ int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long l
     g.block_rows = block_rows;
     for (int i = 0; i < n_blocks; i++) g.blocks[i] = blocks[i];
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+int hb_dev_matvec(int M, int N, const double* A, long long lda, const double* x, double* y, void* stream) {
+    HB_TRY(check_device());
+    if (M < 0 || N < 0 || lda < N) { set_error("hb_dev_matvec: need lda >= N >= 0"); return HB_ERR_INVALID; }
+    return launch_matvec(M, N, A, lda, x, y, static_cast<cudaStream_t>(stream));
+}
+int hb_dev_varfd(int dim, int degree, int direction, const double* var, long long ldv, long long n_rows,
+                 size_t n_polys, int do_fourier, const char* index_set, double* out, long long ldo, void* stream) {
+    HB_TRY(check_device());
+    if (var == out) { set_error("hb_dev_varfd: in-place operation is not supported"); return HB_ERR_INVALID; }
+    std::vector<int> src;
+    std::vector<double> fac;
+    HB_TRY(varfd_column_map(dim, degree, direction, n_polys, do_fourier, index_set, src, fac));
+    const int n = (int)n_polys;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the column map is small (12 bytes per column): stream-ordered scratch, freed behind the kernel
+    int* d_src = nullptr;
+    double* d_fac = nullptr;
+    HB_CUDA(cudaMallocAsync(&d_src, (size_t)n * 4, st));
+    HB_CUDA(cudaMallocAsync(&d_fac, (size_t)n * 8, st));
+    HB_CUDA(cudaMemcpyAsync(d_src, src.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    HB_CUDA(cudaMemcpyAsync(d_fac, fac.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const int rc = launch_varfd(var, ldv, d_src, d_fac, out, ldo, (int)n_rows, n, st);
+    cudaFreeAsync(d_src, st);
+    cudaFreeAsync(d_fac, st);
+    HB_CUDA(cudaStreamSynchronize(st));   // src / fac are host temporaries of this call
+    return rc;
 }
 int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
                   long long* ld) {

@@ -449,17 +449,24 @@ int launch_project(const double* in, int n_in, const int* sel, bool matrix, doub
 
 // varfd (reference: cpp/src/hermite/varf.cpp:290-376): out[r][c] = fac[c] * var[r][src[c]] where, for a
 // Hermite axis, src[c] = index(m_c - e_dir) and fac[c] = sqrt(m_c[dir]) (0 / unused when m_c[dir]==0).
-__global__ void varfd_kernel(const double* __restrict__ var, const int* __restrict__ src, const double* __restrict__ fac,
-                             double* out, int n) {
+__global__ void varfd_kernel(const double* __restrict__ var, long long ldv, const int* __restrict__ src,
+                             const double* __restrict__ fac, double* out, long long ldo, int n) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     if (c >= n) return;
     const int sc = src[c];
-    out[(long long)r * n + c] = sc >= 0 ? __dmul_rn(var[(long long)r * n + sc], fac[c]) : 0.0;
+    out[(long long)r * ldo + c] = sc >= 0 ? __dmul_rn(var[(long long)r * ldv + sc], fac[c]) : 0.0;
 }
-int launch_varfd(const double* var, const int* src, const double* fac, double* out, int n, cudaStream_t s) {
-    dim3 grid(cdiv(n, 256), n);
-    varfd_kernel<<<grid, 256, 0, s>>>(var, src, fac, out, n);
-    return launch_status();
+int launch_varfd(const double* var, long long ldv, const int* src, const double* fac, double* out, long long ldo,
+                 int rows, int n, cudaStream_t s) {
+    // gridDim.y is limited to 65535: walk taller row blocks in slices
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        dim3 grid(cdiv(n, 256), nr);
+        varfd_kernel<<<grid, 256, 0, s>>>(var + (long long)r0 * ldv, ldv, src, fac, out + (long long)r0 * ldo, ldo, n);
+        const int rc = launch_status();
+        if (rc != HB_OK) return rc;
+    }
+    return HB_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -41,7 +41,10 @@ struct TensorizeArgs {
 };
 int launch_tensorize(const TensorizeArgs& a, bool matrices, double* out, int n_out, cudaStream_t s);
 int launch_project(const double* in, int n_in, const int* sel, bool matrix, double* out, int n_out, cudaStream_t s);
-int launch_varfd(const double* var, const int* src, const double* fac, double* out, int n, cudaStream_t s);
+int launch_varfd(const double* var, long long ldv, const int* src, const double* fac, double* out, long long ldo,
+                 int rows, int n, cudaStream_t s);
+// y = A x for a row-major M x N matrix resident in HBM (hb_matvec.cu)
+int launch_matvec(int M, int N, const double* A, long long lda, const double* x, double* y, cudaStream_t s);
 
 struct VarfSparseArgs {
     int dim, n_polys, n_kept;

@@ -31,6 +31,16 @@ def dgemm_scatter(M, N, K, A, lda, B, ldb, blocks, block_rows, ldc, batch=1, str
                                      len(blocks), block_rows, ldc, strideC, _stream()))
 
 
+def varfd_device(dim, degree, direction, var, do_fourier=0, index_set="triangle", out=None):
+    """core.varfd on a resident row block (`var`: rows x n_polys float64 CUDA tensor); returns a new block."""
+    if out is None:
+        out = torch.empty_like(var)
+    check(lib().hb_dev_varfd(int(dim), int(degree), int(direction), var.data_ptr(), var.stride(0), var.shape[0],
+                             var.shape[1], int(do_fourier), index_set.encode(), out.data_ptr(), out.stride(0),
+                             _stream()))
+    return out
+
+
 class Plan:
     def __init__(self, degree, nodes, weights, do_fourier=None, index_set="triangle"):
         nodes = [np.ascontiguousarray(n, dtype=np.float64).ravel() for n in nodes]

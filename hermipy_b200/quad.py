@@ -52,6 +52,8 @@ def tensorize_at(arg_num):
             quad, function = args[0], args[arg_num]
             if isinstance(function, Series):      # integrate(series): evaluated on the full grid
                 enabled = False
+            if kwargs.get('resident'):            # device-resident results are assembled on the full grid
+                enabled = False
             if not enabled or not quad.position.is_diag or isinstance(function, np.ndarray):
                 return method(*args, **kwargs)
             if not isinstance(function, Function):
@@ -268,24 +270,50 @@ class Quad:
     @tensorize_at(1)
     @stats.debug()
     @stats.log_stats()
-    def varf(self, f_grid, degree, sparse=None, index_set="triangle", tensorize=None):
-        """Matrix of the multiplication operator u -> f u in the basis of this quadrature."""
+    def varf(self, f_grid, degree, sparse=None, index_set="triangle", tensorize=None, resident=False):
+        """Matrix of the multiplication operator u -> f u in the basis of this quadrature.  `resident=True`
+        leaves the (dense) matrix in HBM and returns a `ResidentVarf` (hermipy_b200/resident.py)."""
         sparse = settings['sparse'] if sparse is None else sparse
         if not isinstance(f_grid, np.ndarray):
             f_grid = self.discretize(f_grid)
+        if resident:
+            from .resident import ResidentVarf
+            plan = self._resident_plan(degree, index_set)
+            block = plan.varf(plan.pack_grid(np.asarray(f_grid, float))[0], mode="reference")
+            return ResidentVarf(block, self.position, factor=self.factor, index_set=index_set)
         matrix = core.varf(degree, f_grid, self.nodes, self.weights, sparse=sparse,
                            do_fourier=self.do_fourier, index_set=index_set)
         return Varf(matrix, self.position, factor=self.factor, index_set=index_set)
 
+    def _resident_plan(self, degree, index_set):
+        """Device plan (basis / triple-product tables) of this quadrature for one (degree, index set)."""
+        from .plan import Plan
+        plans = self.__dict__.setdefault('_plans', {})
+        key = (int(degree), index_set)
+        if key not in plans:
+            plans[key] = Plan(degree, self.nodes, self.weights, do_fourier=self.do_fourier, index_set=index_set)
+        return plans[key]
+
     @tensorize_at(1)
     @stats.debug()
     @stats.log_stats()
-    def varfd(self, function, degree, directions, sparse=None, index_set="triangle", tensorize=None):
+    def varfd(self, function, degree, directions, sparse=None, index_set="triangle", tensorize=None,
+              resident=False):
         """Matrix of u -> function * d^k u / (dx_{d1} ... dx_{dk}), `directions` = [d1, ..., dk]."""
         directions = [d for d in directions if d in self.position.dirs]
         sparse = settings['sparse'] if sparse is None else sparse
-        matrix = self.varf(function, degree, sparse=sparse, index_set=index_set, tensorize=False).matrix
         eigval, _ = la.eig(self.position.cov)
+        if resident:
+            from .plan import varfd_device
+            from .resident import ResidentMatrix, ResidentVarf
+            block = self.varf(function, degree, index_set=index_set, tensorize=False, resident=True).matrix.block
+            for d in directions:
+                rel = self.position.dirs.index(d)
+                block = varfd_device(self.position.dim, degree, rel, block, do_fourier=self.do_fourier[rel],
+                                     index_set=index_set)
+                block /= float(np.sqrt(eigval[rel]))
+            return ResidentVarf(ResidentMatrix(block), self.position, factor=self.factor, index_set=index_set)
+        matrix = self.varf(function, degree, sparse=sparse, index_set=index_set, tensorize=False).matrix
         for d in directions:
             rel = self.position.dirs.index(d)
             matrix = core.varfd(self.position.dim, degree, rel, matrix, do_fourier=self.do_fourier[rel],
@@ -295,7 +323,7 @@ class Quad:
 
     @stats.debug()
     @stats.log_stats()
-    def discretize_op(self, op, degree, sparse=None, index_set="triangle"):
+    def discretize_op(self, op, degree, sparse=None, index_set="triangle", resident=False):
         """Galerkin matrix of a linear differential operator (conjugated by the weight factor)."""
         if not isinstance(op, Operator):
             op = Operator(op, dirs=self.position.dirs)
@@ -304,13 +332,14 @@ class Quad:
         if op.dirs != self.position.dirs:
             raise ValueError("Invalid argument: directions don't match")
         sparse = settings['sparse'] if sparse is None else sparse
+        extra = {'resident': True} if resident else {}
         terms = op.split()
         if terms == {}:
-            return self.varf(0, degree, sparse=sparse, index_set=index_set)
+            return self.varf(0, degree, sparse=sparse, index_set=index_set, **extra)
         total = 0
         for orders, coefficient in terms.items():
             derivatives = [d for i, d in enumerate(self.position.dirs) for _ in range(orders[i])]
-            total = total + self.varfd(coefficient, degree, derivatives, sparse=sparse, index_set=index_set)
+            total = total + self.varfd(coefficient, degree, derivatives, sparse=sparse, index_set=index_set, **extra)
         return total
 
     # ---- bookkeeping ----------------------------------------------------------------------------

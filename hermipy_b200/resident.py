@@ -1,0 +1,282 @@
+"""Assembled Galerkin matrices that stay in HBM, and their consumers.
+
+Reference: hermipy/varf.py:127-134 (`Varf.__call__`), :170-226 (`solve`) and :228-237 (`eigs`).  There the
+matrix is a NumPy / SciPy object; at the sizes this library assembles (C2 cube: 13 GB, C3 cube: 207 GB
+row-sharded over 8 GPUs) a host copy costs more than the assembly, so `Quad.varf(..., resident=True)`,
+`Quad.varfd(..., resident=True)` and `Quad.discretize_op(..., resident=True)` return a `ResidentVarf`: the
+same object surface (`__call__`, `+ - *`, `solve`, `eigs`, `multi_indices`), with the matrix a row block per
+rank on the device.  The Krylov drivers are SciPy's (ARPACK, GMRES), as in the reference; their only contact
+with the matrix -- the product A x -- is `hb_dev_matvec` (csrc/hb_matvec.cu, HBM-bound), and only vectors
+cross PCIe.  Dense direct solves run on the device through torch.linalg (cuSOLVER), which is library code
+beside the path, not part of it.
+"""
+import ctypes as C
+
+import numpy as np
+import numpy.linalg as la
+import scipy.sparse.linalg as spla
+import torch
+import torch.distributed as dist
+
+from . import core
+from . import function as func
+from . import series as hs
+from . import stats
+from ._lib import check, lib
+
+_NUMBER = (int, float, np.integer, np.floating)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_matvec(A, x, out=None):
+    """out = A @ x for a row-major float64 CUDA matrix (any leading dimension) through hb_dev_matvec."""
+    if A.dtype != torch.float64 or x.dtype != torch.float64 or A.stride(1) != 1 or not x.is_contiguous():
+        raise ValueError("device_matvec: float64 operands, matrix rows contiguous")
+    if x.numel() != A.shape[1]:
+        raise ValueError("device_matvec: vector has %d entries, matrix has %d columns" % (x.numel(), A.shape[1]))
+    if out is None:
+        out = torch.empty(A.shape[0], dtype=torch.float64, device=A.device)
+    check(lib().hb_dev_matvec(A.shape[0], A.shape[1], A.data_ptr(), A.stride(0), x.data_ptr(), out.data_ptr(),
+                              _stream()))
+    return out
+
+
+def reference_matvec(A, x, out=None):
+    """CPU stand-in with device_matvec's semantics; host-logic (gloo) tests only."""
+    res = torch.mv(A, x)
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+class ResidentMatrix:
+    """Rows [row_begin, row_begin + block.shape[0]) of an n x n matrix; `block` is a float64 tensor on the
+    compute device.  With a process group the row blocks of all ranks (contiguous, in rank order) form the
+    matrix and a product ends in one all-gather of the result vector -- the only exchange this path has."""
+
+    def __init__(self, block, n=None, row_begin=0, group=None, matvec=device_matvec):
+        self.block = block
+        self.n = int(block.shape[1] if n is None else n)
+        self.row_begin = int(row_begin)
+        self.group = group
+        self._matvec = matvec
+        self.sharded = group is not None and dist.get_world_size(group) > 1
+        if not self.sharded and block.shape[0] != self.n:
+            raise ValueError("ResidentMatrix: a row block needs a process group")
+        if self.sharded:
+            rows = torch.tensor([block.shape[0]], dtype=torch.int64, device=block.device)
+            counts = [torch.zeros_like(rows) for _ in range(dist.get_world_size(group))]
+            dist.all_gather(counts, rows, group=group)
+            self.row_counts = [int(c.item()) for c in counts]
+            if sum(self.row_counts) != self.n:
+                raise ValueError("ResidentMatrix: row blocks hold %d rows, matrix has %d" % (sum(self.row_counts), self.n))
+
+    shape = property(lambda self: (self.n, self.n))
+
+    def _like(self, block):
+        out = ResidentMatrix.__new__(ResidentMatrix)
+        out.__dict__.update(self.__dict__)
+        out.block = block
+        return out
+
+    # ---- products ------------------------------------------------------------------------------
+    def matvec_device(self, x):
+        """x: full vector on the device -> full result vector on the device (every rank)."""
+        y = self._matvec(self.block, x)
+        if not self.sharded:
+            return y
+        return self._gather_rows(y)
+
+    def _gather_rows(self, local):
+        """Concatenate the ranks' row blocks (vector entries or matrix rows); ragged blocks are padded to the
+        tallest one for the collective, which wants equal contributions."""
+        world, tall = len(self.row_counts), max(self.row_counts)
+        tail = tuple(local.shape[1:])
+        if local.shape[0] != tall:
+            padded = torch.zeros((tall,) + tail, dtype=local.dtype, device=local.device)
+            padded[:local.shape[0]] = local
+            local = padded
+        full = torch.empty((world * tall,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local.contiguous(), group=self.group)
+        if len(set(self.row_counts)) == 1:
+            return full
+        return torch.cat([full[r * tall:r * tall + c] for r, c in enumerate(self.row_counts)])
+
+    def matvec(self, x):
+        """Host vector in, host vector out (complex input: real and imaginary parts separately)."""
+        x = np.asarray(x).reshape(-1)
+        if np.iscomplexobj(x):
+            return self.matvec(x.real) + 1j * self.matvec(x.imag)
+        xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(self.block.device)
+        return self.matvec_device(xd).cpu().numpy()
+
+    def linear_operator(self):
+        return spla.LinearOperator(self.shape, matvec=self.matvec, dtype=np.float64)
+
+    # ---- element-wise algebra (device, library kernels) --------------------------------------
+    def __add__(self, other):
+        if not isinstance(other, ResidentMatrix) or other.shape != self.shape or other.row_begin != self.row_begin:
+            raise ValueError("Invalid argument!")
+        return self._like(self.block + other.block)
+
+    def __mul__(self, number):
+        return self._like(self.block * float(number))
+
+    def diagonal_shift(self, sigma):
+        """A - sigma I on this rank's rows (new buffer)."""
+        out = self.block.clone()
+        rows = out.shape[0]
+        idx = torch.arange(rows, device=out.device)
+        out[idx, idx + self.row_begin] -= float(sigma)
+        return self._like(out)
+
+    def to_host(self):
+        """The full matrix as an ndarray (gathers the row blocks; meant for sizes the host can hold)."""
+        if not self.sharded:
+            return self.block.cpu().numpy()
+        return self._gather_rows(self.block).cpu().numpy()
+
+
+class ResidentVarf:
+    """`Varf` whose matrix is a `ResidentMatrix` (see the module docstring)."""
+
+    def __init__(self, matrix, position, factor=1, index_set="triangle"):
+        if not isinstance(matrix, ResidentMatrix):
+            matrix = ResidentMatrix(matrix)
+        self.is_sparse = False
+        self.matrix = matrix
+        self.position = position
+        self.index_set = index_set
+        self.degree = core.iterator_get_degree(position.dim, matrix.n, index_set=index_set)
+        self.factor = func.Function(factor, dirs=position.dirs)
+
+    def _like(self, matrix):
+        return ResidentVarf(matrix, self.position, factor=self.factor, index_set=self.index_set)
+
+    def _compatible(self, other):
+        return isinstance(other, ResidentVarf) and self.position == other.position and \
+            self.index_set == other.index_set and self.factor == other.factor
+
+    def __add__(self, other):
+        if isinstance(other, _NUMBER):                   # element-wise, as ndarray + number (0: sum() start)
+            return self if other == 0 else self._like(self.matrix._like(self.matrix.block + float(other)))
+        if not self._compatible(other):
+            raise ValueError("Invalid argument!")
+        return self._like(self.matrix + other.matrix)
+
+    __radd__ = __add__
+
+    def __mul__(self, other):
+        if not isinstance(other, _NUMBER):
+            raise ValueError("Invalid argument: {}".format(other))
+        return self._like(self.matrix * other)
+
+    __rmul__ = __mul__
+
+    def __sub__(self, other):
+        return self + other * (-1)
+
+    def __neg__(self):
+        return self * (-1)
+
+    def __call__(self, series):
+        if not isinstance(series, hs.Series) or not self.position == series.position or \
+                self.index_set != series.index_set:
+            raise ValueError("Invalid argument!")
+        return hs.Series(self.matrix.matvec(series.coeffs), self.position, factor=self.factor,
+                         index_set=self.index_set)
+
+    def multi_indices(self):
+        return core.iterator_list_indices(self.position.dim, self.degree, index_set=self.index_set)
+
+    def to_varf(self):
+        """Host copy as a plain `Varf`."""
+        from .varf import Varf
+        return Varf(self.matrix.to_host(), self.position, factor=self.factor, index_set=self.index_set)
+
+    # ---- solvers ---------------------------------------------------------------------------------
+    def _bordered_operator(self, border):
+        """[[A, b], [b^T, 0]] as a LinearOperator (varf.py:200-206 builds this matrix explicitly)."""
+        n = self.matrix.n
+
+        def apply(v):
+            v = np.asarray(v).reshape(-1)
+            top = self.matrix.matvec(v[:n]) + border * v[n]
+            return np.append(top, border @ v[:n])
+        return spla.LinearOperator((n + 1, n + 1), matvec=apply, dtype=np.float64)
+
+    def solve(self, series, use_gmres=True, remove0=False, remove_vec=None, preconditioner=None, quiet=False,
+              **kwargs):
+        """Solve A u = series (varf.py:170-226).  GMRES (the default here: the matrix never leaves the device
+        and is not copied) drives `hb_dev_matvec`; `use_gmres=False` factorises a device copy with
+        torch.linalg.solve.  `remove0` / `remove_vec` border the system exactly as the reference does."""
+        if not self.position == series.position or self.index_set != series.index_set:
+            raise ValueError("Invalid argument: position and index set must coincide!")
+        if preconditioner is not None:
+            raise ValueError("ResidentVarf.solve: no preconditioner is available for a resident dense matrix")
+        bordered = remove0 or remove_vec is not None
+        border = None
+        if bordered:
+            if remove0:
+                [e], [remove_vec] = self.eigs(k=1, which='SM')
+                if not quiet:
+                    print("Removing eigenspace with eigenvalue {}.".format(abs(e)))
+            else:
+                remove_vec = remove_vec / np.sqrt(float(remove_vec * remove_vec))
+                e = float(remove_vec * self(remove_vec))
+                if not quiet:
+                    print("Removing vector with value {}.".format(abs(e)))
+            if abs(e) > 0.01:
+                print("[Hermipy:varf:solve warning] Value of e: {}".format(e))
+            border = np.real(np.asarray(remove_vec.coeffs)).astype(np.float64)
+        vector = np.append(series.coeffs, 0) if bordered else np.asarray(series.coeffs, dtype=np.float64)
+
+        if use_gmres:
+            op = self._bordered_operator(border) if bordered else self.matrix.linear_operator()
+            solution, info = spla.gmres(op, vector, **kwargs)
+            if info != 0 and not quiet:
+                print("[Hermipy:varf:solve warning] GMRES returned info = {}".format(info))
+        else:
+            if self.matrix.sharded:
+                raise ValueError("ResidentVarf.solve: the direct solve needs the whole matrix on one device")
+            A = self.matrix.block
+            dev = A.device
+            if bordered:
+                b = torch.from_numpy(border).to(dev)
+                A = torch.cat((torch.cat((A, b.reshape(1, -1))),
+                               torch.cat((b, torch.zeros(1, dtype=torch.float64, device=dev))).reshape(-1, 1)), dim=1)
+            rhs = torch.from_numpy(np.ascontiguousarray(vector, dtype=np.float64)).to(dev)
+            solution = torch.linalg.solve(A, rhs).cpu().numpy()
+        if bordered:
+            solution = np.array(solution[0:-1])
+        return hs.Series(solution, position=self.position, factor=self.factor, index_set=self.index_set)
+
+    @stats.log_stats()
+    def eigs(self, **kwargs):
+        """scipy.sparse.linalg.eigs (ARPACK) on the resident matrix (varf.py:228-237).  With `sigma`
+        (shift-invert) the factorisation of A - sigma I is a device LU (torch.linalg.lu_factor)."""
+        sigma = kwargs.get('sigma')
+        if sigma is not None and 'OPinv' not in kwargs:
+            if self.matrix.sharded or np.iscomplex(sigma):
+                raise ValueError("ResidentVarf.eigs: shift-invert needs a real shift and the whole matrix on one device")
+            shifted = self.matrix.diagonal_shift(sigma).block
+            LU, piv = torch.linalg.lu_factor(shifted)
+            del shifted
+
+            def opinv(v):
+                v = np.asarray(v).reshape(-1)
+                if np.iscomplexobj(v):
+                    return opinv(v.real) + 1j * opinv(v.imag)
+                rhs = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(LU.device).reshape(-1, 1)
+                return torch.linalg.lu_solve(LU, piv, rhs).reshape(-1).cpu().numpy()
+            kwargs = dict(kwargs, OPinv=spla.LinearOperator(self.matrix.shape, matvec=opinv, dtype=np.float64))
+        values, vectors = spla.eigs(self.matrix.linear_operator(), **kwargs)
+        series = []
+        for v in vectors.T:
+            v = v if la.norm(np.imag(v)) > 1e-15 else np.real(v)
+            series.append(hs.Series(v, self.position, factor=self.factor, index_set=self.index_set))
+        return values, series

@@ -159,6 +159,14 @@ int hb_dev_dgemm(int M, int N, int K, int batch, const double* A, long long lda,
 int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long long lda, long long strideA,
                          int a_mmajor, const double* B, long long ldb, long long strideB, double* const* blocks,
                          int n_blocks, int block_rows, long long ldc, long long strideC, void* cuda_stream);
+/* consumers of an assembled matrix that stays in HBM (reference: hermipy/varf.py:127-134 `Varf.__call__`,
+ * the only contact the Krylov solvers of varf.py:170-237 have with the matrix): y = A x, A row-major M x N
+ * with leading dimension lda (any parity), x and y device vectors.  HBM-bound, deterministic summation. */
+int hb_dev_matvec(int M, int N, const double* A, long long lda, const double* x, double* y, void* cuda_stream);
+/* hb_varfd on a resident row block: var / out are n_rows x n_polys device matrices (distinct buffers) */
+int hb_dev_varfd(int dim, int degree, int direction, const double* var, long long ldv, long long n_rows,
+                 size_t n_polys, int do_fourier, const char* index_set, double* out, long long ldo,
+                 void* cuda_stream);
 int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
                   long long* ld);
 /* after hb_plan_varf(HB_VARF_REFERENCE): retained alpha count and path (0 = few-alpha assembly, 1 = dense GEMM) */

@@ -89,3 +89,34 @@ def test_split_range_partitions_exactly():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(parts - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _matvec_worker(rank, world, port_no, A, x, result):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hermipy_b200.dist import split_range
+        from hermipy_b200.resident import ResidentMatrix, reference_matvec
+        lo, hi = split_range(A.shape[0], world, rank)
+        mat = ResidentMatrix(torch.from_numpy(A[lo:hi].copy()), n=A.shape[0], row_begin=lo, group=dist.group.WORLD,
+                             matvec=reference_matvec)
+        y = mat.matvec(x)
+        shifted = mat.diagonal_shift(0.25).to_host()
+        result[rank] = (y, shifted, mat.row_counts)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 11])
+def test_row_sharded_resident_matrix_world2(n):
+    """Row-sharded matrix: local product + one all-gather (even and ragged row blocks)."""
+    rng = np.random.default_rng(n)
+    A, x = rng.standard_normal((n, n)), rng.standard_normal(n)
+    result = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_matvec_worker, args=(2, _free_port(), A, x, result), nprocs=2, join=True)
+    for rank in range(2):
+        y, shifted, counts = result[rank]
+        assert sum(counts) == n
+        np.testing.assert_allclose(y, A @ x, rtol=0, atol=1e-14 * np.abs(A).sum())
+        assert np.array_equal(shifted, A - 0.25 * np.eye(n))
