@@ -426,6 +426,10 @@ def run_ours(args):
             }
             # consumer of the resident matrix: y = A x (hb_dev_matvec), HBM-bound at 8 |I|^2 bytes per product
             from hermipy_b200.resident import device_matvec
+            try:
+                mv_traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("matvec_c2_cube_bytes_per_launch")
+            except (OSError, ValueError):
+                mv_traffic = None
             xv = torch.randn(npol, dtype=torch.float64, device="cuda")
             yv = torch.empty(npol, dtype=torch.float64, device="cuda")
             ms_mv = max_over_ranks(time_steps(torch, lambda: device_matvec(out, xv, yv), 5, 2, flush, barrier)) / 5
@@ -434,7 +438,8 @@ def run_ours(args):
                                "algorithmic_bytes": 8.0 * npol ** 2, "achieved_gbs": 8.0 * npol ** 2 / ms_mv * 1e-6,
                                "peak_gbs": peaks.get("hbm_gbs"),
                                "frac": 8.0 * npol ** 2 / ms_mv * 1e-6 / peaks.get("hbm_gbs"),
-                               "rel_diff_vs_torch_mv": mv_err}
+                               "rel_diff_vs_torch_mv": mv_err,
+                               "traffic": (mv_traffic or {}).get("read") if set_name == "cube" else None}
             del xv, yv
             if args.check:
                 vplan.varf(fV, "gram", out)

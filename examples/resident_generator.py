@@ -6,12 +6,14 @@
 the matrix-vector product (`hb_dev_matvec`, HBM-bound) on the device, so only vectors cross PCIe.  At
 degree 200 on the cube set the matrix is 13 GB: one product takes 2 ms.
 """
+import os
 import sys
 
 import numpy as np
 import sympy as sym
 
-import hermipy_b200 as hm
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hermipy_b200 as hm  # noqa: E402
 
 degree = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 x, y, f = hm.x, hm.y, hm.f

@@ -3,6 +3,7 @@
     python tools/profile_target.py c2        # 2 x (forward + inverse) C2 transform step, batch 17
     python tools/profile_target.py varf      # C2 cube varf: polynomial f (banded assembly) + dense f (Gram GEMM)
     python tools/profile_target.py c5        # one C5 forward+inverse over 8192 rows
+    python tools/profile_target.py matvec    # y = A x on a 40401 x 40401 resident matrix (the C2 cube varf size)
 """
 import os
 import sys
@@ -46,5 +47,12 @@ elif which == "c5":
     f = torch.randn(8192, pl.grid_size, dtype=torch.float64, device="cuda")
     c = pl.forward(f)
     pl.backward(c)
+elif which == "matvec":
+    from hermipy_b200.resident import device_matvec
+    n = 40401
+    A = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    xv = torch.randn(n, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        yv = device_matvec(A, xv)
 torch.cuda.synchronize()
 print("done", which)
