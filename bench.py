@@ -317,18 +317,24 @@ def run_ours(args):
 
     # per-launch device times of the same step (events around every GEMM launch)
     plan.set_timing(True)
-    acc = {}
+    acc, executed = {}, {}
     for _ in range(max(K, 3)):
         flush()
         plan.forward(F, Cf)
         for tag, ms, _ in plan.timings():
             acc.setdefault(("fwd", tag), []).append(ms)
         plan.backward(Cf, G)
-        for tag, ms, _ in plan.timings():
+        for tag, ms, fl in plan.timings():
             acc.setdefault(("bwd", tag), []).append(ms)
+            executed[("bwd", tag)] = fl
     plan.set_timing(False)
-    alg = {("fwd", 2): 2.0 * B * n * n * P, ("fwd", 1): 2.0 * B * P * n * P,
-           ("bwd", 12): 2.0 * B * P * P * n, ("bwd", 11): 2.0 * B * n * P * n}
+    # algorithmic flops per stage (2 n^2 P for the stage between the grid and the half-transformed
+    # array, 2 n P^2 for the one next to the coefficients).  The inverse may run its two stages in either order
+    # (last axis first, or axis 0 first): the stage that executed more flops is the 2 n^2 P one.
+    big, small = 2.0 * B * n * n * P, 2.0 * B * P * n * P
+    alg = {("fwd", 2): big, ("fwd", 1): small}
+    first_is_big = executed.get(("bwd", 11), 1.0) >= executed.get(("bwd", 12), 0.0)
+    alg[("bwd", 11)], alg[("bwd", 12)] = (big, small) if first_is_big else (small, big)
     launches_info = {"%s_tag%d" % k: {"ms": float(np.mean(v)), "tflops_algorithmic": alg[k] / np.mean(v) * 1e-9}
                      for k, v in acc.items() if k in alg}
     dom = max((k for k in acc if k in alg), key=lambda k: np.mean(acc[k]))

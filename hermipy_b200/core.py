@@ -134,6 +134,9 @@ def transform(degree, fgrid, nodes, weights, forward, do_fourier=None, index_set
     return out
 
 
+_SIZES = {}
+
+
 def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, index_set="triangle", out=None):
     """`batch` independent transforms in one call; fgrids has shape (batch, n_in).  No reference equivalent
     (the reference loops over hm.Quad.transform in Python).  `out` may be a preallocated (batch, n_out)
@@ -143,7 +146,10 @@ def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, in
     f = _d(fgrids)
     batch = f.shape[0]
     n_grid = int(np.prod(n_pts))
-    n_polys = iterator_size(dim, int(degree), index_set)
+    key = (dim, int(degree), index_set)
+    n_polys = _SIZES.get(key)
+    if n_polys is None:                       # the decorated iterator_size costs 20 us per call
+        n_polys = _SIZES[key] = iterator_size(dim, int(degree), index_set)
     n_in, n_out = (n_grid, n_polys) if forward else (n_polys, n_grid)
     if batch == 0:
         return np.zeros((0, n_out))

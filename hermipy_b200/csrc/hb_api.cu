@@ -7,6 +7,7 @@
 #include <cstring>
 #include <list>
 #include <mutex>
+#include <chrono>
 #include <vector>
 
 #include "hb_kernels.h"
@@ -99,7 +100,7 @@ int cached_plan(hb_plan** out, int dim, const int* n_pts, int degree, const doub
 
 // staging buffers shared by the host-pointer entry points (one call at a time per process)
 std::mutex g_call_mutex;
-DevBuf g_in, g_out, g_stage, g_aux[HB_MAX_FACTORS], g_auxi[HB_MAX_FACTORS];
+DevBuf g_in, g_out, g_stage, g_stage_coef, g_aux[HB_MAX_FACTORS], g_auxi[HB_MAX_FACTORS];
 
 // last sparse result
 DevBuf g_sp_indptr, g_sp_indices, g_sp_data, g_sp_rownnz;
@@ -220,27 +221,149 @@ int hb_hermite_eval(const double* x, int n, int degree, double* out) {
 // chunk i+1 is uploaded (H2D engine) while chunk i is transformed (SMs) and chunk i-1 is downloaded (D2H
 // engine).  Three non-blocking streams chained by events; chunks run in order on the compute stream, so the
 // plan's workspace is never used by two chunks at once.
+//
+// Issuing that pipeline costs ~100 CUDA API calls (per chunk: copies, events, tensor-map encodes, 3-6 launches),
+// a few hundred microseconds of host time that is on the critical path of a 1 ms call.  A caller that keeps
+// passing the same page-locked buffers -- a time-stepping loop -- gets the whole pipeline replayed from a CUDA
+// graph instead: the first call with a given (plan, batch, direction, buffers) runs eagerly (and lets the GEMM
+// autotuner time its candidates), the second is captured, later ones are one cudaGraphLaunch.
 namespace hb {
 namespace {
 struct Pipeline {
     static const int kMaxChunks = 16;
     cudaStream_t in = nullptr, compute = nullptr, out = nullptr;
     cudaEvent_t uploaded[kMaxChunks] = {nullptr}, computed[kMaxChunks] = {nullptr};
-    bool ok = false;
+    cudaEvent_t fork = nullptr, join_in = nullptr, join_out = nullptr;
+    cudaEvent_t downloaded[kMaxChunks] = {nullptr}, start = nullptr;   // HB_PIPE_DEBUG=1: per-chunk timeline on stderr
+    bool ok = false, debug = false;
+    int last_chunks = 0;
     int init() {
         if (ok) return HB_OK;
         HB_CUDA(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
         HB_CUDA(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
         HB_CUDA(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+        debug = getenv("HB_PIPE_DEBUG") && atoi(getenv("HB_PIPE_DEBUG")) != 0;
+        const unsigned flags = debug ? cudaEventDefault : cudaEventDisableTiming;
         for (int i = 0; i < kMaxChunks; i++) {
-            HB_CUDA(cudaEventCreateWithFlags(&uploaded[i], cudaEventDisableTiming));
-            HB_CUDA(cudaEventCreateWithFlags(&computed[i], cudaEventDisableTiming));
+            HB_CUDA(cudaEventCreateWithFlags(&uploaded[i], flags));
+            HB_CUDA(cudaEventCreateWithFlags(&computed[i], flags));
+            HB_CUDA(cudaEventCreateWithFlags(&downloaded[i], flags));
         }
+        HB_CUDA(cudaEventCreateWithFlags(&start, flags));
+        HB_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        HB_CUDA(cudaEventCreateWithFlags(&join_in, cudaEventDisableTiming));
+        HB_CUDA(cudaEventCreateWithFlags(&join_out, cudaEventDisableTiming));
         ok = true;
         return HB_OK;
     }
 };
 Pipeline g_pipe;
+
+// one captured pipeline; valid while no device buffer it refers to has been freed (g_devbuf_generation)
+struct PipeGraph {
+    const hb_plan* plan = nullptr;
+    int batch = 0, forward = 0;
+    const void* src = nullptr;
+    const void* dst = nullptr;
+    unsigned long long generation = 0, stamp = 0;
+    int calls = 0;               // calls seen with this key (0: slot free)
+    bool refused = false;        // capture failed once: stay on the eager path
+    long long launches = 0;      // kernels of this library inside the graph (hb_launch_count bookkeeping)
+    cudaGraphExec_t exec = nullptr;
+    void drop() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+    }
+};
+const int kMaxPipeGraphs = 8;
+PipeGraph g_pipe_graphs[kMaxPipeGraphs];
+unsigned long long g_pipe_stamp = 0;
+
+bool page_locked(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// enqueue the whole pipeline on g_pipe's streams (eagerly, or into the capture that g_pipe.compute is in)
+int issue_pipeline(hb_plan* pl, int dim, int batch, const double* f, int forward, double* out, bool capturing) {
+    const Axis& L = pl->ax[dim - 1];
+    const long long n_grid = pl->grid_rows * L.n;
+    const long long cstride = even_up(pl->n_polys);
+    const long long in_dev = forward ? pl->grid_size : cstride, out_dev = forward ? cstride : pl->grid_size;
+    const bool pitched = L.np != L.n, cpitched = cstride != pl->n_polys;
+    // Chunk sizes.  A chunk's transform takes about as long for 2 functions as for 17 at the C2 size (one wave of
+    // GEMM tiles either way: ~60-90 us), so equal small chunks make the SMs, not PCIe, the bottleneck (6 x 88 us
+    // against 400 us of upload).  The chunks therefore HALVE: the big ones keep the compute stream behind the
+    // copy engine, and what is left exposed at the end -- transform + download of the last chunk (forward), or
+    // upload + transform of the first (inverse) -- belongs to the smallest one (each chunk takes 58 % of what is left).  Forward runs large -> small
+    // (the tail is after the last upload), inverse small -> large (the head is before the first download).
+    const double total_mb = (double)batch * pl->grid_size * 8e-6;
+    static const int max_chunks = [] { const char* e = getenv("HB_PIPE_CHUNKS"); const int v = e ? atoi(e) : 8;
+                                       return std::max(1, std::min(v, (int)Pipeline::kMaxChunks)); }();
+    int n_chunks = (int)std::min<double>(max_chunks, std::max(1.0, total_mb / 8.0 + 0.5));
+    if (total_mb >= 4.0) n_chunks = std::max(n_chunks, std::min(3, max_chunks));
+    n_chunks = std::min(n_chunks, batch);
+    int sizes[Pipeline::kMaxChunks];
+    for (int c = 0, left = batch; c < n_chunks; c++) {
+        const int chunks_left = n_chunks - c;
+        sizes[c] = chunks_left == 1 ? left : std::max(1, std::min((int)(0.58 * left + 0.99), left - (chunks_left - 1)));
+        left -= sizes[c];
+    }
+    if (!forward) std::reverse(sizes, sizes + n_chunks);
+    if (capturing) {   // fork the upload stream off the capture origin
+        HB_CUDA(cudaEventRecord(g_pipe.fork, g_pipe.compute));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.in, g_pipe.fork, 0));
+    }
+    g_pipe.last_chunks = n_chunks;
+    if (g_pipe.debug) HB_CUDA(cudaEventRecord(g_pipe.start, g_pipe.in));
+    // Host rows of n doubles <-> device rows padded to an even count (16-byte TMA rows).  A pitched copy over
+    // PCIe runs at 23 GB/s on this PCIe 5 x16 link against 55 GB/s for a flat one (tools/pcie_probe.cu), so the
+    // rows cross the bus contiguously (g_stage) and are re-pitched by a kernel (a 2-D device-to-device memcpy
+    // would queue on a copy engine, behind or ahead of the PCIe transfers the pipeline is trying to keep busy).
+    for (int c = 0, b0 = 0; c < n_chunks; b0 += sizes[c], c++) {
+        const int nb = sizes[c];
+        double* d_in = g_in.d() + (size_t)b0 * in_dev;
+        double* d_out = g_out.d() + (size_t)b0 * out_dev;
+        double* d_flat = g_stage.d() + (size_t)b0 * n_grid;
+        double* d_cflat = g_stage_coef.d() + (size_t)b0 * pl->n_polys;
+        if (forward) {
+            HB_CUDA(cudaMemcpyAsync(pitched ? d_flat : d_in, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8,
+                                    cudaMemcpyHostToDevice, g_pipe.in));
+        } else {
+            HB_CUDA(cudaMemcpyAsync(cpitched ? d_cflat : d_in, f + (size_t)b0 * pl->n_polys, (size_t)nb * pl->n_polys * 8,
+                                    cudaMemcpyHostToDevice, g_pipe.in));
+        }
+        HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.uploaded[c], 0));
+        if (forward) {
+            if (pitched) HB_TRY(launch_repack_rows(d_flat, L.n, d_in, L.np, pl->grid_rows * nb, L.n, g_pipe.compute));
+            HB_TRY(plan_forward(pl, d_in, pl->grid_size, nb, d_out, cstride, g_pipe.compute));
+            if (cpitched) HB_TRY(launch_repack_rows(d_out, cstride, d_cflat, pl->n_polys, nb, (int)pl->n_polys, g_pipe.compute));
+        } else {
+            if (cpitched) HB_TRY(launch_repack_rows(d_cflat, pl->n_polys, d_in, cstride, nb, (int)pl->n_polys, g_pipe.compute));
+            HB_TRY(plan_backward(pl, d_in, cstride, nb, d_out, pl->grid_size, g_pipe.compute));
+            if (pitched) HB_TRY(launch_repack_rows(d_out, L.np, d_flat, L.n, pl->grid_rows * nb, L.n, g_pipe.compute));
+        }
+        HB_CUDA(cudaEventRecord(g_pipe.computed[c], g_pipe.compute));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.computed[c], 0));
+        if (forward) {
+            HB_CUDA(cudaMemcpyAsync(out + (size_t)b0 * pl->n_polys, cpitched ? d_cflat : d_out, (size_t)nb * pl->n_polys * 8,
+                                    cudaMemcpyDeviceToHost, g_pipe.out));
+        } else {
+            HB_CUDA(cudaMemcpyAsync(out + (size_t)b0 * n_grid, pitched ? d_flat : d_out, (size_t)nb * n_grid * 8,
+                                    cudaMemcpyDeviceToHost, g_pipe.out));
+        }
+        if (g_pipe.debug) HB_CUDA(cudaEventRecord(g_pipe.downloaded[c], g_pipe.out));
+    }
+    if (capturing) {   // join both side streams back into the origin
+        HB_CUDA(cudaEventRecord(g_pipe.join_in, g_pipe.in));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.join_in, 0));
+        HB_CUDA(cudaEventRecord(g_pipe.join_out, g_pipe.out));
+        HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.join_out, 0));
+    }
+    return HB_OK;
+}
 }  // namespace
 }  // namespace hb
 
@@ -263,50 +386,79 @@ int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const d
     const long long in_dev = forward ? pl->grid_size : cstride, out_dev = forward ? cstride : pl->grid_size;
     HB_TRY(g_in.ensure((size_t)batch * in_dev * 8));
     HB_TRY(g_out.ensure((size_t)batch * out_dev * 8));
-    if (forward && L.np != L.n) HB_TRY(g_stage.ensure((size_t)batch * n_grid * 8));
-    // chunks of >= 2 MB of grid data, at most kMaxChunks
-    const double grid_mb = (double)pl->grid_size * 8e-6;
-    static const int max_chunks = [] { const char* e = getenv("HB_PIPE_CHUNKS"); const int v = e ? atoi(e) : 8;
-                                       return std::max(1, std::min(v, (int)Pipeline::kMaxChunks)); }();
-    int n_chunks = (int)std::min<double>(max_chunks, std::max(1.0, batch * grid_mb / 2.0));
-    n_chunks = std::min(n_chunks, batch);
-    const int per = (batch + n_chunks - 1) / n_chunks;
-    for (int c = 0, b0 = 0; b0 < batch; c++, b0 += per) {
-        const int nb = std::min(per, batch - b0);
-        double* d_in = g_in.d() + (size_t)b0 * in_dev;
-        double* d_out = g_out.d() + (size_t)b0 * out_dev;
-        if (forward && L.np == L.n) {
-            HB_CUDA(cudaMemcpyAsync(d_in, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8, cudaMemcpyHostToDevice, g_pipe.in));
-        } else if (forward) {
-            // host rows of n doubles -> device rows padded to an even count (16-byte TMA rows).  A pitched
-            // host->device copy runs at 23 GB/s on this PCIe 5 x16 link against 55 GB/s for a flat one
-            // (tools/pcie_probe.cu), so the rows cross the bus contiguously and are re-pitched on the device.
-            double* d_flat = g_stage.d() + (size_t)b0 * n_grid;
-            HB_CUDA(cudaMemcpyAsync(d_flat, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8, cudaMemcpyHostToDevice, g_pipe.in));
-            HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
-            HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.uploaded[c], 0));
-            HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)L.np * 8, d_flat, (size_t)L.n * 8, (size_t)L.n * 8,
-                                      (size_t)pl->grid_rows * nb, cudaMemcpyDeviceToDevice, g_pipe.compute));
-        } else {
-            HB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)cstride * 8, f + (size_t)b0 * pl->n_polys, (size_t)pl->n_polys * 8,
-                                      (size_t)pl->n_polys * 8, nb, cudaMemcpyHostToDevice, g_pipe.in));
+    if (L.np != L.n) HB_TRY(g_stage.ensure((size_t)batch * n_grid * 8));
+    if (cstride != pl->n_polys) HB_TRY(g_stage_coef.ensure((size_t)batch * pl->n_polys * 8));
+
+    // ---- graph replay for repeated calls on the same page-locked buffers ----
+    static const bool use_graphs = [] { const char* e = getenv("HB_PIPE_GRAPH"); return !(e && atoi(e) == 0); }();
+    PipeGraph* slot = nullptr;
+    if (use_graphs && !g_pipe.debug && (size_t)batch * n_grid * 8 >= (1u << 20) && page_locked(f) && page_locked(out)) {
+        PipeGraph* oldest = &g_pipe_graphs[0];
+        for (PipeGraph& g : g_pipe_graphs) {
+            if (g.calls && g.plan == pl && g.batch == batch && g.forward == forward && g.src == f && g.dst == out) {
+                slot = &g;
+                break;
+            }
+            if (g.stamp < oldest->stamp) oldest = &g;
         }
-        HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
-        HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.uploaded[c], 0));
-        if (forward) HB_TRY(plan_forward(pl, d_in, pl->grid_size, nb, d_out, cstride, g_pipe.compute));
-        else HB_TRY(plan_backward(pl, d_in, cstride, nb, d_out, pl->grid_size, g_pipe.compute));
-        HB_CUDA(cudaEventRecord(g_pipe.computed[c], g_pipe.compute));
-        HB_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.computed[c], 0));
-        if (forward) {
-            HB_CUDA(cudaMemcpy2DAsync(out + (size_t)b0 * pl->n_polys, (size_t)pl->n_polys * 8, d_out, (size_t)cstride * 8,
-                                      (size_t)pl->n_polys * 8, nb, cudaMemcpyDeviceToHost, g_pipe.out));
-        } else {
-            HB_CUDA(cudaMemcpy2DAsync(out + (size_t)b0 * n_grid, (size_t)L.n * 8, d_out, (size_t)L.np * 8, (size_t)L.n * 8,
-                                      (size_t)pl->grid_rows * nb, cudaMemcpyDeviceToHost, g_pipe.out));
+        if (!slot) {
+            slot = oldest;
+            slot->drop();
+            *slot = PipeGraph();
+            slot->plan = pl; slot->batch = batch; slot->forward = forward; slot->src = f; slot->dst = out;
+        }
+        slot->stamp = ++g_pipe_stamp;
+        slot->calls++;
+        const unsigned long long gen = g_devbuf_generation.load(std::memory_order_relaxed);
+        if (slot->exec && slot->generation != gen) { slot->drop(); slot->calls = 2; }   // a buffer moved: recapture
+        if (!slot->exec && slot->calls >= 2 && !slot->refused) {
+            cudaGraph_t graph = nullptr;
+            bool good = cudaStreamBeginCapture(g_pipe.compute, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (good) {
+                const long long launches_before = hb::launch_count(0);
+                const int rc = issue_pipeline(pl, dim, batch, f, forward, out, true);
+                const cudaError_t e = cudaStreamEndCapture(g_pipe.compute, &graph);
+                good = rc == HB_OK && e == cudaSuccess && graph != nullptr;
+                if (good) good = cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess;
+                if (graph) cudaGraphDestroy(graph);
+                slot->launches = hb::launch_count(0) - launches_before;
+                hb::note_launch(-slot->launches);   // nothing ran yet: replays are counted when launched
+            }
+            if (!good) {
+                cudaGetLastError();
+                slot->drop();
+                slot->refused = true;
+            }
+            // anything allocated while capturing (first use of a table) moved the generation: take it after
+            slot->generation = g_devbuf_generation.load(std::memory_order_relaxed);
+            if (good && slot->generation != gen) { slot->drop(); slot->calls = 1; }
+        }
+        if (slot->exec) {
+            HB_CUDA(cudaGraphLaunch(slot->exec, g_pipe.compute));
+            hb::note_launch(slot->launches);
+            HB_CUDA(cudaStreamSynchronize(g_pipe.compute));
+            return HB_OK;
         }
     }
+    const auto t0 = std::chrono::steady_clock::now();
+    HB_TRY(issue_pipeline(pl, dim, batch, f, forward, out, false));
+    const auto t1 = std::chrono::steady_clock::now();
     HB_CUDA(cudaStreamSynchronize(g_pipe.out));
     HB_CUDA(cudaStreamSynchronize(g_pipe.compute));
+    if (g_pipe.debug) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hb pipe] %s batch %d: issue %.0f us, issue+wait %.0f us; per chunk (us after the first upload starts):",
+                forward ? "forward" : "inverse", batch, std::chrono::duration<double, std::micro>(t1 - t0).count(),
+                std::chrono::duration<double, std::micro>(t2 - t0).count());
+        for (int c = 0; c < g_pipe.last_chunks; c++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, g_pipe.start, g_pipe.uploaded[c]);
+            cudaEventElapsedTime(&b, g_pipe.start, g_pipe.computed[c]);
+            cudaEventElapsedTime(&d, g_pipe.start, g_pipe.downloaded[c]);
+            fprintf(stderr, " [up %.0f, done %.0f, down %.0f]", a * 1e3, b * 1e3, d * 1e3);
+        }
+        fprintf(stderr, "\n");
+    }
     return HB_OK;
 }
 

@@ -130,7 +130,6 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        grid_launch_dependents();
         for (int s = 0; s < STAGES; s++) {
             mbar_init(bar_base + 8 * s, 1);
             mbar_init(bar_base + 8 * (STAGES + s), NCW);
@@ -242,6 +241,10 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     }
 
     // ---------------- epilogue ----------------
+    // Programmatic dependent launch: once every CTA is past its main loop the successor's CTAs may take the
+    // slots this grid frees and run their prologue under our epilogues (they block in grid_dependency_wait
+    // until this grid has completed).  Triggering earlier lets them steal slots from our own later waves.
+    if (warp == 0 && lane == 0) grid_launch_dependents();
     if constexpr (EPI == EPI_LUT) {
         // Scatter through the look-up table (last stage of a d-dim forward transform).  The table entries
         // of one accumulator row are fetched first (independent loads in flight together), then stored.

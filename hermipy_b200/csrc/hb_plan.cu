@@ -44,8 +44,13 @@ int launch_status() {
 }
 
 DevBuf::~DevBuf() { release(); }
+std::atomic<unsigned long long> g_devbuf_generation{0};
+
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p) {
+        cudaFree(p);
+        g_devbuf_generation.fetch_add(1, std::memory_order_relaxed);   // captured graphs hold this address
+    }
     p = nullptr;
     bytes = 0;
 }

@@ -3,6 +3,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <atomic>
 #include <vector>
 
 #include "hb_index.h"
@@ -40,6 +41,10 @@ struct DevBuf {
     double* d() const { return static_cast<double*>(p); }
     int* i() const { return static_cast<int*>(p); }
 };
+
+// bumped whenever a DevBuf frees its memory (growth, release, plan destruction): a captured CUDA graph that baked
+// device addresses in is valid only while this counter has the value it had at capture
+extern std::atomic<unsigned long long> g_devbuf_generation;
 
 inline long long even_up(long long v) { return (v + 1) & ~1LL; }
 
