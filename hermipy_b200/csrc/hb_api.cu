@@ -321,20 +321,28 @@ int issue_pipeline(hb_plan* pl, int dim, int batch, const double* f, int forward
     // PCIe runs at 23 GB/s on this PCIe 5 x16 link against 55 GB/s for a flat one (tools/pcie_probe.cu), so the
     // rows cross the bus contiguously (g_stage) and are re-pitched by a kernel (a 2-D device-to-device memcpy
     // would queue on a copy engine, behind or ahead of the PCIe transfers the pipeline is trying to keep busy).
+    // All uploads are queued first.  With both directions busy this link gives each ~30 GB/s instead of 55, so
+    // the forward transform (large uploads, small downloads) holds its downloads back until the last upload has
+    // landed: the uploads then finish at full rate and the downloads overlap the transform of the last chunk.
+    for (int c = 0, b0 = 0; c < n_chunks; b0 += sizes[c], c++) {
+        const int nb = sizes[c];
+        if (forward) {
+            double* dst = pitched ? g_stage.d() + (size_t)b0 * n_grid : g_in.d() + (size_t)b0 * in_dev;
+            HB_CUDA(cudaMemcpyAsync(dst, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8, cudaMemcpyHostToDevice, g_pipe.in));
+        } else {
+            double* dst = cpitched ? g_stage_coef.d() + (size_t)b0 * pl->n_polys : g_in.d() + (size_t)b0 * in_dev;
+            HB_CUDA(cudaMemcpyAsync(dst, f + (size_t)b0 * pl->n_polys, (size_t)nb * pl->n_polys * 8, cudaMemcpyHostToDevice,
+                                    g_pipe.in));
+        }
+        HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
+    }
+    if (forward && n_chunks > 1) HB_CUDA(cudaStreamWaitEvent(g_pipe.out, g_pipe.uploaded[n_chunks - 1], 0));
     for (int c = 0, b0 = 0; c < n_chunks; b0 += sizes[c], c++) {
         const int nb = sizes[c];
         double* d_in = g_in.d() + (size_t)b0 * in_dev;
         double* d_out = g_out.d() + (size_t)b0 * out_dev;
         double* d_flat = g_stage.d() + (size_t)b0 * n_grid;
         double* d_cflat = g_stage_coef.d() + (size_t)b0 * pl->n_polys;
-        if (forward) {
-            HB_CUDA(cudaMemcpyAsync(pitched ? d_flat : d_in, f + (size_t)b0 * n_grid, (size_t)nb * n_grid * 8,
-                                    cudaMemcpyHostToDevice, g_pipe.in));
-        } else {
-            HB_CUDA(cudaMemcpyAsync(cpitched ? d_cflat : d_in, f + (size_t)b0 * pl->n_polys, (size_t)nb * pl->n_polys * 8,
-                                    cudaMemcpyHostToDevice, g_pipe.in));
-        }
-        HB_CUDA(cudaEventRecord(g_pipe.uploaded[c], g_pipe.in));
         HB_CUDA(cudaStreamWaitEvent(g_pipe.compute, g_pipe.uploaded[c], 0));
         if (forward) {
             if (pitched) HB_TRY(launch_repack_rows(d_flat, L.n, d_in, L.np, pl->grid_rows * nb, L.n, g_pipe.compute));
