@@ -79,6 +79,20 @@ __device__ __forceinline__ long long global_ns() {
 
 constexpr int GEMM_BK = 16;  // doubles per k-tile = one 128-byte swizzle span
 
+// developer timeline (hb_debug_trace): word `w` of this CTA's 5-word record = now; record 0 also holds the SM id.
+// Called by one lane of consumer warp 0; nothing is kept in registers between calls.
+__device__ __forceinline__ void gemm_trace(long long* trace, int w) {
+    if (trace == nullptr || (long long)blockIdx.x >= trace[1]) return;
+    long long* rec = trace + 2 + 5 * (long long)blockIdx.x;
+    if (w == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        rec[0] = smid;
+        atomicAdd(reinterpret_cast<unsigned long long*>(trace), 1ull);
+    }
+    rec[w == 0 ? 1 : w + 1] = global_ns();
+}
+
 template <int BM, int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
     return STAGES * (BM + BN) * GEMM_BK * 8 + 1024 /*alignment slack*/ + 2 * STAGES * 8;
@@ -128,6 +142,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     const int tile_n = t_grp / g_rows;
     const int m_base = tile_m * BM, n_base = tile_n * BN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) gemm_trace(p.trace, 0);   // [1] CTA start
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -214,6 +229,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     for (int kt = 0; kt < KT; kt++) {
         const int s = kt % STAGES;
         mbar_wait(bar_base + 8 * s, (kt / STAGES) & 1);
+        if (kt == 0 && threadIdx.x == 0) gemm_trace(p.trace, 1);   // [2] first operands landed
         const uint8_t* st = smem_gen + s * STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ks++) {
@@ -245,6 +261,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     // slots this grid frees and run their prologue under our epilogues (they block in grid_dependency_wait
     // until this grid has completed).  Triggering earlier lets them steal slots from our own later waves.
     if (warp == 0 && lane == 0) grid_launch_dependents();
+    if (threadIdx.x == 0) gemm_trace(p.trace, 2);   // [3] main loop done
     if constexpr (EPI == EPI_LUT) {
         // Scatter through the look-up table (last stage of a d-dim forward transform).  The table entries
         // of one accumulator row are fetched first (independent loads in flight together), then stored.
@@ -273,6 +290,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
                 if (idx[nj].y >= 0) out[idx[nj].y] = acc[mi][nj][1] * p.alpha;
             }
         }
+        if (threadIdx.x == 0) gemm_trace(p.trace, 3);   // [4] this warp's epilogue issued
         return;
     }
     // Plain store.  Everything that depends only on the row (destination block, pitch, alignment) is resolved once
@@ -326,6 +344,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
             }
         }
     }
+    if (threadIdx.x == 0) gemm_trace(p.trace, 3);   // [4] this warp's epilogue issued
 }
 
 }  // namespace hb

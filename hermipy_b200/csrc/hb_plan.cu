@@ -88,6 +88,12 @@ namespace hb {
 
 int timed_gemm(hb_plan* pl, const GemmArgs& g, int tag, cudaStream_t st) {
     if (!pl->timing) return gemm_launch(g, st);
+    // developer timeline: HB_TRACE_TAG restricts the per-CTA trace (hb_debug_trace) to the launches with this tag
+    long long* trace = gemm_get_trace();
+    const char* only = trace ? getenv("HB_TRACE_TAG") : nullptr;
+    const bool mute = only && atoi(only) != tag;
+    if (mute) gemm_set_trace(nullptr);
+    struct Restore { long long* t; bool on; ~Restore() { if (on) gemm_set_trace(t); } } restore{trace, mute};
     if (pl->n_timed >= (int)pl->timed.size()) {
         hb_plan::Timed t;
         HB_CUDA(cudaEventCreate(&t.e0));

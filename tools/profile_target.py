@@ -4,6 +4,7 @@
     python tools/profile_target.py varf      # C2 cube varf: polynomial f (banded assembly) + dense f (Gram GEMM)
     python tools/profile_target.py c5        # one C5 forward+inverse over 8192 rows
     python tools/profile_target.py matvec    # y = A x on a 40401 x 40401 resident matrix (the C2 cube varf size)
+    python tools/profile_target.py gemm M N K CFG   # three launches of one plain GEMM with tile configuration CFG
 """
 import os
 import sys
@@ -47,6 +48,18 @@ elif which == "c5":
     f = torch.randn(8192, pl.grid_size, dtype=torch.float64, device="cuda")
     c = pl.forward(f)
     pl.backward(c)
+elif which == "gemm":
+    from hermipy_b200.plan import dgemm
+    M, N, K, cfg = (int(v) for v in sys.argv[2:6])
+    os.environ["HB_GEMM_CFG"] = str(cfg)
+    ev = lambda v: (v + 1) & ~1
+    A = torch.randn((M, ev(K)), dtype=torch.float64, device="cuda")
+    Bm = torch.randn((K, ev(N)), dtype=torch.float64, device="cuda")
+    Cm = torch.empty((M, ev(N)), dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        dgemm(M, N, K, A, ev(K), Bm, ev(N), Cm, ev(N))
+    torch.cuda.synchronize()
+    print("max err vs torch", float((Cm[:, :N] - A[:, :K] @ Bm[:, :N]).abs().max()))
 elif which == "matvec":
     from hermipy_b200.resident import device_matvec
     n = 40401
