@@ -81,7 +81,13 @@ constexpr int GEMM_BK = 16;  // doubles per k-tile = one 128-byte swizzle span
 
 // developer timeline (hb_debug_trace): word `w` of this CTA's 5-word record = now; record 0 also holds the SM id.
 // Called by one lane of consumer warp 0; nothing is kept in registers between calls.
+// Compiled in only with -DHB_GEMM_TRACE (make NVCC="nvcc -DHB_GEMM_TRACE"): even predicated off, the hook in the
+// main loop cost the 128-register two-CTA configurations 2 us of a 37 us kernel.
 __device__ __forceinline__ void gemm_trace(long long* trace, int w) {
+#ifndef HB_GEMM_TRACE
+    (void)trace; (void)w;
+    return;
+#endif
     if (trace == nullptr || (long long)blockIdx.x >= trace[1]) return;
     long long* rec = trace + 2 + 5 * (long long)blockIdx.x;
     if (w == 0) {
@@ -117,9 +123,15 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                           const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     constexpr int NCW = WARPS_M * WARPS_N;  // consumer warps
-    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
-    constexpr int MI = WM / 8, NJ = WN / 8;
-    static_assert(WN % 8 == 0 && WM % 8 == 0 && BN % 16 == 0 && (!A_MMAJOR || BM % 16 == 0), "tile granularity");
+    constexpr int WM = BM / WARPS_M;
+    // The tile is NU = BN/8 eight-column MMA slots wide.  When WARPS_N does not divide NU the first NU % WARPS_N
+    // warp columns take one slot more (RAGGED): NJ is the per-warp maximum, `nj_full` says whether this warp uses
+    // its last slot.  (48 x 208 over 2 x 4 warps: 7,7,6,6 slots -- with warp w on sub-partition w % 4 and
+    // wn = w / 2, every sub-partition gets 13 slots x 3 row blocks.)
+    constexpr int NU = BN / 8;
+    constexpr int NJ = (NU + WARPS_N - 1) / WARPS_N, MI = WM / 8;
+    constexpr bool RAGGED = (NU % WARPS_N) != 0;
+    static_assert(BM % WARPS_M == 0 && WM % 8 == 0 && BN % 16 == 0 && (!A_MMAJOR || BM % 16 == 0), "tile granularity");
     constexpr int A_BYTES = BM * GEMM_BK * 8, B_BYTES = BN * GEMM_BK * 8;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 
@@ -194,6 +206,8 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     // ---------------- consumers: DMMA ----------------
     if constexpr (Regs::kRealloc) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Regs::kConsumer));
     const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    const int jn0 = RAGGED ? wn * (NU / WARPS_N) + min(wn, NU % WARPS_N) : wn * NJ;   // first MMA slot along N
+    const bool nj_full = !RAGGED || wn < NU % WARPS_N;
     const int g = lane >> 2, t = lane & 3;
     const int rm = 2 * (g & 3) + (g >> 2);                          // rowmap(g)
     const int cm = (g & 1) + 8 * ((g >> 1) & 1) + 2 * (g >> 2);     // colmap(g)
@@ -215,7 +229,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     }
 #pragma unroll
     for (int nj = 0; nj < NJ; nj++) {
-        const int jn = wn * NJ + nj;  // MMA slot along N: 16-wide group jn>>1, half jn&1
+        const int jn = jn0 + nj;  // MMA slot along N: 16-wide group jn>>1, half jn&1
         const int n_in = 4 * (jn & 1) + cm;
         b_off[nj] = A_BYTES + (jn >> 1) * 2048 + t * 128 + ((((n_in >> 1) ^ t)) << 4) + (n_in & 1) * 8;
     }
@@ -245,12 +259,14 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {
                 const uint32_t o = (b_off[nj] + 512 * ks) ^ ((ks & 1) << 6);
-                bf[nj] = *reinterpret_cast<const double*>(st + o);
+                bf[nj] = 0.0;
+                if (!RAGGED || nj < NJ - 1 || nj_full) bf[nj] = *reinterpret_cast<const double*>(st + o);
             }
 #pragma unroll
             for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int nj = 0; nj < NJ; nj++) dmma_8x8x4(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
+                for (int nj = 0; nj < NJ; nj++)
+                    if (!RAGGED || nj < NJ - 1 || nj_full) dmma_8x8x4(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
@@ -275,9 +291,10 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
             int2 idx[NJ];
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {
-                const int jn = wn * NJ + nj;
+                const int jn = jn0 + nj;
                 const int col = n_base + 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
                 idx[nj] = make_int2(-1, -1);
+                if (RAGGED && nj == NJ - 1 && !nj_full) continue;   // slot not owned by this warp
                 if (col + 1 < p.N && (p.N & 1) == 0) idx[nj] = __ldg(reinterpret_cast<const int2*>(lrow + col));
                 else {
                     if (col < p.N) idx[nj].x = __ldg(lrow + col);
@@ -309,9 +326,10 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         if (p.col_stride != 1) {   // interleaved output (even / odd coefficients of the 1-D parity transform)
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {
-                const int jn = wn * NJ + nj;
+                const int jn = jn0 + nj;
                 const int col = n_base + 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
                 if (col >= p.N) continue;
+                if (RAGGED && nj == NJ - 1 && !nj_full) continue;   // slot not owned by this warp
                 double* dst = rowp + p.col_offset + (long long)col * p.col_stride;
                 dst[0] = acc[mi][nj][0] * p.alpha;
                 if (col + 1 < p.N) dst[p.col_stride] = acc[mi][nj][1] * p.alpha;
@@ -323,7 +341,8 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         if (vec && interior_n) {
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {
-                const int jn = wn * NJ + nj;
+                const int jn = jn0 + nj;
+                if (RAGGED && nj == NJ - 1 && !nj_full) continue;   // slot not owned by this warp
                 *reinterpret_cast<double2*>(base + 16 * (jn >> 1) + 4 * (jn & 1)) =
                     make_double2(acc[mi][nj][0] * p.alpha, acc[mi][nj][1] * p.alpha);
             }
@@ -331,10 +350,11 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         }
 #pragma unroll
         for (int nj = 0; nj < NJ; nj++) {
-            const int jn = wn * NJ + nj;
+            const int jn = jn0 + nj;
             const int off = 16 * (jn >> 1) + 4 * (jn & 1);
             const int col = n_base + off + 8 * (t & 1) + 2 * (t >> 1);
             if (col >= p.N) continue;
+            if (RAGGED && nj == NJ - 1 && !nj_full) continue;   // slot not owned by this warp
             const double v0 = acc[mi][nj][0] * p.alpha, v1 = acc[mi][nj][1] * p.alpha;
             if (vec && col + 1 < p.N) {
                 *reinterpret_cast<double2*>(base + off) = make_double2(v0, v1);

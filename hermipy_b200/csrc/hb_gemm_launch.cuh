@@ -16,6 +16,9 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
 // Tile configurations {BM, BN, warps along M, warps along N, pipeline stages, resident CTAs per SM}.  The number
 // of consumer warps is a multiple of 4 everywhere: FP64 DMMA issues at one instruction per 16 clocks per SM
 // sub-partition, so 6 consumer warps (2+2+1+1 over the four sub-partitions) cap the tile at 75 % of the rate.
+// One warp per sub-partition cannot keep that cadence alone either (19.3 clocks per DMMA measured in the main loop
+// of configuration 5: 83 %), two can (96 % for configuration 1): configuration 8 is configuration 5's tile on
+// 2 x 4 consumer warps, the 26 column slots dealt 7,7,6,6 so that each sub-partition owns 39 of the 156 MMAs.
 #define HB_GEMM_CONFIGS(X, AM, EPI)   \
     X(0, 128, 128, 4, 2, 4, AM, 1, EPI) \
     X(1, 64, 64, 2, 2, 6, AM, 2, EPI)   \
@@ -24,7 +27,8 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
     X(4, 32, 208, 2, 2, 3, AM, 2, EPI)  \
     X(5, 48, 208, 2, 2, 4, AM, 1, EPI)  \
     X(6, 96, 128, 4, 2, 4, AM, 1, EPI)  \
-    X(7, 32, 128, 2, 2, 4, AM, 2, EPI)
+    X(7, 32, 128, 2, 2, 4, AM, 2, EPI)  \
+    X(8, 48, 208, 2, 4, 4, AM, 1, EPI)
 
 template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB, int EPI>
 static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-N_CFGS = 8
+N_CFGS = 9
 
 
 def _run(torch, M, N, K, batch, a_mmajor, shared_a, cfg):
@@ -46,6 +46,28 @@ def test_every_tile_configuration(cfg, a_mmajor):
                                      (32, 256, 256, 4, True), (1, 64, 64, 1, False), (515, 333, 77, 2, True)]:
         err = _run(torch, M, N, K, batch, a_mmajor, shared, cfg)
         assert err < 1e-14, (cfg, a_mmajor, M, N, K, batch, shared, err)
+
+
+def test_tile_configurations_agree_bitwise():
+    """Every configuration accumulates each output over k in the same order: the autotuner's choice (which depends
+    on timing) must never change a result."""
+    import torch
+    from hermipy_b200.plan import dgemm
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K, batch = 530, 402, 201, 3
+    A = torch.randn((M, K + 1), generator=g, dtype=torch.float64, device="cuda")
+    B = torch.randn((batch, K, N), generator=g, dtype=torch.float64, device="cuda")
+    results = []
+    for cfg in range(N_CFGS):
+        C = torch.zeros((batch, M, N), dtype=torch.float64, device="cuda")
+        os.environ["HB_GEMM_CFG"] = str(cfg)
+        try:
+            dgemm(M, N, K, A, K + 1, B, N, C, N, batch=batch, strideA=0, strideB=B.stride(0), strideC=C.stride(0))
+        finally:
+            os.environ["HB_GEMM_CFG"] = "-1"
+        results.append(C)
+    for cfg in range(1, N_CFGS):
+        assert torch.equal(results[cfg], results[0]), cfg
 
 
 def test_alignment_is_checked():

@@ -1,4 +1,4 @@
-"""Developer script: per-CTA timeline of every GEMM launch of one C2 forward + inverse transform (batch 17).
+"""Developer script (needs a library built with `make -C hermipy_b200/csrc NVCC="nvcc -DHB_GEMM_TRACE"`): per-CTA timeline of every GEMM launch of one C2 forward + inverse transform (batch 17).
 For each launch: when CTAs start relative to the first one, how long until their first operands land, main-loop
 and epilogue durations, and what is left between the last CTA's end and ... the next launch's first CTA."""
 import ctypes as C, os, sys
