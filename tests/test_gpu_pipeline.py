@@ -73,3 +73,25 @@ def test_alternating_buffers_and_plans_keep_separate_graphs():
             core.transform_batch(degree, f_pin, nodes, weights, True, index_set="cube", out=c_pin)
             want = core.transform_batch(degree, f_pin.copy(), nodes, weights, True, index_set="cube")
             assert np.array_equal(c_pin, want), (call, degree)
+
+
+@pytest.mark.parametrize("dim,n,degree,batch,index_set", [(1, 257, 128, 4096, "triangle"), (1, 64, 63, 20000, "cube"),
+                                                          (3, 48, 20, 5, "triangle"), (3, 32, 31, 6, "cube")])
+def test_graph_replay_other_dimensions(dim, n, degree, batch, index_set):
+    """1-D batches (even and odd row lengths: with and without the re-pitch kernels) and 3-D grids through the
+    pinned-buffer path, forward and inverse, against the eager path."""
+    from hermipy_b200 import core
+    x, w = gauss_hermite(n)
+    nodes, weights = [x] * dim, [w] * dim
+    npol = core.iterator_size(dim, degree, index_set)
+    rng = np.random.default_rng(dim * 1000 + n)
+    f_pin, c_pin, g_pin = _pinned((batch, n ** dim)), _pinned((batch, npol)), _pinned((batch, n ** dim))
+    for call in range(4):
+        f = rng.standard_normal((batch, n ** dim))
+        f_pin[:] = f
+        core.transform_batch(degree, f_pin, nodes, weights, True, index_set=index_set, out=c_pin)
+        want_c = core.transform_batch(degree, f, nodes, weights, True, index_set=index_set)
+        assert np.array_equal(c_pin, want_c), call
+        core.transform_batch(degree, c_pin, nodes, weights, False, index_set=index_set, out=g_pin)
+        want_g = core.transform_batch(degree, want_c, nodes, weights, False, index_set=index_set)
+        assert np.array_equal(g_pin, want_g), call
