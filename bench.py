@@ -379,7 +379,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     n_polys = plan.n_polys
     e2e = {"value": world * pts_per_step * e2e_reps / e2e_s * 1e-9, "unit": "Gpts/s",
-           "h2d_bytes_per_step": 8 * B * (n * n + n_polys), "d2h_bytes_per_step": 8 * B * (n * n + n_polys),
+           "h2d_bytes_per_step": world * 8 * B * (n * n + n_polys), "d2h_bytes_per_step": world * 8 * B * (n * n + n_polys),
            "api": "hermipy_b200.core.transform_batch (hb_transform_batch: host buffers, copies inside)"}
 
     # ---------------- varf of the same config ----------------
