@@ -554,10 +554,11 @@ __global__ void varf_band_kernel(VarfSparseArgs a, VarfBandArgs b, double* __res
     out[(long long)(r - a.row_begin) * a.ldo + c] = acc;
 }
 
-int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s) {
+int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s, bool zero_filled) {
     const long long rows = a.row_end - a.row_begin;
     if (rows <= 0) return HB_OK;
-    if (cudaMemset2DAsync(out, (size_t)a.ldo * 8, 0, (size_t)a.n_polys * 8, (size_t)rows, s) != cudaSuccess)
+    if (!zero_filled &&
+        cudaMemset2DAsync(out, (size_t)a.ldo * 8, 0, (size_t)a.n_polys * 8, (size_t)rows, s) != cudaSuccess)
         return HB_ERR_CUDA;
     const long long total = rows * b.width_total;
     if (total == 0) return HB_OK;

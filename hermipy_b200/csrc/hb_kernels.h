@@ -65,7 +65,8 @@ struct VarfBandArgs {
     long long width_total;    // prod (2*amax+1)
     const int* lut_box;       // padded lexicographic box -> position (-1 absent)
 };
-int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s);
+int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s,
+                     bool zero_filled = false);   // zero_filled: the caller has already cleared the rows
 
 int launch_inner(const double* s1, const double* s2, const int* ind1, const int* ind2, int n_res, int n_inner,
                  double* out, cudaStream_t s);

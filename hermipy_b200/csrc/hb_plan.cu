@@ -78,6 +78,10 @@ int DevBuf::ensure_zero(size_t need, cudaStream_t s) {
 
 hb_plan::~hb_plan() {
     delete plan2;
+    if (fill_stream) cudaStreamDestroy(fill_stream);
+    if (fill_ready) cudaEventDestroy(fill_ready);
+    if (fill_done) cudaEventDestroy(fill_done);
+    if (h_Hf_pinned) cudaFreeHost(h_Hf_pinned);
     for (Timed& t : timed) {
         if (t.e0) cudaEventDestroy(t.e0);
         if (t.e1) cudaEventDestroy(t.e1);
@@ -870,13 +874,48 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     hb_plan* p2 = pl->plan2;
     const long long n2 = p2->n_polys;
     HB_TRY(pl->Hf.ensure(even_up(n2) * 8));
+    // The banded assembly (polynomial-like f: the regime the reference algebra is meaningful in) is a zero-fill of
+    // the output (HBM-write-bound, 1.8 ms for the 13 GB C2 cube matrix) plus a few entries per row.  What precedes
+    // it -- transform of f at degree 2N, fetching Hf, the sequential norm and threshold on the host, ~0.6 ms --
+    // does not touch the output, so when the previous call on this plan ended in the banded assembly the zero-fill
+    // starts now on a side stream and the band kernel waits for it.  (A wrong guess only costs the wait.)
+    const long long fill_rows = row_end - row_begin;
+    static const bool early_fill_enabled = [] { const char* e = getenv("HB_VARF_EARLY_FILL"); return !(e && e[0] == '0'); }();
+    const bool early_fill = early_fill_enabled && pl->last_path == 2 && fill_rows > 0;
+    if (early_fill) {
+        if (!pl->fill_stream) {
+            HB_CUDA(cudaStreamCreateWithFlags(&pl->fill_stream, cudaStreamNonBlocking));
+            HB_CUDA(cudaEventCreateWithFlags(&pl->fill_ready, cudaEventDisableTiming));
+            HB_CUDA(cudaEventCreateWithFlags(&pl->fill_done, cudaEventDisableTiming));
+        }
+    }
     HB_TRY(plan_forward(p2, d_f, pl->grid_size, 1, pl->Hf.d(), even_up(n2), st));
-    pl->h_Hf.resize(n2);
-    HB_CUDA(cudaMemcpyAsync(pl->h_Hf.data(), pl->Hf.p, n2 * 8, cudaMemcpyDeviceToHost, st));
+    if (pl->h_Hf_pinned_len < (size_t)n2) {
+        if (pl->h_Hf_pinned) cudaFreeHost(pl->h_Hf_pinned);
+        pl->h_Hf_pinned = nullptr;
+        pl->h_Hf_pinned_len = 0;
+        HB_CUDA(cudaMallocHost(&pl->h_Hf_pinned, (size_t)n2 * 8));
+        pl->h_Hf_pinned_len = (size_t)n2;
+    }
+    // Hf goes to the host through a kernel that stores into the page-locked buffer (mapped under unified
+    // addressing), not through cudaMemcpyAsync: the copy engine is what executes the zero-fill, and a D2H copy
+    // queued behind it waited the whole 1.8 ms (measured: no gain from the early fill until this changed).
+    if (early_fill) {
+        HB_TRY(launch_repack_rows(pl->Hf.d(), n2, pl->h_Hf_pinned, n2, 1, (int)n2, st));
+        // The fill is queued behind the (60 us) transform: launched first, its CTAs would hold every SM slot and the
+        // transform kernels of `st` -- same priority -- would run after it.
+        HB_CUDA(cudaEventRecord(pl->fill_ready, st));                 // earlier users of the output buffer
+        HB_CUDA(cudaStreamWaitEvent(pl->fill_stream, pl->fill_ready, 0));
+        HB_CUDA(cudaMemset2DAsync(d_out, (size_t)ldo * 8, 0, (size_t)pl->n_polys * 8, (size_t)fill_rows, pl->fill_stream));
+        HB_CUDA(cudaEventRecord(pl->fill_done, pl->fill_stream));
+    } else {
+        HB_CUDA(cudaMemcpyAsync(pl->h_Hf_pinned, pl->Hf.p, n2 * 8, cudaMemcpyDeviceToHost, st));
+    }
     HB_CUDA(cudaStreamSynchronize(st));
+    if (early_fill) HB_CUDA(cudaStreamWaitEvent(st, pl->fill_done, 0));   // everything queued on st from here on
     // threshold exactly as the reference: sequential sum of squares, sqrt, max(norm,1) (varf.cpp:190-195),
     // keep alpha unless |Hf| < 1e-12*norm (:238-241; a NaN coefficient is therefore kept).
-    const std::vector<double>& Hf = pl->h_Hf;
+    const double* Hf = pl->h_Hf_pinned;
     double norm = 0;
     for (long long i = 0; i < n2; i++) norm += std::fabs(Hf[i]) * std::fabs(Hf[i]);
     norm = std::sqrt(norm);
@@ -947,7 +986,7 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
         b.width_total = 1;
         for (int k = 0; k < d; k++) b.width_total *= 2 * b.amax[k] + 1;
         pl->last_path = 2;
-        return launch_varf_band(a, b, d_out, st);
+        return launch_varf_band(a, b, d_out, st, /*zero_filled=*/early_fill);
     }
     return launch_varf_sparse(a, d_out, st);
 }

@@ -101,6 +101,12 @@ struct hb_plan {
     long long tiles_key[3] = {-1, -1, -1};
     int n_tiles = 0;
     int last_n_kept = 0, last_path = 0;
+    // reference-algebra varf: speculative zero-fill of the output on a side stream while Hf is transformed,
+    // fetched and thresholded on the host (taken when the previous call on this plan ended in the banded assembly)
+    cudaStream_t fill_stream = nullptr;
+    cudaEvent_t fill_ready = nullptr, fill_done = nullptr;
+    double* h_Hf_pinned = nullptr;     // page-locked copy of Hf for the host-side threshold
+    size_t h_Hf_pinned_len = 0;
     // optional device timing (CUDA events on the launch stream) of every GEMM launch of the last call
     struct Timed { cudaEvent_t e0 = nullptr, e1 = nullptr; int tag = 0; double flops = 0; };
     bool timing = false;
