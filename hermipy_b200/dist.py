@@ -11,7 +11,8 @@ results.  Sharding follows the structure of each workload
     (tiles that hold no owned row are skipped inside the GEMM), never gathered.
 
 The host-side logic (partitioning, layouts, the exchange) also runs on CPU tensors with the gloo
-backend so that it can be tested without GPUs: pass `gemm=reference_gemm`.
+backend so that it can be tested without GPUs: the tests inject a CPU stand-in for the GEMM (`gemm=`, defined
+in tests/test_dist_gloo.py); the package itself ships no CPU arithmetic.
 """
 import numpy as np
 import torch
@@ -27,11 +28,6 @@ def split_range(total, parts, index):
     base, rem = divmod(total, parts)
     lo = index * base + min(index, rem)
     return lo, lo + base + (1 if index < rem else 0)
-
-
-def reference_gemm(A, B, out):
-    """CPU stand-in with the device GEMM's semantics (out[b] = A[b] @ B[b]); host-logic tests only."""
-    torch.matmul(A, B, out=out)
 
 
 def device_gemm(A, B, out):

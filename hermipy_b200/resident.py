@@ -44,15 +44,6 @@ def device_matvec(A, x, out=None):
     return out
 
 
-def reference_matvec(A, x, out=None):
-    """CPU stand-in with device_matvec's semantics; host-logic (gloo) tests only."""
-    res = torch.mv(A, x)
-    if out is None:
-        return res
-    out.copy_(res)
-    return out
-
-
 class ResidentMatrix:
     """Rows [row_begin, row_begin + block.shape[0]) of an n x n matrix; `block` is a float64 tensor on the
     compute device.  With a process group the row blocks of all ranks (contiguous, in rank order) form the

@@ -11,8 +11,23 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from conftest import gauss_hermite
-from hermipy_b200.dist import ShardedTransform, even_up, reference_gemm, split_range
+from hermipy_b200.dist import ShardedTransform, even_up, split_range
 from oracle import port
+
+
+def reference_gemm(A, B, out):
+    """CPU stand-in with the device GEMM's semantics (out[b] = A[b] @ B[b]): the gloo tests exercise the host
+    logic (partitioning, layouts, the exchange), not the arithmetic."""
+    torch.matmul(A, B, out=out)
+
+
+def reference_matvec(A, x, out=None):
+    """CPU stand-in with hermipy_b200.resident.device_matvec's semantics."""
+    res = torch.mv(A, x)
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
 
 N_PTS, P = [6, 5, 7], [4, 5, 3]
 
@@ -97,7 +112,7 @@ def _matvec_worker(rank, world, port_no, A, x, result):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from hermipy_b200.dist import split_range
-        from hermipy_b200.resident import ResidentMatrix, reference_matvec
+        from hermipy_b200.resident import ResidentMatrix
         lo, hi = split_range(A.shape[0], world, rank)
         mat = ResidentMatrix(torch.from_numpy(A[lo:hi].copy()), n=A.shape[0], row_begin=lo, group=dist.group.WORLD,
                              matvec=reference_matvec)
