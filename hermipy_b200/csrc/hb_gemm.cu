@@ -56,9 +56,9 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
 // modelled time: small or oddly shaped problems (P = 201, n = 401, batch 17 ...) otherwise lose most of
 // their time to tile quantisation and partial waves over the 148 SMs.
 struct TileCfg { int bm, bn, ctas; };
-static const int kNumCfgs = 9;
+static const int kNumCfgs = 10;
 static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2},
-                                {48, 208, 1},  {96, 128, 1}, {32, 128, 2}, {48, 208, 1}};
+                                {48, 208, 1},  {96, 128, 1}, {32, 128, 2}, {48, 208, 1}, {32, 208, 1}};
 
 // Modelled time (microseconds) of configuration i on the problem `a`: full waves over 148 SMs x resident CTAs,
 // a partial last wave, a per-configuration steady-state efficiency and a per-configuration fixed cost
@@ -66,8 +66,8 @@ static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 2
 // least-squares fit to tools/cfg_sweep.py on B200 (nine shapes from 0.5 GFLOP to 1.3 TFLOP, fit error <= 10 %
 // except for partial second waves of the two-CTA configurations).
 static double model_us(const GemmArgs& a, int i) {
-    static const double kEff[kNumCfgs] = {1.005, 1.036, 0.956, 0.957, 0.926, 0.881, 0.994, 0.979, 0.96};
-    static const double kFixedUs[kNumCfgs] = {7.8, 11.7, 10.0, 6.9, 12.0, 7.9, 5.8, 10.8, 7.9};
+    static const double kEff[kNumCfgs] = {1.005, 1.036, 0.956, 0.957, 0.926, 0.881, 0.994, 0.979, 0.96, 0.90};
+    static const double kFixedUs[kNumCfgs] = {7.8, 11.7, 10.0, 6.9, 12.0, 7.9, 5.8, 10.8, 7.9, 7.0};
     const double sms = 148.0, clk_per_us = 1920.0;
     const double ksteps = (a.K + 15) / 16;
     const TileCfg& c = kCfgs[i];

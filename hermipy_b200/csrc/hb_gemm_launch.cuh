@@ -18,7 +18,8 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
 // sub-partition, so 6 consumer warps (2+2+1+1 over the four sub-partitions) cap the tile at 75 % of the rate.
 // One warp per sub-partition cannot keep that cadence alone either (19.3 clocks per DMMA measured in the main loop
 // of configuration 5: 83 %), two can (96 % for configuration 1): configuration 8 is configuration 5's tile on
-// 2 x 4 consumer warps, the 26 column slots dealt 7,7,6,6 so that each sub-partition owns 39 of the 156 MMAs.
+// 2 x 4 consumer warps, the 26 column slots dealt 7,7,6,6 so that each sub-partition owns 39 of the 156 MMAs;
+// configuration 9 does the same for the 32 x 208 tile when its tiles fit one wave at one CTA per SM.
 #define HB_GEMM_CONFIGS(X, AM, EPI)   \
     X(0, 128, 128, 4, 2, 4, AM, 1, EPI) \
     X(1, 64, 64, 2, 2, 6, AM, 2, EPI)   \
@@ -28,7 +29,8 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
     X(5, 48, 208, 2, 2, 4, AM, 1, EPI)  \
     X(6, 96, 128, 4, 2, 4, AM, 1, EPI)  \
     X(7, 32, 128, 2, 2, 4, AM, 2, EPI)  \
-    X(8, 48, 208, 2, 4, 4, AM, 1, EPI)
+    X(8, 48, 208, 2, 4, 4, AM, 1, EPI)  \
+    X(9, 32, 208, 2, 4, 4, AM, 1, EPI)
 
 template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB, int EPI>
 static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-N_CFGS = 9
+N_CFGS = 10
 
 
 def _run(torch, M, N, K, batch, a_mmajor, shared_a, cfg):
