@@ -1,6 +1,7 @@
 // Host-side launch template of the DMMA/TMA GEMM, shared by the translation units that instantiate the
 // kernel (hb_gemm_inst_*.cu: one per (epilogue, A layout) so that they compile in parallel).
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 
 #include "hb_gemm.cuh"
@@ -54,8 +55,15 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
     p.group_m = a.group_m > 0 ? a.group_m : 1;
     p.a_bmul = a_batched ? 1 : 0;
     p.b_bmul = b_batched ? 1 : 0;
-    const long long n_cta = (long long)p.tiles_m * p.tiles_n * a.batch;
-    if (n_cta > 0x7fffffffLL) return HB_ERR_INVALID;
+    const long long n_tiles = (long long)p.tiles_m * p.tiles_n * a.batch;
+    if (n_tiles > 0x7fffffffLL) return HB_ERR_INVALID;
+    p.n_tiles = (int)n_tiles;
+    static const int sm_count = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        return n;
+    }();
+    const long long n_cta = std::min<long long>(n_tiles, (long long)sm_count * MINB);   // persistent: one wave
     auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM, MINB, EPI>;
     constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
     static bool attr_set = false;
