@@ -60,7 +60,9 @@ static const int kNumCfgs = 10;
 static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2},
                                 {48, 208, 1},  {96, 128, 1}, {32, 128, 2}, {48, 208, 1}, {32, 208, 1}};
 
-// Modelled time (microseconds) of configuration i on the problem `a`: full waves over 148 SMs x resident CTAs,
+// Modelled time (microseconds) of configuration i on the problem `a` (used to rank candidates; fitted before the
+// CTAs became persistent, so the per-wave fixed cost is now pessimistic for multi-wave problems -- the first-call
+// tuner, which measures, has the last word for everything below 150 us): full waves over 148 SMs x resident CTAs,
 // a partial last wave, a per-configuration steady-state efficiency and a per-configuration fixed cost
 // (prologue + epilogue, largely hidden between co-resident CTAs).  Efficiencies and fixed costs are a
 // least-squares fit to tools/cfg_sweep.py on B200 (nine shapes from 0.5 GFLOP to 1.3 TFLOP, fit error <= 10 %
@@ -80,16 +82,6 @@ static double model_us(const GemmArgs& a, int i) {
     double n_fixed = full * (c.ctas > 1 ? 0.3 : 1.0);
     if (rem) { clk += std::ceil((double)rem / sms) * tile_t; n_fixed += 1.0; }
     return clk / clk_per_us / kEff[i] + n_fixed * kFixedUs[i];
-}
-
-static int pick_cfg(const GemmArgs& a) {
-    int best_i = 0;
-    double best = 1e300;
-    for (int i = 0; i < kNumCfgs; i++) {
-        const double t = model_us(a, i);
-        if (t < best) { best = t; best_i = i; }
-    }
-    return best_i;
 }
 
 static int dispatch(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);

@@ -73,10 +73,9 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
         attr_set = true;
     }
     // Programmatic dependent launch (opt-in, HB_GEMM_PDL=1): the CTA launch and barrier setup of this kernel overlap
-    // the tail of its predecessor in the stream (every warp blocks in griddepcontrol.wait before touching operands).
-    // Measured on B200: C4 1.63 -> 1.60 ms, but the C2 step of five 30-60 us kernels gets SLOWER (170 -> 191 us in a
-    // CUDA graph: the early CTAs take shared memory and registers from the kernel that is still running), so it is
-    // off by default.
+    // the tail of its predecessor in the stream (every warp blocks in griddepcontrol.wait before touching operands;
+    // the predecessor triggers after the main loop of its last tile).  Measured on B200: C4 1.45 -> 1.42 ms, but the
+    // C2 step of four 30-55 us GEMMs replayed from a CUDA graph gets SLOWER (163 -> 185 us), so it is off by default.
     static const bool pdl = [] { const char* e = getenv("HB_GEMM_PDL"); return e && e[0] == '1'; }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_cta);
