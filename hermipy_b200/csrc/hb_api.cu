@@ -296,8 +296,9 @@ int issue_pipeline(hb_plan* pl, int dim, int batch, const double* f, int forward
     // GEMM tiles either way: ~60-90 us), so equal small chunks make the SMs, not PCIe, the bottleneck (6 x 88 us
     // against 400 us of upload).  The chunks therefore HALVE: the big ones keep the compute stream behind the
     // copy engine, and what is left exposed at the end -- transform + download of the last chunk (forward), or
-    // upload + transform of the first (inverse) -- belongs to the smallest one (each chunk takes 58 % of what is left).  Forward runs large -> small
-    // (the tail is after the last upload), inverse small -> large (the head is before the first download).
+    // upload + transform of the first (inverse) -- belongs to the smallest one (each chunk takes 58 % of what is
+    // left).  Forward runs large -> small (the tail is after the last upload), inverse small -> large (the head
+    // is before the first download).
     const double total_mb = (double)batch * pl->grid_size * 8e-6;
     static const int max_chunks = [] { const char* e = getenv("HB_PIPE_CHUNKS"); const int v = e ? atoi(e) : 8;
                                        return std::max(1, std::min(v, (int)Pipeline::kMaxChunks)); }();
