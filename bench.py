@@ -341,7 +341,8 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("c2_transform_dominant_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("c2_transform_bytes_per_launch", {}).get("%s_tag%d" % dom, tj.get("c2_transform_dominant_bytes_per_launch"))
     roofline = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (%s stage, tag %d)" % dom,
                 "achieved": alg[dom] / np.mean(acc[dom]) * 1e-9, "peak": dgemm_burst, "unit": "TFLOP/s",
                 "frac": alg[dom] / np.mean(acc[dom]) * 1e-9 / dgemm_burst, "traffic": traffic,
