@@ -359,6 +359,19 @@ def run_ours(args):
     rt = float((((G - F) * sw).norm() / (F * sw).norm()).item())
 
     # ---------------- e2e: the host-pointer C ABI with pinned host buffers ----------------
+    # One rank per GPU: the page-locked buffers and the thread that drives the copies should sit on the NUMA node
+    # the GPU hangs off (NVML knows which CPUs those are); the previous affinity is restored afterwards because the
+    # CPU-baseline leg wants every core.
+    old_affinity, numa_note = os.sched_getaffinity(0), "unchanged"
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(torch.cuda.current_device())
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        numa_note = "%d CPUs near the GPU (NVML)" % len(os.sched_getaffinity(0))
+    except Exception as exc:                      # no NVML, no permission: run unbound
+        numa_note = "unbound (%s)" % type(exc).__name__
     Fh = torch.empty((B, n * n), dtype=torch.float64).pin_memory()
     Fh.copy_(torch.from_numpy(F_host.reshape(B, -1)))
     Fnp = Fh.numpy()
@@ -381,7 +394,9 @@ def run_ours(args):
     n_polys = plan.n_polys
     e2e = {"value": world * pts_per_step * e2e_reps / e2e_s * 1e-9, "unit": "Gpts/s",
            "h2d_bytes_per_step": world * 8 * B * (n * n + n_polys), "d2h_bytes_per_step": world * 8 * B * (n * n + n_polys),
-           "api": "hermipy_b200.core.transform_batch (hb_transform_batch: host buffers, copies inside)"}
+           "api": "hermipy_b200.core.transform_batch (hb_transform_batch: host buffers, copies inside)",
+           "cpu_affinity": numa_note}
+    os.sched_setaffinity(0, old_affinity)
 
     # ---------------- varf of the same config ----------------
     varf = {}
