@@ -289,7 +289,10 @@ bool page_locked(const void* p) {
 int issue_pipeline(hb_plan* pl, int dim, int batch, const double* f, int forward, double* out, bool capturing) {
     const Axis& L = pl->ax[dim - 1];
     const long long n_grid = pl->grid_rows * L.n;
-    const long long cstride = even_up(pl->n_polys);
+    // Coefficient rows on the device: in d >= 2 dimensions they are only touched through the look-up table (scalar
+    // scatter of the last forward stage, gather of the first inverse stage), so they can keep the host's row length
+    // and cross PCIe without a re-pitch; in 1-D they are a GEMM operand and need an even pitch.
+    const long long cstride = dim >= 2 ? pl->n_polys : even_up(pl->n_polys);
     const long long in_dev = forward ? pl->grid_size : cstride, out_dev = forward ? cstride : pl->grid_size;
     const bool pitched = L.np != L.n, cpitched = cstride != pl->n_polys;
     // Chunk sizes.  A chunk's transform takes about as long for 2 functions as for 17 at the C2 size (one wave of
@@ -386,7 +389,7 @@ int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const d
     HB_TRY(g_pipe.init());
     const Axis& L = pl->ax[dim - 1];
     const long long n_grid = pl->grid_rows * L.n;
-    const long long cstride = even_up(pl->n_polys);
+    const long long cstride = dim >= 2 ? pl->n_polys : even_up(pl->n_polys);   // see issue_pipeline
     const size_t expect = forward ? (size_t)pl->n_polys : (size_t)n_grid;
     if (out_len_each != expect) {
         set_error("transform: out_len %zu != %s %zu", out_len_each, forward ? "n_polys" : "grid size", expect);
