@@ -1,0 +1,94 @@
+"""CPU tests (-m "not gpu") of the host-side logic of hermipy_b200.resident (reference: hermipy/varf.py:127-237):
+operator algebra, the bordered system of `solve(remove_vec=...)`, the ARPACK / GMRES drivers.  The matrix-vector
+product is a CPU stand-in injected through `ResidentMatrix(matvec=...)`; the device product is covered by
+tests/test_gpu_resident.py."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_backend
+
+from hermipy_b200 import Position, Series
+from hermipy_b200.resident import ResidentMatrix, ResidentVarf
+
+
+def cpu_matvec(A, x, out=None):
+    res = torch.mv(A, x)
+    if out is None:
+        return res
+    out.copy_(res)
+    return out
+
+
+@pytest.fixture()
+def operator():
+    rng = np.random.default_rng(4)
+    n = 28                                         # triangle set, dim 2, degree 6
+    A = rng.standard_normal((n, n)) * 0.3 - 3.0 * np.eye(n)
+    position = Position(dim=2)
+    varf = ResidentVarf(ResidentMatrix(torch.from_numpy(A.copy()), matvec=cpu_matvec), position)
+    return A, position, varf
+
+
+def test_degree_indices_and_call(operator):
+    A, position, varf = operator
+    assert varf.degree == 6 and len(varf.multi_indices()) == 28
+    u = Series(np.arange(28.0), position)
+    np.testing.assert_allclose(varf(u).coeffs, A @ np.arange(28.0), rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        varf(Series(np.ones(7), Position(dim=1)))
+
+
+def test_algebra(operator):
+    A, position, varf = operator
+    np.testing.assert_allclose((varf * 2 - varf).matrix.to_host(), A, rtol=0, atol=1e-15)
+    np.testing.assert_allclose((-varf + varf * 3.0).matrix.to_host(), 2 * A, rtol=0, atol=1e-14)
+    np.testing.assert_allclose((0 + varf).matrix.to_host(), A)
+    np.testing.assert_allclose((varf + 1.5).matrix.to_host(), A + 1.5)
+    with pytest.raises(ValueError):
+        varf * varf
+    with pytest.raises(ValueError):
+        varf + ResidentVarf(varf.matrix, position, index_set="cube" if False else "triangle", factor=2)
+    host = varf.to_varf()
+    np.testing.assert_allclose(host.matrix, A)
+
+
+def test_solve_gmres_and_direct(operator):
+    A, position, varf = operator
+    b = Series(np.linspace(-1, 1, 28), position)
+    want = np.linalg.solve(A, b.coeffs)
+    got = varf.solve(b, rtol=1e-13, restart=28, quiet=True).coeffs
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-10)
+    got_lu = varf.solve(b, use_gmres=False).coeffs
+    np.testing.assert_allclose(got_lu, want, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        varf.solve(b, preconditioner="ilu")
+
+
+def test_bordered_solve_matches_explicit_system(operator):
+    A, position, varf = operator
+    rng = np.random.default_rng(5)
+    v = Series(rng.standard_normal(28), position)
+    b = Series(rng.standard_normal(28), position)
+    vn = v.coeffs / np.sqrt(v.coeffs @ v.coeffs)
+    big = np.block([[A, vn[:, None]], [vn[None, :], np.zeros((1, 1))]])          # varf.py:200-206
+    want = np.linalg.solve(big, np.append(b.coeffs, 0))[:-1]
+    with oracle_backend.oracle_core():            # Series * Series (the normalisation of remove_vec) is core.inner
+        got_lu = varf.solve(b, use_gmres=False, remove_vec=v, quiet=True).coeffs
+        got_gm = varf.solve(b, remove_vec=v, rtol=1e-13, restart=29, quiet=True).coeffs
+    np.testing.assert_allclose(got_lu, want, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(got_gm, want, rtol=0, atol=1e-9)
+
+
+def test_eigs_regular_and_shift_invert(operator):
+    A, position, varf = operator
+    true = np.linalg.eigvals(A)
+    values, vectors = varf.eigs(k=3, which="LM", v0=np.ones(28))
+    for lam, vec in zip(values, vectors):
+        assert np.min(np.abs(true - lam)) < 1e-8
+        resid = A @ vec.coeffs - lam * vec.coeffs
+        assert np.linalg.norm(resid) < 1e-8 * np.linalg.norm(vec.coeffs)
+    sigma = -3.0
+    values, _ = varf.eigs(k=2, sigma=sigma, v0=np.ones(28))
+    nearest = true[np.argsort(np.abs(true - sigma))[:2]]
+    assert all(np.min(np.abs(nearest - lam)) < 1e-8 for lam in values)
