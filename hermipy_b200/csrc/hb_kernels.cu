@@ -357,6 +357,28 @@ int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int
     return launch_status();
 }
 
+// De-interleave by parity in one pass (1-D inverse transform on a symmetric node set): row r of `src` holds the
+// coefficients in natural order; even[r][j] = src[r][2j] (j < Pe), odd[r][j] = src[r][2j+1] (j < Po), pad columns
+// up to the even pitches lde / ldo zeroed (they are GEMM operands).  Each source sector is read once.
+__global__ void deinterleave_rows_kernel(const double* __restrict__ src, long long src_ld, int Pe, int Po,
+                                         double* __restrict__ even, long long lde, double* __restrict__ odd,
+                                         long long ldo, long long rows, long long width) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * width) return;
+    const long long r = idx / width;
+    const int j = (int)(idx - r * width);
+    const double* row = src + r * src_ld;
+    if (j < lde) even[r * lde + j] = (j < Pe) ? row[2 * j] : 0.0;
+    if (j < ldo) odd[r * ldo + j] = (j < Po) ? row[2 * j + 1] : 0.0;
+}
+int launch_deinterleave_rows(const double* src, long long src_ld, int Pe, int Po, double* even, long long lde, double* odd,
+                             long long ldo, long long rows, cudaStream_t s) {
+    const long long width = lde > ldo ? lde : ldo;
+    if (rows <= 0 || width <= 0) return HB_OK;
+    deinterleave_rows_kernel<<<cdiv(rows * width, 256), 256, 0, s>>>(src, src_ld, Pe, Po, even, lde, odd, ldo, rows, width);
+    return launch_status();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pitch repack / gather helpers.
 __global__ void repack_rows_kernel(const double* __restrict__ src, long long src_ld, double* __restrict__ dst,

@@ -28,6 +28,8 @@ int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int
                         long long dst_ld, long long rows, int cols, int batch, long long src_bstride,
                         long long dst_bstride, cudaStream_t s);
 int launch_parity_split(const double* f, int n, int nh, int seg, long long pitch, double* out, cudaStream_t s);
+int launch_deinterleave_rows(const double* src, long long src_ld, int Pe, int Po, double* even, long long lde, double* odd,
+                             long long ldo, long long rows, cudaStream_t s);
 int launch_repack_rows(const double* src, long long src_ld, double* dst, long long dst_ld, long long rows, int cols,
                        cudaStream_t s);
 int launch_gather_lut(const double* src, long long src_stride, const int* lut, double* dst, long long dst_stride,

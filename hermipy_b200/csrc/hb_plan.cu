@@ -363,9 +363,8 @@ static int backward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_coef,
     if (sorted) {   // the rows already hold [even block | odd block at Pep]
         ce = d_coef; co = d_coef + d.Pep; lde = ldo = c_pitch;
     } else {        // natural order (1-D transform): de-interleave
-        HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 0, 2, pl->parA.d(), d.Pep, rows, d.Pe, 1, 0, 0, st));
-        HB_TRY(launch_strided_copy(d_coef, c_pitch, 0, 1, 1, 2, pl->parA.d() + (size_t)rows * d.Pep, d.Pop, rows, d.Po,
-                                   1, 0, 0, st));
+        HB_TRY(launch_deinterleave_rows(d_coef, c_pitch, d.Pe, d.Po, pl->parA.d(), d.Pep,
+                                        pl->parA.d() + (size_t)rows * d.Pep, d.Pop, rows, st));
     }
     for (int par = 0; par < 2; par++) {
         GemmArgs g;
