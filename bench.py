@@ -397,13 +397,15 @@ def run_ours(args):
     for _ in range(3):                      # call 1 eager (tunes), call 2 captures the pipeline graph, call 3 replays
         e2e_step()
     sampler.pause(True)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_reps = max(10, min(3 * K, 30))      # ~1.1 ms each: enough of them that one host hiccup does not decide
-    for _ in range(e2e_reps):
-        e2e_step()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    sampler.pause(False)
+    try:
+        barrier()
+        t0 = time.perf_counter()
+        e2e_reps = max(10, min(3 * K, 30))  # ~1.1 ms each: enough of them that one host hiccup does not decide
+        for _ in range(e2e_reps):
+            e2e_step()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+    finally:
+        sampler.pause(False)
     n_polys = plan.n_polys
     e2e = {"value": world * pts_per_step * e2e_reps / e2e_s * 1e-9, "unit": "Gpts/s",
            "h2d_bytes_per_step": world * 8 * B * (n * n + n_polys), "d2h_bytes_per_step": world * 8 * B * (n * n + n_polys),
