@@ -63,9 +63,14 @@ class Plan:
         self.coef_stride = (self.n_polys + 1) & ~1
 
     def __del__(self):
-        if getattr(self, "_h", None) and _lib._lib is not None:
-            lib().hb_plan_destroy(self._h)
-            self._h = None
+        # at interpreter shutdown the module globals may already be gone: then the process-exit cleanup of the
+        # library frees the plan
+        try:
+            if getattr(self, "_h", None) and _lib is not None and _lib._lib is not None:
+                _lib._lib.hb_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     # --- layout helpers -------------------------------------------------------------------------
     def pack_grid(self, f):
