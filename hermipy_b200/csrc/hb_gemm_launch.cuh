@@ -56,7 +56,7 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
     p.a_bmul = a_batched ? 1 : 0;
     p.b_bmul = b_batched ? 1 : 0;
     const long long n_tiles = (long long)p.tiles_m * p.tiles_n * a.batch;
-    if (n_tiles > 0x7fffffffLL) return HB_ERR_INVALID;
+    if (n_tiles > 0x7fffffffLL - 65536) return HB_ERR_INVALID;   // the kernel's tile counter steps by the grid size in int
     p.n_tiles = (int)n_tiles;
     static const int sm_count = [] {
         int dev = 0, n = 0;
