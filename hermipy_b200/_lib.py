@@ -20,10 +20,15 @@ c_up = C.POINTER(C.c_uint32)
 c_llp = C.POINTER(C.c_longlong)
 
 
+_CODE_NAMES = ["HB_OK", "HB_ERR_INVALID", "HB_ERR_INDEX_SET", "HB_ERR_FOURIER_DEGREE", "HB_ERR_DEGREE", "HB_ERR_CUDA",
+               "HB_ERR_ALIGN", "HB_ERR_NOMEM"]
+
+
 class HermiteB200Error(RuntimeError):
     def __init__(self, code, text):
         self.code = code
-        super().__init__("libhermite_b200 status %d: %s" % (code, text))
+        name = _CODE_NAMES[code] if 0 <= code < len(_CODE_NAMES) else "?"
+        super().__init__("libhermite_b200 status %d (%s): %s" % (code, name, text))
 
 
 class DegreeError(HermiteB200Error, ValueError):

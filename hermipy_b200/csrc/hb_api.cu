@@ -382,10 +382,12 @@ int issue_pipeline(hb_plan* pl, int dim, int batch, const double* f, int forward
 int hb_transform_batch(int dim, const int* n_pts, int degree, int batch, const double* f, const double* nodes,
                        const double* weights, const int* do_fourier, int forward, const char* index_set,
                        double* out, size_t out_len_each) {
+    // the call mutex is taken BEFORE the plan look-up: the LRU eviction in cached_plan() deletes plans, and a plan
+    // may only be deleted while no other host-pointer call is using it
+    std::lock_guard<std::mutex> lock(g_call_mutex);
     hb_plan* pl = nullptr;
     HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
     if (batch < 1) return HB_OK;
-    std::lock_guard<std::mutex> lock(g_call_mutex);
     HB_TRY(g_pipe.init());
     const Axis& L = pl->ax[dim - 1];
     const long long n_grid = pl->grid_rows * L.n;

@@ -107,6 +107,22 @@ static int tuned_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
     std::sort(order, order + kNumCfgs, [&](int x, int y) { return t[x] < t[y]; });
     static const bool enabled = [] { const char* e = getenv("HB_GEMM_AUTOTUNE"); return !(e && e[0] == '0'); }();
     if (!enabled || t[order[0]] > 150.0 || a.block_rows > 0 || a.epi == EPI_VARF2D) return order[0];
+    // Timing replays the caller's GEMM ~19 times on the caller's operands: only safe when C aliases neither input
+    // (an in-place product would be fed its own output on the second launch).  Overlapping calls take the model's pick.
+    {
+        auto extent = [](const double* p, long long rows, long long ld, long long stride, int batch) {
+            const long long n = (batch > 1 ? (long long)(batch - 1) * (stride > 0 ? stride : 0) : 0) + rows * ld;
+            return std::make_pair(reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p + (n > 0 ? n : 0)));
+        };
+        const auto ra = extent(a.A, a.a_mmajor ? a.K : a.M, a.lda, a.strideA, a.batch);
+        const auto rb = extent(a.B, a.K, a.ldb, a.strideB, a.batch);
+        auto rc = extent(a.C, a.M, a.ldc > 0 ? a.ldc : a.N, a.strideC, a.batch);
+        if (a.epi == EPI_LUT) rc.second = rc.first + (uintptr_t)8 * ((a.batch - 1) * (a.strideC > 0 ? a.strideC : 0) + (long long)a.M * a.N);
+        auto overlap = [](std::pair<uintptr_t, uintptr_t> x, std::pair<uintptr_t, uintptr_t> y) {
+            return x.first < y.second && y.first < x.second;
+        };
+        if (overlap(rc, ra) || overlap(rc, rb)) return order[0];
+    }
     const TuneKey key{a.M, a.N, a.K, a.batch,
                       (a.a_mmajor ? 1 : 0) | (a.epi << 1) | ((a.strideA == 0) << 4) | ((a.strideB == 0) << 5) |
                           ((a.col_stride > 1) << 6)};
@@ -154,9 +170,13 @@ long long* gemm_get_trace() { return g_trace; }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return HB_OK;
+    if (a.K <= 0) { set_error("gemm: K = %d (need K >= 1)", a.K); return HB_ERR_INVALID; }
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
-        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1))) || a.K <= 0)
+        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1)))) {
+        set_error("gemm: operands need 16-byte aligned bases and even leading dimensions / batch strides (lda %lld, "
+                  "ldb %lld, strideA %lld, strideB %lld)", a.lda, a.ldb, a.strideA, a.strideB);
         return HB_ERR_ALIGN;
+    }
     GemmParams p;
     p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
     p.C = a.C; p.ldc = a.ldc; p.strideC = a.strideC;
@@ -172,7 +192,10 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.col_stride = a.col_stride > 0 ? a.col_stride : 1; p.col_offset = a.col_offset;
     p.row_stride = a.row_stride > 0 ? a.row_stride : 1; p.row_offset = a.row_offset;
     for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.blocks[i] = a.blocks[i];
-    if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) return HB_ERR_INVALID;
+    if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) {
+        set_error("gemm: at most %d destination row blocks", GEMM_MAX_BLOCKS);
+        return HB_ERR_INVALID;
+    }
     int cfg = a.cfg;
     if (cfg < 0) {
         static const char* env = getenv("HB_GEMM_CFG_FIXED");      // developer override, read once

@@ -2,6 +2,7 @@
 // kernel (hb_gemm_inst_*.cu: one per (epilogue, A layout) so that they compile in parallel).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "hb_gemm.cuh"
@@ -9,6 +10,21 @@
 #include "hb_plan.h"
 
 namespace hb {
+
+// current device (index clamped to 63 for the per-device bit masks) and its SM count, cached per device
+struct DeviceInfo { int index, sms; };
+inline DeviceInfo current_device_info() {
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    if (dev > 63) dev = 63;
+    int n = sms[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        sms[dev].store(n, std::memory_order_relaxed);
+    }
+    return DeviceInfo{dev, n};
+}
 
 // rank-3 FP64 tensor map: dims {d0 (contiguous), d1 (pitch ld elements), d2 (batch, stride elements)}
 int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld, uint64_t stride,
@@ -58,19 +74,16 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
     const long long n_tiles = (long long)p.tiles_m * p.tiles_n * a.batch;
     if (n_tiles > 0x7fffffffLL - 65536) return HB_ERR_INVALID;   // the kernel's tile counter steps by the grid size in int
     p.n_tiles = (int)n_tiles;
-    static const int sm_count = [] {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
-        return n;
-    }();
-    const long long n_cta = std::min<long long>(n_tiles, (long long)sm_count * MINB);   // persistent: one wave
+    const DeviceInfo dev = current_device_info();
+    const long long n_cta = std::min<long long>(n_tiles, (long long)dev.sms * MINB);   // persistent: one wave
     auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM, MINB, EPI>;
     constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the > 48 KB dynamic shared memory opt-in is a per-device property of the function: one bit per device
+    static std::atomic<unsigned long long> attr_set{0};
+    if (!(attr_set.load(std::memory_order_relaxed) >> dev.index & 1)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return HB_ERR_CUDA;
-        attr_set = true;
+        attr_set.fetch_or(1ull << dev.index, std::memory_order_relaxed);
     }
     // Programmatic dependent launch (opt-in, HB_GEMM_PDL=1): the CTA launch and barrier setup of this kernel overlap
     // the tail of its predecessor in the stream (every warp blocks in griddepcontrol.wait before touching operands;

@@ -6,11 +6,15 @@
 #include "hb_kernels.h"
 #include "hb_plan.h"
 
+#include <algorithm>
 #include <cmath>
 
 namespace hb {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+// gridDim.y (batch entry / matrix row of several kernels here) is limited to 65535: larger counts -- a 3-D transform
+// of many functions, any 4-D grid, matrices of more than 65535 rows -- are launched in slices
+static const int kMaxGridY = 65535;
 
 // ------------------------------------------------------------------------------------------------
 // Basis tables.  Reference: hermite_eval (cpp/src/hermite/hermite.cpp:29-41, REC_A/REC_B
@@ -321,17 +325,25 @@ __global__ void axis_parity_merge_kernel(const double* __restrict__ ge, const do
 int launch_axis_parity_split(const double* in, long long in_stride, int n, int nh, long long cols, int batch,
                              double* be, double* bo, cudaStream_t s) {
     const long long per_batch = (long long)nh * cols;
-    dim3 grid(cdiv(per_batch, 256), batch);
-    axis_parity_split_kernel<<<grid, 256, 0, s>>>(in, in_stride, n, nh, cols, be, bo, per_batch);
-    return launch_status();
+    for (int b0 = 0; b0 < batch; b0 += kMaxGridY) {
+        dim3 grid(cdiv(per_batch, 256), std::min(batch - b0, kMaxGridY));
+        axis_parity_split_kernel<<<grid, 256, 0, s>>>(in + b0 * in_stride, in_stride, n, nh, cols, be + b0 * per_batch,
+                                                      bo + b0 * per_batch, per_batch);
+        HB_TRY(launch_status());
+    }
+    return HB_OK;
 }
 
 int launch_axis_parity_merge(const double* ge, const double* go, int n, int nh, long long cols, int batch, double* out,
                              long long out_stride, cudaStream_t s) {
     const long long per_batch = (long long)nh * cols;
-    dim3 grid(cdiv(per_batch, 256), batch);
-    axis_parity_merge_kernel<<<grid, 256, 0, s>>>(ge, go, n, nh, cols, out, out_stride, per_batch);
-    return launch_status();
+    for (int b0 = 0; b0 < batch; b0 += kMaxGridY) {
+        dim3 grid(cdiv(per_batch, 256), std::min(batch - b0, kMaxGridY));
+        axis_parity_merge_kernel<<<grid, 256, 0, s>>>(ge + b0 * per_batch, go + b0 * per_batch, n, nh, cols,
+                                                      out + b0 * out_stride, out_stride, per_batch);
+        HB_TRY(launch_status());
+    }
+    return HB_OK;
 }
 
 int launch_rows_parity_split(const double* f, long long f_stride, int n, int nh, double* fe, double* fo,
@@ -351,10 +363,13 @@ int launch_rows_parity_merge(const double* ge, const double* go, long long h_str
 int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int c0, int cs, double* dst,
                         long long dst_ld, long long rows, int cols, int batch, long long src_bstride,
                         long long dst_bstride, cudaStream_t s) {
-    dim3 grid(cdiv(rows * dst_ld, 256), batch);
-    strided_copy_kernel<<<grid, 256, 0, s>>>(src, src_ld, r0, rs, c0, cs, dst, dst_ld, rows, cols, src_bstride,
-                                             dst_bstride);
-    return launch_status();
+    for (int b0 = 0; b0 < batch; b0 += kMaxGridY) {
+        dim3 grid(cdiv(rows * dst_ld, 256), std::min(batch - b0, kMaxGridY));
+        strided_copy_kernel<<<grid, 256, 0, s>>>(src + b0 * src_bstride, src_ld, r0, rs, c0, cs, dst + b0 * dst_bstride,
+                                                 dst_ld, rows, cols, src_bstride, dst_bstride);
+        HB_TRY(launch_status());
+    }
+    return HB_OK;
 }
 
 // De-interleave by parity in one pass (1-D inverse transform on a symmetric node set): row r of `src` holds the
@@ -426,8 +441,8 @@ __global__ void tensorize_vec_kernel(TensorizeArgs a, double* __restrict__ out, 
     out[i] = v;
 }
 
-__global__ void tensorize_mat_kernel(TensorizeArgs a, double* __restrict__ out, int n_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+__global__ void tensorize_mat_kernel(TensorizeArgs a, double* __restrict__ out, int n_out, int r0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = r0 + blockIdx.y;
     if (c >= n_out) return;
     // the reference folds factors left to right: ((A0*A1)*A2)...
     double v = a.in[0][(long long)a.map[0][r] * a.size[0] + a.map[0][c]];
@@ -438,8 +453,10 @@ __global__ void tensorize_mat_kernel(TensorizeArgs a, double* __restrict__ out, 
 
 int launch_tensorize(const TensorizeArgs& a, bool matrices, double* out, int n_out, cudaStream_t s) {
     if (matrices) {
-        dim3 grid(cdiv(n_out, 256), n_out);
-        tensorize_mat_kernel<<<grid, 256, 0, s>>>(a, out, n_out);
+        for (int r0 = 0; r0 < n_out; r0 += kMaxGridY) {   // gridDim.y <= 65535
+            dim3 grid(cdiv(n_out, 256), std::min(n_out - r0, kMaxGridY));
+            tensorize_mat_kernel<<<grid, 256, 0, s>>>(a, out, n_out, r0);
+        }
     } else {
         tensorize_vec_kernel<<<cdiv(n_out, 256), 256, 0, s>>>(a, out, n_out);
     }
@@ -453,16 +470,18 @@ __global__ void project_vec_kernel(const double* __restrict__ in, const int* __r
     if (i < n_out) out[i] = sel[i] >= 0 ? in[sel[i]] : 0.0;
 }
 __global__ void project_mat_kernel(const double* __restrict__ in, int n_in, const int* __restrict__ sel, double* out,
-                                   int n_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+                                   int n_out, int r0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = r0 + blockIdx.y;
     if (c >= n_out) return;
     const int sr = sel[r], sc = sel[c];
     out[(long long)r * n_out + c] = (sr >= 0 && sc >= 0) ? in[(long long)sr * n_in + sc] : 0.0;
 }
 int launch_project(const double* in, int n_in, const int* sel, bool matrix, double* out, int n_out, cudaStream_t s) {
     if (matrix) {
-        dim3 grid(cdiv(n_out, 256), n_out);
-        project_mat_kernel<<<grid, 256, 0, s>>>(in, n_in, sel, out, n_out);
+        for (int r0 = 0; r0 < n_out; r0 += kMaxGridY) {   // gridDim.y <= 65535
+            dim3 grid(cdiv(n_out, 256), std::min(n_out - r0, kMaxGridY));
+            project_mat_kernel<<<grid, 256, 0, s>>>(in, n_in, sel, out, n_out, r0);
+        }
     } else {
         project_vec_kernel<<<cdiv(n_out, 256), 256, 0, s>>>(in, sel, out, n_out);
     }

@@ -17,7 +17,10 @@
 namespace hb {
 
 // ---------------------------------------------------------------------------------------------
+// Error text of the calling thread.  hb_last_error() hands the message out ONCE: a later failure that sets no text
+// of its own then reports "(no detail)" instead of repeating the message of an older, unrelated error.
 static thread_local char g_err[512] = "";
+static thread_local char g_err_out[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -26,7 +29,12 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-const char* last_error() { return g_err; }
+const char* last_error() {
+    if (g_err[0]) memcpy(g_err_out, g_err, sizeof(g_err));
+    else snprintf(g_err_out, sizeof(g_err_out), "(no detail)");
+    g_err[0] = 0;
+    return g_err_out;
+}
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error '%s' in %s", cudaGetErrorString(e), what);
     return HB_ERR_CUDA;
@@ -974,8 +982,15 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     VarfBandArgs b;
     b.width_total = 1;
     for (int k = 0; k < d; k++) {
+        // half-width of the band on axis k.  Hermite: T[a][m][n] = 0 unless |m - n| <= a.  Fourier (varf.cpp:99-162):
+        // index a has wave number ceil(a/2) and e_a e_m e_n integrates to 0 unless the wave numbers satisfy
+        // |k_m - k_n| <= k_a; with COS(k) = 2k, SIN(k) = 2k - 1 that is |m - n| <= 2 ceil(a/2) + 1 (a sine against
+        // the cosine two wave numbers up sits a + 2 away for odd a).
         b.amax[k] = 0;
-        for (int t = 0; t < n_kept; t++) b.amax[k] = std::max(b.amax[k], kept_alpha[(size_t)t * d + k]);
+        for (int t = 0; t < n_kept; t++) {
+            const int al = kept_alpha[(size_t)t * d + k];
+            b.amax[k] = std::max(b.amax[k], pl->ax[k].fourier ? 2 * ((al + 1) / 2) + 1 : al);
+        }
         b.extent[k] = pl->ax[k].P;
         b.width_total *= std::min(2 * b.amax[k] + 1, 2 * pl->ax[k].P - 1);
     }

@@ -390,16 +390,14 @@ int varf_stage2_launch(const GemmArgs& a, const int2* d_tiles, int n_tiles, cuda
     p.col_stride = 1;
     p.trace = gemm_get_trace();
     { const char* dbg = getenv("HB_VARF_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }   // developer switch: bit0 / bit1 drop the direct / mirrored stores
-    static bool attr_set = false;
-    if (!attr_set) {
+    const DeviceInfo dev = current_device_info();
+    static std::atomic<unsigned long long> attr_set{0};   // one bit per device (the opt-in is per device)
+    if (!(attr_set.load(std::memory_order_relaxed) >> dev.index & 1)) {
         if (cudaFuncSetAttribute(varf2d_pingpong_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PP_SMEM) != cudaSuccess)
             return HB_ERR_CUDA;
-        attr_set = true;
+        attr_set.fetch_or(1ull << dev.index, std::memory_order_relaxed);
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = std::min(sms, (n_tiles + 1) / 2);
+    const int grid = std::min(dev.sms, (n_tiles + 1) / 2);
     int* counter = reinterpret_cast<int*>(const_cast<int2*>(d_tiles) + n_tiles);   // one spare entry after the list
     HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), stream));
     varf2d_pingpong_kernel<<<grid, 384, PP_SMEM, stream>>>(tmA, tmB, p, d_tiles, n_tiles, counter);

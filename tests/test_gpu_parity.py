@@ -168,6 +168,47 @@ def test_varf_3d_polynomial(core, ref):
     assert rel_err(A, R) < TOL
 
 
+def _fourier_rule(n):
+    return -np.pi + 2 * np.pi * np.arange(n) / n, np.full(n, 2 * np.pi / n)
+
+
+@pytest.mark.parametrize("name,degree", [("sin", 40), ("sin+cos2", 48)])
+def test_varf_fourier_1d_band_path(ref, name, degree):
+    """Banded assembly on a Fourier axis (varf.cpp:99-162): the triple product of index a couples basis functions
+    up to 2*ceil(a/2)+1 apart -- e.g. sin(kx) with cos((k+1)x) through e_1 = sin(x), |m - n| = 3 -- not a apart as
+    for Hermite axes.  Degree high enough that the library takes the zero-fill + band path (path 2)."""
+    from hermipy_b200.plan import Plan
+    x, w = _fourier_rule(128)
+    f = np.sin(x) + (np.cos(2 * x) if name == "sin+cos2" else 0)
+    plan = Plan(degree, [x], [w], do_fourier=[1])
+    A = plan.varf(plan.pack_grid(f[None])[0], "reference").cpu().numpy()
+    assert plan.varf_info()[1] == 2
+    R = ref.varf(degree, f, [x], [w], do_fourier=[1])
+    assert np.array_equal(A != 0, R != 0)
+    assert rel_err(A, R) < TOL
+    assert max(abs(i - j) for i, j in np.argwhere(R != 0)) >= 3      # entries a Hermite-width band would miss
+
+
+@pytest.mark.parametrize("index_set", ["cube", "triangle"])
+def test_varf_fourier_x_hermite_2d_band_path(core, ref, index_set):
+    """2-D Fourier x Hermite (the reference's langevin examples) at a degree where the band path is taken."""
+    from hermipy_b200.plan import Plan
+    x, w = _fourier_rule(64)
+    y, v = gauss_hermite(41)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    degree = 14
+    for k, f in enumerate((np.sin(X) + Y, np.sin(X) * Y + np.cos(2 * X) + Y ** 2)):
+        plan = Plan(degree, [x, y], [w, v], do_fourier=[1, 0], index_set=index_set)
+        A = plan.varf(plan.pack_grid(f[None])[0], "reference").cpu().numpy()
+        assert plan.varf_info()[1] == 2 or (k == 1 and index_set == "triangle")   # (11 x 5 band > 120 / 4 there)
+        R = ref.varf(degree, f.ravel(), [x, y], [w, v], do_fourier=[1, 0], index_set=index_set)
+        assert np.array_equal(A != 0, R != 0)
+        assert rel_err(A, R) < TOL
+        assert rel_err(core.varf(degree, f, [x, y], [w, v], do_fourier=[1, 0], index_set=index_set), R) < TOL
+        D = core.varfd(2, degree, 0, A, do_fourier=1, index_set=index_set)
+        assert np.array_equal(D, ref.varfd(2, degree, 0, A, do_fourier=1, index_set=index_set))
+
+
 @pytest.mark.parametrize("index_set", SETS)
 def test_varfd(core, ref, index_set):
     rng = np.random.default_rng(3)
