@@ -52,6 +52,27 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
     return HB_OK;
 }
 
+// rank-4 FP64 map: dims {d0 (contiguous), d1 (pitch ld), n_lo (stride_lo), n_hi (stride_hi)}, strides in elements
+int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t n_lo, uint64_t n_hi, uint64_t ld,
+              uint64_t stride_lo, uint64_t stride_hi, uint32_t b0, uint32_t b1) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return HB_ERR_CUDA;
+    cuuint64_t dims[4] = {d0, d1, n_lo, n_hi};
+    cuuint64_t strides[3] = {ld * 8, stride_lo * 8, stride_hi * 8};
+    cuuint32_t box[4] = {b0, b1, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(base), dims, strides, box,
+                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu, ld %llu, strides %llu %llu", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)n_lo, (unsigned long long)n_hi,
+                  (unsigned long long)ld, (unsigned long long)stride_lo, (unsigned long long)stride_hi);
+        return HB_ERR_CUDA;
+    }
+    return HB_OK;
+}
+
 // Tile configurations: {BM, BN, resident CTAs per SM}.  The launcher picks the one with the smallest
 // modelled time: small or oddly shaped problems (P = 201, n = 401, batch 17 ...) otherwise lose most of
 // their time to tile quantisation and partial waves over the 148 SMs.
@@ -73,7 +94,7 @@ static double model_us(const GemmArgs& a, int i) {
     const double sms = 148.0, clk_per_us = 1920.0;
     const double ksteps = (a.K + 15) / 16;
     const TileCfg& c = kCfgs[i];
-    const long long tiles = (long long)((a.M + c.bm - 1) / c.bm) * ((a.N + c.bn - 1) / c.bn) * a.batch;
+    const long long tiles = (long long)((a.M + c.bm - 1) / c.bm) * ((a.N + c.bn - 1) / c.bn) * a.batch * a.batch_lo;
     // DMMA-bound time of one tile in SM clocks (one DMMA.8x8x4 per 4 clocks per SM)
     const double tile_t = (double)c.bm * c.bn * ksteps * 16.0 / 256.0 * 4.0;
     const long long slots = (long long)sms * c.ctas;
@@ -110,14 +131,18 @@ static int tuned_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
     // Timing replays the caller's GEMM ~19 times on the caller's operands: only safe when C aliases neither input
     // (an in-place product would be fed its own output on the second launch).  Overlapping calls take the model's pick.
     {
-        auto extent = [](const double* p, long long rows, long long ld, long long stride, int batch) {
-            const long long n = (batch > 1 ? (long long)(batch - 1) * (stride > 0 ? stride : 0) : 0) + rows * ld;
+        const int nlo = a.batch_lo;
+        auto extent = [nlo](const double* p, long long rows, long long ld, long long stride, int batch, long long stride_lo) {
+            const long long n = (batch > 1 ? (long long)(batch - 1) * (stride > 0 ? stride : 0) : 0) +
+                                (nlo > 1 ? (long long)(nlo - 1) * (stride_lo > 0 ? stride_lo : 0) : 0) + rows * ld;
             return std::make_pair(reinterpret_cast<uintptr_t>(p), reinterpret_cast<uintptr_t>(p + (n > 0 ? n : 0)));
         };
-        const auto ra = extent(a.A, a.a_mmajor ? a.K : a.M, a.lda, a.strideA, a.batch);
-        const auto rb = extent(a.B, a.K, a.ldb, a.strideB, a.batch);
-        auto rc = extent(a.C, a.M, a.ldc > 0 ? a.ldc : a.N, a.strideC, a.batch);
-        if (a.epi == EPI_LUT) rc.second = rc.first + (uintptr_t)8 * ((a.batch - 1) * (a.strideC > 0 ? a.strideC : 0) + (long long)a.M * a.N);
+        const auto ra = extent(a.A, a.a_mmajor ? a.K : a.M, a.lda, a.strideA, a.batch, a.strideA_lo);
+        const auto rb = extent(a.B, a.K, a.ldb, a.strideB, a.batch, a.strideB_lo);
+        auto rc = extent(a.C, a.M, a.ldc > 0 ? a.ldc : a.N, a.strideC, a.batch, a.strideC_lo);
+        if (a.epi == EPI_LUT)
+            rc.second = rc.first + (uintptr_t)8 * ((a.batch - 1) * (a.strideC > 0 ? a.strideC : 0) +
+                                                   (long long)a.M * a.N * a.batch_lo * 2);
         auto overlap = [](std::pair<uintptr_t, uintptr_t> x, std::pair<uintptr_t, uintptr_t> y) {
             return x.first < y.second && y.first < x.second;
         };
@@ -125,7 +150,7 @@ static int tuned_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
     }
     const TuneKey key{a.M, a.N, a.K, a.batch,
                       (a.a_mmajor ? 1 : 0) | (a.epi << 1) | ((a.strideA == 0) << 4) | ((a.strideB == 0) << 5) |
-                          ((a.col_stride > 1) << 6)};
+                          ((a.col_stride > 1) << 6) | (a.batch_lo << 7)};
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     auto it = g_tuned.find(key);
     if (it != g_tuned.end()) return it->second;
@@ -169,10 +194,11 @@ void gemm_set_trace(long long* dev) { g_trace = dev; }
 long long* gemm_get_trace() { return g_trace; }
 
 int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
-    if (a.M <= 0 || a.N <= 0 || a.batch <= 0) return HB_OK;
+    if (a.M <= 0 || a.N <= 0 || a.batch <= 0 || a.batch_lo <= 0) return HB_OK;
     if (a.K <= 0) { set_error("gemm: K = %d (need K >= 1)", a.K); return HB_ERR_INVALID; }
     if ((a.lda & 1) || (a.ldb & 1) || (reinterpret_cast<uintptr_t>(a.A) & 15) ||
-        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1)))) {
+        (reinterpret_cast<uintptr_t>(a.B) & 15) || (a.batch > 1 && ((a.strideA & 1) || (a.strideB & 1))) ||
+        (a.batch_lo > 1 && ((a.strideA_lo & 1) || (a.strideB_lo & 1)))) {
         set_error("gemm: operands need 16-byte aligned bases and even leading dimensions / batch strides (lda %lld, "
                   "ldb %lld, strideA %lld, strideB %lld)", a.lda, a.ldb, a.strideA, a.strideB);
         return HB_ERR_ALIGN;
@@ -191,6 +217,8 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.block_rows = a.block_rows;
     p.col_stride = a.col_stride > 0 ? a.col_stride : 1; p.col_offset = a.col_offset;
     p.row_stride = a.row_stride > 0 ? a.row_stride : 1; p.row_offset = a.row_offset;
+    p.batch_lo = a.batch_lo; p.strideC_lo = a.strideC_lo;
+    p.row_offset_lo = a.row_offset_lo; p.col_offset_lo = a.col_offset_lo;
     for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.blocks[i] = a.blocks[i];
     if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) {
         set_error("gemm: at most %d destination row blocks", GEMM_MAX_BLOCKS);

@@ -62,7 +62,15 @@ struct GemmParams {
     int tiles_m, tiles_n;    // tiles are numbered b*tiles_m*tiles_n + (grouped tile order, see the kernel)
     int n_tiles;             // tiles_m * tiles_n * batch; CTA c of the (at most one-wave) grid takes c, c + grid, ...
     int group_m;             // tile rows per rasterisation group (>= 1)
-    int a_bmul, b_bmul;      // 0: operand shared by all batch entries, 1: batched
+    // Two-level batch index b = b_hi * batch_lo + b_lo (batch_lo = 1: plain batch).  The low level is how a parity-
+    // split transform stage runs its even and odd halves in ONE launch: b_lo selects the per-parity table and the
+    // even / odd block of the data operand and of the result.  Per level and operand a multiplier 0 / 1 says whether
+    // the operand varies with that index (tensor-map coordinates 2 and 3).
+    int batch_lo;
+    int a_lo_mul, a_hi_mul, b_lo_mul, b_hi_mul;
+    long long strideC_lo;    // C offset per b_lo (strideC is per b_hi)
+    int row_offset_lo;       // added to row_offset per b_lo (EPI_LUT rows, destination row of the block scatter)
+    int col_offset_lo;       // added to col_offset per b_lo (interleaved columns)
     // EPI_STORE with row blocks: output row r goes to blocks[r / block_rows] + (r % block_rows)*ldc.
     // The block pointers may be peer-GPU addresses (NVLink P2P): this is how a GEMM's epilogue performs
     // the all-to-all of the sharded transform.
@@ -151,8 +159,10 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     // (group_m = 1 is the plain row-major order).
     const int per_batch = p.tiles_n * p.tiles_m;
     const int per_group = p.group_m * p.tiles_n;
-    auto tile_coords = [&](int tile, int& b, int& m_base, int& n_base) {
-        b = tile / per_batch;
+    auto tile_coords = [&](int tile, int& b_lo, int& b_hi, int& m_base, int& n_base) {
+        const int b = tile / per_batch;
+        b_hi = b / p.batch_lo;
+        b_lo = b - b_hi * p.batch_lo;
         const int t_in = tile - b * per_batch;
         const int first_m = (t_in / per_group) * p.group_m;
         const int g_rows = min(p.group_m, p.tiles_m - first_m);
@@ -190,8 +200,9 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
 
             int it = 0;   // k-tiles issued so far by this CTA, over all of its tiles
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                int b, m_base, n_base;
-                tile_coords(tile, b, m_base, n_base);
+                int b_lo, b_hi, m_base, n_base;
+                tile_coords(tile, b_lo, b_hi, m_base, n_base);
+                const int a2 = b_lo * p.a_lo_mul, a3 = b_hi * p.a_hi_mul, b2 = b_lo * p.b_lo_mul, b3 = b_hi * p.b_hi_mul;
                 for (int kt = 0; kt < KT; kt++, it++) {
                     const int s = it % STAGES;
                     if (it >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), ((it / STAGES) - 1) & 1);
@@ -202,13 +213,13 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
                     if (A_MMAJOR) {
 #pragma unroll
                         for (int g = 0; g < BM / 16; g++)
-                            tma_load_3d(sA + g * 2048, &tmA, full, m_base + 16 * g, k0, b * p.a_bmul);
+                            tma_load_4d(sA + g * 2048, &tmA, full, m_base + 16 * g, k0, a2, a3);
                     } else {
-                        tma_load_3d(sA, &tmA, full, k0, m_base, b * p.a_bmul);
+                        tma_load_4d(sA, &tmA, full, k0, m_base, a2, a3);
                     }
 #pragma unroll
                     for (int g = 0; g < BN / 16; g++)
-                        tma_load_3d(sB + g * 2048, &tmB, full, n_base + 16 * g, k0, b * p.b_bmul);
+                        tma_load_4d(sB + g * 2048, &tmB, full, n_base + 16 * g, k0, b2, b3);
                 }
             }
         }
@@ -248,8 +259,9 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
 
     int it = 0;   // k-tiles consumed so far by this CTA, over all of its tiles
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    int b, m_base, n_base;
-    tile_coords(tile, b, m_base, n_base);
+    int b_lo, b_hi, m_base, n_base;
+    tile_coords(tile, b_lo, b_hi, m_base, n_base);
+    const long long c_batch_off = (long long)b_hi * p.strideC + (long long)b_lo * p.strideC_lo;
     const bool first_tile = tile == (int)blockIdx.x, last_tile = tile + (int)gridDim.x >= p.n_tiles;
     double acc[MI][NJ][2];
 #pragma unroll
@@ -298,13 +310,14 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     if constexpr (EPI == EPI_LUT) {
         // Scatter through the look-up table (last stage of a d-dim forward transform).  The table entries
         // of one accumulator row are fetched first (independent loads in flight together), then stored.
-        double* out = p.C + (long long)b * p.strideC;
+        double* out = p.C + c_batch_off;
+        const int lut_row0 = p.row_offset + b_lo * p.row_offset_lo;
 #pragma unroll
         for (int mi = 0; mi < MI; mi++) {
             const int im = wm * MI + mi;
             const int row = m_base + (A_MMAJOR ? (16 * (im >> 1) + 4 * (im & 1) + cm) : (wm * WM + 8 * mi + rm));
             if (row >= p.M) continue;
-            const int* __restrict__ lrow = p.lut + (long long)(p.row_offset + row * p.row_stride) * p.N;
+            const int* __restrict__ lrow = p.lut + (long long)(lut_row0 + row * p.row_stride) * p.N;
             int2 idx[NJ];
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {
@@ -337,9 +350,15 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         const int im = wm * MI + mi;
         const int row = m_base + (A_MMAJOR ? (16 * (im >> 1) + 4 * (im & 1) + cm) : (wm * WM + 8 * mi + rm));
         if (row >= p.M) continue;
-        double* rowp = p.block_rows ? p.blocks[row / p.block_rows] + (long long)(row % p.block_rows) * p.ldc
-                                    : p.C + (long long)row * p.ldc;
-        rowp += (long long)b * p.strideC;
+        double* rowp;
+        if (p.block_rows) {   // destination row = row_offset + b_lo * row_offset_lo + row, dealt over the row blocks
+            const int drow = p.row_offset + b_lo * p.row_offset_lo + row;
+            rowp = p.blocks[drow / p.block_rows] + (long long)(drow % p.block_rows) * p.ldc;
+        } else {
+            rowp = p.C + (long long)row * p.ldc;
+        }
+        rowp += c_batch_off;
+        const int col_offset = p.col_offset + b_lo * p.col_offset_lo;
         if (p.col_stride != 1) {   // interleaved output (even / odd coefficients of the 1-D parity transform)
 #pragma unroll
             for (int nj = 0; nj < NJ; nj++) {
@@ -347,7 +366,7 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
                 const int col = n_base + 16 * (jn >> 1) + 4 * (jn & 1) + 8 * (t & 1) + 2 * (t >> 1);
                 if (col >= p.N) continue;
                 if (RAGGED && nj == NJ - 1 && !nj_full) continue;   // slot not owned by this warp
-                double* dst = rowp + p.col_offset + (long long)col * p.col_stride;
+                double* dst = rowp + col_offset + (long long)col * p.col_stride;
                 dst[0] = acc[mi][nj][0] * p.alpha;
                 if (col + 1 < p.N) dst[p.col_stride] = acc[mi][nj][1] * p.alpha;
             }

@@ -29,6 +29,9 @@ inline DeviceInfo current_device_info() {
 // rank-3 FP64 tensor map: dims {d0 (contiguous), d1 (pitch ld elements), d2 (batch, stride elements)}
 int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld, uint64_t stride,
              uint32_t b0, uint32_t b1);
+// rank-4: dims {d0, d1, n_lo, n_hi} with strides {ld, stride_lo, stride_hi} (the two-level batch of the GEMM)
+int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint64_t n_lo, uint64_t n_hi, uint64_t ld,
+              uint64_t stride_lo, uint64_t stride_hi, uint32_t b0, uint32_t b1);
 
 // Tile configurations {BM, BN, warps along M, warps along N, pipeline stages, resident CTAs per SM}.  The number
 // of consumer warps is a multiple of 4 everywhere: FP64 DMMA issues at one instruction per 16 clocks per SM
@@ -52,26 +55,28 @@ int make_map(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint6
 template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB, int EPI>
 static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
-    // A batch stride of 0 means "shared operand": the map gets a batch extent of 1 and the kernel
-    // multiplies the batch coordinate by a_bmul/b_bmul = 0.
-    const bool a_batched = a.batch > 1 && a.strideA != 0, b_batched = a.batch > 1 && a.strideB != 0;
-    const uint64_t strideA = a_batched ? (uint64_t)a.strideA : (uint64_t)a.lda * (AM ? a.K : a.M);
-    const uint64_t strideB = b_batched ? (uint64_t)a.strideB : (uint64_t)a.ldb * a.K;
+    // An operand that does not vary with a batch level (stride 0, or a level with one entry) gets an extent of 1 at
+    // that level of its map and the kernel multiplies the coordinate by 0.
+    const bool a_hi = a.batch > 1 && a.strideA != 0, b_hi = a.batch > 1 && a.strideB != 0;
+    const bool a_lo = a.batch_lo > 1 && a.strideA_lo != 0, b_lo = a.batch_lo > 1 && a.strideB_lo != 0;
+    const uint64_t dummyA = (uint64_t)a.lda * (AM ? a.K : a.M), dummyB = (uint64_t)a.ldb * a.K;
     int rc;
     if (AM)
-        rc = make_map(&tmA, a.A, a.M, a.K, a_batched ? a.batch : 1, a.lda, strideA, 16, GEMM_BK);
+        rc = make_map4(&tmA, a.A, a.M, a.K, a_lo ? a.batch_lo : 1, a_hi ? a.batch : 1, a.lda,
+                       a_lo ? (uint64_t)a.strideA_lo : dummyA, a_hi ? (uint64_t)a.strideA : dummyA, 16, GEMM_BK);
     else
-        rc = make_map(&tmA, a.A, a.K, a.M, a_batched ? a.batch : 1, a.lda, strideA, GEMM_BK, BM);
+        rc = make_map4(&tmA, a.A, a.K, a.M, a_lo ? a.batch_lo : 1, a_hi ? a.batch : 1, a.lda,
+                       a_lo ? (uint64_t)a.strideA_lo : dummyA, a_hi ? (uint64_t)a.strideA : dummyA, GEMM_BK, BM);
     if (rc) return rc;
-    rc = make_map(&tmB, a.B, a.N, a.K, b_batched ? a.batch : 1, a.ldb, strideB, 16, GEMM_BK);
+    rc = make_map4(&tmB, a.B, a.N, a.K, b_lo ? a.batch_lo : 1, b_hi ? a.batch : 1, a.ldb,
+                   b_lo ? (uint64_t)a.strideB_lo : dummyB, b_hi ? (uint64_t)a.strideB : dummyB, 16, GEMM_BK);
     if (rc) return rc;
     GemmParams p = p_in;
     p.tiles_m = (a.M + BM - 1) / BM;
     p.tiles_n = (a.N + BN - 1) / BN;
     p.group_m = a.group_m > 0 ? a.group_m : 1;
-    p.a_bmul = a_batched ? 1 : 0;
-    p.b_bmul = b_batched ? 1 : 0;
-    const long long n_tiles = (long long)p.tiles_m * p.tiles_n * a.batch;
+    p.a_lo_mul = a_lo; p.a_hi_mul = a_hi; p.b_lo_mul = b_lo; p.b_hi_mul = b_hi;
+    const long long n_tiles = (long long)p.tiles_m * p.tiles_n * a.batch * a.batch_lo;
     if (n_tiles > 0x7fffffffLL - 65536) return HB_ERR_INVALID;   // the kernel's tile counter steps by the grid size in int
     p.n_tiles = (int)n_tiles;
     const DeviceInfo dev = current_device_info();

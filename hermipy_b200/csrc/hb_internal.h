@@ -10,7 +10,7 @@
 namespace hb {
 
 struct GemmArgs {
-    int M = 0, N = 0, K = 0, batch = 1;
+    int M = 0, N = 0, K = 0, batch = 1;   // batch = number of b_hi entries; total GEMMs = batch * batch_lo
     const double* A = nullptr;  // a_mmajor ? [K][M] : [M][K]
     long long lda = 0, strideA = 0;  // stride 0 with batch > 1: operand shared by the batch
     bool a_mmajor = false;
@@ -18,6 +18,11 @@ struct GemmArgs {
     long long ldb = 0, strideB = 0;
     double* C = nullptr;
     long long ldc = 0, strideC = 0;
+    // two-level batch index b = b_hi * batch_lo + b_lo (see GemmParams): strideX is per b_hi, strideX_lo per b_lo;
+    // a stride of 0 at a level with more than one entry shares the operand across that level
+    int batch_lo = 1;
+    long long strideA_lo = 0, strideB_lo = 0, strideC_lo = 0;
+    int row_offset_lo = 0, col_offset_lo = 0;
     int epi = 0;
     const int* lut = nullptr;
     // varf scatter epilogue (see GemmParams in hb_gemm.cuh)

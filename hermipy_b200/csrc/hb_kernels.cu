@@ -372,6 +372,149 @@ int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int
     return HB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// d-dimensional parity split / merge (see ParityNDArgs).  One thread per point (h_a on the split axes, x_a on the
+// others) of every batch entry, last axis fastest: it loads the 2^M mirror images of its point, runs the M
+// butterflies in registers and stores the 2^M parity combinations -- every element is read once and written once
+// whatever the number of split axes (the per-axis passes this replaces moved the array once per axis).
+struct ParityNDWork {          // host-derived addressing of the work index (last axis fastest)
+    long long div[HB_MAX_DIM];  // product of the work extents of the faster axes
+    long long per_batch;        // work items per batch entry
+    int sq_axis[3];             // the split axes, outermost first
+};
+
+template <int M, bool MERGE>
+__global__ void nd_parity_kernel(ParityNDArgs a, ParityNDWork wk, const double* __restrict__ in,
+                                 double* __restrict__ out, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long b = idx / wk.per_batch;
+    long long nat = b * a.nat_bstride, srt = b * a.srt_bstride;
+    // natural / sorted offsets of the point, and per split axis: the two natural positions and the parity offset
+    long long pos_p[M], pos_m[M], par[M];
+    bool degenerate[M];
+#pragma unroll
+    for (int q = 0; q < M; q++) {
+        const int ax = wk.sq_axis[q];
+        const int c = (int)((idx / wk.div[ax]) % a.nh[ax]);
+        const int xp = a.n[ax] - a.nh[ax] + c, xm = a.n[ax] - 1 - xp;
+        pos_p[q] = xp * a.nat_stride[ax];
+        pos_m[q] = xm * a.nat_stride[ax];
+        degenerate[q] = (xm == xp);
+        par[q] = a.srt_par[ax];
+        srt += c * a.srt_stride[ax];
+    }
+#pragma unroll 1
+    for (int ax = 0; ax < a.d; ax++) {
+        if (a.split[ax]) continue;
+        const int c = (int)((idx / wk.div[ax]) % a.n[ax]);
+        nat += c * a.nat_stride[ax];
+        srt += c * a.srt_stride[ax];
+    }
+    const int last = a.d - 1;
+    const bool last_split = a.split[last] != 0;   // then slot M - 1 is the last axis
+    double v[1 << M];
+    if (!MERGE) {
+#pragma unroll
+        for (int s = 0; s < (1 << M); s++) {
+            long long off = nat;
+            bool absent = false;
+#pragma unroll
+            for (int q = 0; q < M; q++) {
+                const bool mirror = (s >> q) & 1;
+                off += mirror ? pos_m[q] : pos_p[q];
+                absent |= mirror && degenerate[q];
+            }
+            v[s] = absent ? 0.0 : in[off];
+        }
+#pragma unroll
+        for (int q = 0; q < M; q++)
+#pragma unroll
+            for (int s = 0; s < (1 << M); s++)
+                if (!((s >> q) & 1)) {
+                    const double x = v[s], y = v[s | (1 << q)];
+                    v[s] = x + y;
+                    v[s | (1 << q)] = degenerate[q] ? x * 0.0 : x - y;
+                }
+#pragma unroll
+        for (int s = 0; s < (1 << M); s++) {
+            long long off = srt;
+#pragma unroll
+            for (int q = 0; q < M; q++) off += ((s >> q) & 1) ? par[q] : 0;
+            out[off] = v[s];
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < (1 << M); s++) {
+            long long off = srt;
+#pragma unroll
+            for (int q = 0; q < M; q++) off += ((s >> q) & 1) ? par[q] : 0;
+            v[s] = in[off];
+        }
+#pragma unroll
+        for (int q = 0; q < M; q++)
+#pragma unroll
+            for (int s = 0; s < (1 << M); s++)
+                if (!((s >> q) & 1)) {
+                    const double e = v[s], o = v[s | (1 << q)];
+                    v[s] = e + o;
+                    v[s | (1 << q)] = e - o;
+                }
+        // the thread at work coordinate 0 of the last axis also zero-fills the pad columns of the rows it touches
+        const bool pads = a.nat_pad_last > a.n[last] && (idx % (last_split ? a.nh[last] : a.n[last])) == 0;
+#pragma unroll
+        for (int s = 0; s < (1 << M); s++) {
+            long long off = nat, row = nat;   // row: the same point with the last axis at its origin
+            bool absent = false;
+#pragma unroll
+            for (int q = 0; q < M; q++) {
+                const bool mirror = (s >> q) & 1;
+                const long long pq = mirror ? pos_m[q] : pos_p[q];
+                off += pq;
+                if (!(q == M - 1 && last_split)) row += pq;
+                absent |= mirror && degenerate[q];
+            }
+            if (absent) continue;
+            out[off] = v[s];
+            if (pads && !(last_split && ((s >> (M - 1)) & 1)))
+                for (int c = a.n[last]; c < a.nat_pad_last; c++) out[row + c * a.nat_stride[last]] = 0.0;
+        }
+    }
+}
+
+template <bool MERGE>
+static int launch_nd_parity(const ParityNDArgs& a, const double* in, double* out, cudaStream_t s) {
+    if (a.d < 1 || a.d > HB_MAX_DIM) { set_error("nd parity pass: 1..%d axes supported", HB_MAX_DIM); return HB_ERR_INVALID; }
+    ParityNDWork wk = {};
+    int m = 0;
+    long long total = 1;
+    for (int ax = a.d - 1; ax >= 0; ax--) {
+        wk.div[ax] = total;
+        total *= a.split[ax] ? a.nh[ax] : a.n[ax];
+    }
+    for (int ax = 0; ax < a.d; ax++)
+        if (a.split[ax]) {
+            if (m < 3) wk.sq_axis[m] = ax;
+            m++;
+        }
+    wk.per_batch = total;
+    total *= a.batch;
+    if (total <= 0) return HB_OK;
+    if (m < 1 || m > 3) { set_error("nd parity pass: 1..3 split axes supported (got %d)", m); return HB_ERR_INVALID; }
+    const long long blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) { set_error("nd parity pass: grid too large"); return HB_ERR_INVALID; }
+    if (m == 1) nd_parity_kernel<1, MERGE><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+    else if (m == 2) nd_parity_kernel<2, MERGE><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+    else nd_parity_kernel<3, MERGE><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+    return launch_status();
+}
+int launch_nd_parity_split(const ParityNDArgs& a, const double* natural, double* sorted, cudaStream_t s) {
+    return launch_nd_parity<false>(a, natural, sorted, s);
+}
+int launch_nd_parity_merge(const ParityNDArgs& a, const double* sorted, double* natural, cudaStream_t s) {
+    return launch_nd_parity<true>(a, sorted, natural, s);
+}
+
 // De-interleave by parity in one pass (1-D inverse transform on a symmetric node set): row r of `src` holds the
 // coefficients in natural order; even[r][j] = src[r][2j] (j < Pe), odd[r][j] = src[r][2j+1] (j < Po), pad columns
 // up to the even pitches lde / ldo zeroed (they are GEMM operands).  Each source sector is read once.

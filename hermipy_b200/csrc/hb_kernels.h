@@ -28,6 +28,23 @@ int launch_strided_copy(const double* src, long long src_ld, int r0, int rs, int
                         long long dst_ld, long long rows, int cols, int batch, long long src_bstride,
                         long long dst_bstride, cudaStream_t s);
 int launch_parity_split(const double* f, int n, int nh, int seg, long long pitch, double* out, cudaStream_t s);
+
+// Parity split / merge of a d-dimensional grid function along up to three axes AT ONCE (one pass over the data).
+// "Natural" array: axis a has n[a] entries nat_stride[a] apart.  "Sorted" array: a split axis is indexed by
+// (parity p, h) with h < nh[a] = ceil(n[a]/2) counting the non-negative nodes x = n - nh + h; the entry sits at
+// h * srt_stride[a] + p * srt_par[a].  Other axes keep their index (srt_stride[a] apart).
+//   split:  sorted[p..][h..] = sum over the sign combinations of (+-1)^(p.s) natural[x(+-)..]   (even part: f(x)+f(-x))
+//   merge:  natural[x(+-)..] = sum over parities of (+-1)^(p.s) sorted[p..][h..]               (f(+-x) = g_e +- g_o)
+// The middle node of an odd rule is taken once: its odd part is 0 * f (NaN / inf stay visible, as in 0 * f * w * phi).
+struct ParityNDArgs {
+    int d = 0;
+    int n[HB_MAX_DIM] = {0}, nh[HB_MAX_DIM] = {0}, split[HB_MAX_DIM] = {0};
+    long long nat_stride[HB_MAX_DIM] = {0}, srt_stride[HB_MAX_DIM] = {0}, srt_par[HB_MAX_DIM] = {0};
+    long long batch = 1, nat_bstride = 0, srt_bstride = 0;
+    int nat_pad_last = 0;   // merge: columns n[d-1] .. nat_pad_last-1 of every natural row are zero-filled
+};
+int launch_nd_parity_split(const ParityNDArgs& a, const double* natural, double* sorted, cudaStream_t s);
+int launch_nd_parity_merge(const ParityNDArgs& a, const double* sorted, double* natural, cudaStream_t s);
 int launch_deinterleave_rows(const double* src, long long src_ld, int Pe, int Po, double* even, long long lde, double* odd,
                              long long ldo, long long rows, cudaStream_t s);
 int launch_repack_rows(const double* src, long long src_ld, double* dst, long long dst_ld, long long rows, int cols,

@@ -114,7 +114,7 @@ int timed_gemm(hb_plan* pl, const GemmArgs& g, int tag, cudaStream_t st) {
     }
     hb_plan::Timed& t = pl->timed[pl->n_timed++];
     t.tag = tag;
-    t.flops = 2.0 * g.M * (double)g.N * g.K * g.batch;
+    t.flops = 2.0 * g.M * (double)g.N * g.K * g.batch * g.batch_lo;
     HB_CUDA(cudaEventRecord(t.e0, st));
     const int rc = gemm_launch(g, st);
     HB_CUDA(cudaEventRecord(t.e1, st));
@@ -263,9 +263,9 @@ static int ensure_parity_tables(Axis& A, cudaStream_t st) {
 }
 
 // The coefficient box in which the axes of `mask` are parity-sorted: per sorted axis the index runs over the even
-// basis functions first and then the odd ones (on the last axis the odd block starts at the even offset Pep, so
-// that both blocks are 16-byte aligned; the pitch is Pep + Pop).  Returns the look-up table box cell -> position in
-// the index set (-1 for padding and for cells outside the set).
+// basis functions first and then the odd ones, both blocks padded to the same extent (Pe = ceil(P/2) rows; on the
+// last axis Pep = Pe rounded up to even columns, so that both blocks are 16-byte aligned).  Returns the look-up
+// table box cell -> position in the index set (-1 for padding and for cells outside the set).
 static int sorted_box(hb_plan* pl, int mask, hb_plan::SortedBox** out, cudaStream_t st) {
     auto it = pl->sorted_boxes.find(mask);
     if (it != pl->sorted_boxes.end()) { *out = &it->second; return HB_OK; }
@@ -275,11 +275,12 @@ static int sorted_box(hb_plan* pl, int mask, hb_plan::SortedBox** out, cudaStrea
         const Axis& A = pl->ax[a];
         const Parity1D q = parity_dims(A);
         const bool last = (a == d - 1);
-        if (mask >> a & 1) {
+        if (mask >> a & 1) {   // both parity blocks have the same extent: Pe rows, or Pep columns on the last axis
+            const int blk = last ? q.Pep : q.Pe;
             for (int k = 0; k < q.Pe; k++) index[a].push_back(2 * k);
-            if (last) while ((int)index[a].size() < q.Pep) index[a].push_back(-1);
+            while ((int)index[a].size() < blk) index[a].push_back(-1);
             for (int k = 0; k < q.Po; k++) index[a].push_back(2 * k + 1);
-            if (last) while ((int)index[a].size() < q.Pep + q.Pop) index[a].push_back(-1);
+            while ((int)index[a].size() < 2 * blk) index[a].push_back(-1);
         } else {
             for (int k = 0; k < A.P; k++) index[a].push_back(k);
             if (last) while ((int)index[a].size() < A.Pp) index[a].push_back(-1);
@@ -311,23 +312,6 @@ static int sorted_box(hb_plan* pl, int mask, hb_plan::SortedBox** out, cudaStrea
     HB_CUDA(cudaStreamSynchronize(st));   // `lut` goes out of scope
     *out = &box;
     return HB_OK;
-}
-
-// Which axis contractions of a d-dimensional transform of `batch` functions are split by parity (bit a).
-static int parity_mask(const hb_plan* pl, int batch, bool flat_last) {
-    const int d = pl->dim;
-    int mask = 0;
-    // sum-factorised stage sizes of the forward transform (the inverse mirrors them)
-    long long prefix = (long long)batch * pl->grid_rows;
-    double cols = pl->ax[d - 1].P;
-    if (flat_last && parity_stage(pl->ax[d - 1], 2.0 * prefix * pl->ax[d - 1].n * pl->ax[d - 1].P)) mask |= 1 << (d - 1);
-    for (int a = d - 2; a >= 0; a--) {
-        const Axis& A = pl->ax[a];
-        prefix /= A.n;
-        if (parity_stage(A, 2.0 * prefix * A.P * A.n * cols)) mask |= 1 << a;
-        cols *= A.P;
-    }
-    return mask;
 }
 
 // Contraction of the LAST grid axis of `rows` rows (pitch f_pitch) into interleaved even / odd coefficients
@@ -386,6 +370,243 @@ static int backward_last_axis_parity(hb_plan* pl, Axis& A, const double* d_coef,
                                     (int)rows, st);
 }
 
+// Which axes of a d-dimensional (d >= 2) transform of `batch` functions are split by parity (bit a).  The split
+// costs one extra pass over the grid values per direction (all axes at once), so it is taken when the transform is
+// large enough for half the flops to pay for it; every symmetric axis is split then (at most three: the pass
+// handles 2^3 mirror images per thread).
+static int parity_mask(const hb_plan* pl, int batch) {
+    const int mode = parity_mode();
+    if (mode == 0) return 0;
+    const int d = pl->dim;
+    double flops = 0, prefix = (double)batch * pl->grid_rows * pl->ax[d - 1].n, cols = 1;
+    for (int a = d - 1; a >= 0; a--) {
+        const Axis& A = pl->ax[a];
+        prefix /= A.n;
+        flops += 2.0 * prefix * A.n * A.P * cols;
+        cols *= A.P;
+    }
+    static const double min_gflop = [] { const char* e = getenv("HB_TRANSFORM_PARITY_GFLOP"); return e && e[0] ? atof(e) : 4.0; }();
+    if (mode != 2 && flops < min_gflop * 1e9) return 0;
+    int mask = 0, count = 0;
+    for (int a = d - 1; a >= 0 && count < 3; a--) {
+        const Axis& A = pl->ax[a];
+        if (A.symmetric_nodes && A.n >= 4 && A.P >= 4) { mask |= 1 << a; count++; }
+    }
+    return mask;
+}
+
+static int ensure_combined_parity_tables(Axis& A, cudaStream_t st) {
+    if (A.cpar_tables) return HB_OK;
+    const Parity1D d = parity_dims(A);
+    const size_t ik = (size_t)d.nh * d.Pep, ki = (size_t)d.Pe * d.nhp;
+    HB_TRY(A.cW.ensure_zero(2 * ik * 8, st));
+    HB_TRY(A.cPhi.ensure_zero(2 * ik * 8, st));
+    HB_TRY(A.cWT.ensure_zero(2 * ki * 8, st));
+    HB_TRY(A.cPhiT.ensure_zero(2 * ki * 8, st));
+    for (int par = 0; par < 2; par++) {
+        const int Pq = par ? d.Po : d.Pe;
+        if (Pq == 0) continue;
+        // [node h][basis]: rows lo + h, every second column
+        HB_TRY(launch_strided_copy(A.wgt.d(), A.Pp, d.lo, 1, par, 2, A.cW.d() + par * ik, d.Pep, d.nh, Pq, 1, 0, 0, st));
+        HB_TRY(launch_strided_copy(A.plain.d(), A.Pp, d.lo, 1, par, 2, A.cPhi.d() + par * ik, d.Pep, d.nh, Pq, 1, 0, 0, st));
+        // [basis][node h]: every second row, columns lo + h
+        HB_TRY(launch_strided_copy(A.wgtT.d(), A.np, par, 2, d.lo, 1, A.cWT.d() + par * ki, d.nhp, Pq, d.nh, 1, 0, 0, st));
+        HB_TRY(launch_strided_copy(A.plainT.d(), A.np, par, 2, d.lo, 1, A.cPhiT.d() + par * ki, d.nhp, Pq, d.nh, 1, 0, 0, st));
+    }
+    A.cpar_tables = true;
+    return HB_OK;
+}
+
+// Geometry of a d >= 2 transform whose axes in `mask` are split by parity.  A split axis is indexed by
+// (parity, h) on the grid side -- 2 x nh entries, 2 x nhp on the last axis -- and by (parity, k') on the
+// coefficient side -- 2 x Pe entries, 2 x Pep on the last axis (see sorted_box).
+struct ParityGeom {
+    int d = 0;
+    long long G[HB_MAX_DIM], C[HB_MAX_DIM];   // grid-side / coefficient-side extent of every axis
+    long long grid_size = 1, box_size = 1;
+};
+static ParityGeom parity_geometry(const hb_plan* pl, int mask) {
+    ParityGeom g;
+    g.d = pl->dim;
+    for (int a = 0; a < g.d; a++) {
+        const Axis& A = pl->ax[a];
+        const bool last = (a == g.d - 1);
+        if (mask >> a & 1) {
+            const Parity1D q = parity_dims(A);
+            g.G[a] = last ? 2 * q.nhp : 2 * q.nh;
+            g.C[a] = last ? 2 * q.Pep : 2 * q.Pe;
+        } else {
+            g.G[a] = last ? A.np : A.n;
+            g.C[a] = last ? A.Pp : A.P;
+        }
+        g.grid_size *= g.G[a];
+        g.box_size *= g.C[a];
+    }
+    return g;
+}
+
+// natural grid layout <-> parity-sorted layout of this plan (batch entries f_stride / geom.grid_size apart)
+static ParityNDArgs parity_pass_args(const hb_plan* pl, int mask, const ParityGeom& geom, long long f_stride, int batch) {
+    ParityNDArgs pa;
+    const int d = pl->dim;
+    pa.d = d;
+    long long nat = 1, srt = 1;
+    for (int a = d - 1; a >= 0; a--) {
+        const Axis& A = pl->ax[a];
+        const Parity1D q = parity_dims(A);
+        pa.n[a] = A.n; pa.nh[a] = q.nh; pa.split[a] = (mask >> a) & 1;
+        pa.nat_stride[a] = nat;
+        pa.srt_stride[a] = srt;
+        pa.srt_par[a] = (a == d - 1 ? q.nhp : q.nh) * srt;
+        nat *= (a == d - 1) ? A.np : A.n;
+        srt *= geom.G[a];
+    }
+    pa.batch = batch; pa.nat_bstride = f_stride; pa.srt_bstride = geom.grid_size;
+    pa.nat_pad_last = pl->ax[d - 1].np;
+    return pa;
+}
+
+// Forward transform with the axes in `mask` split by parity: ONE pass sorts the grid values by parity along all
+// split axes (nd_parity_kernel), then every axis contraction is one GEMM launch whose two low-level batch entries
+// are the even and the odd half (half the flops of the plain stage), the last one scattering into set order.
+static int forward_parity(hb_plan* pl, int mask, const double* d_f, long long f_stride, int batch, double* d_coef,
+                          long long coef_stride, cudaStream_t st) {
+    const int d = pl->dim, L = d - 1;
+    const ParityGeom geom = parity_geometry(pl, mask);
+    hb_plan::SortedBox* box = nullptr;
+    HB_TRY(sorted_box(pl, mask, &box, st));
+    for (int a = 0; a < d; a++)
+        if (mask >> a & 1) HB_TRY(ensure_combined_parity_tables(pl->ax[a], st));
+    // workspace: the sorted grid and every intermediate [grid axes < a][coefficient axes >= a]
+    size_t need = (size_t)batch * geom.grid_size;
+    {
+        long long size = (long long)batch * geom.grid_size;
+        for (int a = L; a >= 1; a--) {
+            size = size / geom.G[a] * geom.C[a];
+            need = std::max(need, (size_t)size);
+        }
+    }
+    HB_TRY(pl->ws[0].ensure(need * 8));
+    HB_TRY(pl->ws[1].ensure(need * 8));
+    pl->n_timed = 0;
+    HB_TRY(launch_nd_parity_split(parity_pass_args(pl, mask, geom, f_stride, batch), d_f, pl->ws[0].d(), st));
+    long long prefix = (long long)batch * geom.grid_size / geom.G[L];   // rows of the last-axis stage
+    {
+        Axis& A = pl->ax[L];
+        GemmArgs g;
+        g.M = (int)prefix;
+        g.A = pl->ws[0].d(); g.lda = geom.G[L];
+        g.C = pl->ws[1].d(); g.ldc = geom.C[L];
+        if (mask >> L & 1) {
+            const Parity1D q = parity_dims(A);
+            g.K = q.nh; g.N = q.Pe; g.batch_lo = 2;
+            g.strideA_lo = q.nhp;
+            g.B = A.cW.d(); g.ldb = q.Pep; g.strideB_lo = (long long)q.nh * q.Pep;
+            g.strideC_lo = q.Pep;
+        } else {
+            g.K = A.n; g.N = A.Pp;
+            g.B = A.wgt.d(); g.ldb = A.Pp;
+        }
+        HB_TRY(timed_gemm(pl, g, d, st));
+    }
+    int cur = 1;
+    long long cols = geom.C[L];
+    for (int a = L - 1; a >= 0; a--) {
+        Axis& A = pl->ax[a];
+        prefix /= geom.G[a];
+        GemmArgs g;
+        g.N = (int)cols; g.batch = (int)prefix;
+        g.B = pl->ws[cur].d(); g.ldb = cols; g.strideB = geom.G[a] * cols;
+        if (mask >> a & 1) {
+            const Parity1D q = parity_dims(A);
+            g.M = q.Pe; g.K = q.nh; g.batch_lo = 2;
+            g.A = A.cWT.d(); g.lda = q.nhp; g.strideA_lo = (long long)q.Pe * q.nhp;
+            g.strideB_lo = (long long)q.nh * cols;
+            g.strideC_lo = (long long)q.Pe * cols;
+            g.row_offset_lo = q.Pe;
+        } else {
+            g.M = A.P; g.K = A.n;
+            g.A = A.wgtT.d(); g.lda = A.np;
+        }
+        if (a == 0) {
+            g.C = d_coef; g.strideC = coef_stride; g.strideC_lo = 0; g.epi = EPI_LUT; g.lut = box->lut.i();
+        } else {
+            g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = geom.C[a] * cols; g.row_offset_lo = 0;
+        }
+        HB_TRY(timed_gemm(pl, g, 1 + a, st));
+        cols *= geom.C[a];
+        cur ^= 1;
+    }
+    return HB_OK;
+}
+
+// Inverse of it: coefficients gathered into the parity-sorted box, one GEMM launch per axis (even / odd halves as
+// low-level batch entries), and ONE butterfly pass f(+-x) = g_e +- g_o over all split axes at the end.
+static int backward_parity(hb_plan* pl, int mask, const double* d_coef, long long coef_stride, int batch, double* d_f,
+                           long long f_stride, cudaStream_t st) {
+    const int d = pl->dim, L = d - 1;
+    const ParityGeom geom = parity_geometry(pl, mask);
+    hb_plan::SortedBox* box = nullptr;
+    HB_TRY(sorted_box(pl, mask, &box, st));
+    for (int a = 0; a < d; a++)
+        if (mask >> a & 1) HB_TRY(ensure_combined_parity_tables(pl->ax[a], st));
+    size_t need = (size_t)batch * geom.box_size;
+    {
+        long long size = (long long)batch * geom.box_size;
+        for (int a = L; a >= 0; a--) {
+            size = size / geom.C[a] * geom.G[a];
+            need = std::max(need, (size_t)size);
+        }
+    }
+    HB_TRY(pl->ws[0].ensure(need * 8));
+    HB_TRY(pl->ws[1].ensure(need * 8));
+    HB_TRY(launch_gather_lut(d_coef, coef_stride, box->lut.i(), pl->ws[0].d(), geom.box_size, geom.box_size, batch, st));
+    pl->n_timed = 0;
+    long long prefix = (long long)batch * geom.box_size / geom.C[L];
+    {
+        Axis& A = pl->ax[L];
+        GemmArgs g;
+        g.M = (int)prefix;
+        g.A = pl->ws[0].d(); g.lda = geom.C[L];
+        g.C = pl->ws[1].d(); g.ldc = geom.G[L];
+        if (mask >> L & 1) {
+            const Parity1D q = parity_dims(A);
+            g.K = q.Pe; g.N = q.nh; g.batch_lo = 2;
+            g.strideA_lo = q.Pep;
+            g.B = A.cPhiT.d(); g.ldb = q.nhp; g.strideB_lo = (long long)q.Pe * q.nhp;
+            g.strideC_lo = q.nhp;
+        } else {
+            g.K = A.P; g.N = A.np;
+            g.B = A.plainT.d(); g.ldb = A.np;
+        }
+        HB_TRY(timed_gemm(pl, g, 10 + d, st));
+    }
+    int cur = 1;
+    long long cols = geom.G[L];
+    for (int a = L - 1; a >= 0; a--) {
+        Axis& A = pl->ax[a];
+        prefix /= geom.C[a];
+        GemmArgs g;
+        g.N = (int)cols; g.batch = (int)prefix;
+        g.B = pl->ws[cur].d(); g.ldb = cols; g.strideB = geom.C[a] * cols;
+        g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = geom.G[a] * cols;
+        if (mask >> a & 1) {
+            const Parity1D q = parity_dims(A);
+            g.M = q.nh; g.K = q.Pe; g.batch_lo = 2;
+            g.A = A.cPhi.d(); g.lda = q.Pep; g.strideA_lo = (long long)q.nh * q.Pep;
+            g.strideB_lo = (long long)q.Pe * cols;
+            g.strideC_lo = (long long)q.nh * cols;
+        } else {
+            g.M = A.n; g.K = A.P;
+            g.A = A.plain.d(); g.lda = A.Pp;
+        }
+        HB_TRY(timed_gemm(pl, g, 11 + a, st));
+        cols *= geom.G[a];
+        cur ^= 1;
+    }
+    return launch_nd_parity_merge(parity_pass_args(pl, mask, geom, f_stride, batch), pl->ws[cur].d(), d_f, st);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Forward: c[j] = sum_i f[i] prod_d w_d[i_d] phi_{m_j,d}(x_{i_d})   (transform.cpp:115-139), contracted
 // one axis at a time, last axis first.
@@ -408,20 +629,12 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
         pl->n_timed = 0;
         return timed_gemm(pl, g, 1, st);
     }
+    if (const int mask = parity_mask(pl, batch)) return forward_parity(pl, mask, d_f, f_stride, batch, d_coef, coef_stride, st);
     Axis& L = pl->ax[d - 1];
     const long long rows1 = pl->grid_rows;
     const bool flat = (f_stride == rows1 * L.np || batch == 1);
-    // Axes whose contraction is split by parity keep their coefficient index parity-sorted in every intermediate
-    // and in the look-up table of the final scatter (see sorted_box).
-    const int mask = parity_mask(pl, batch, flat);
     const int* lut = pl->lut_box.i();
     long long cols = L.Pp;
-    if (mask) {
-        hb_plan::SortedBox* box = nullptr;
-        HB_TRY(sorted_box(pl, mask, &box, st));
-        lut = box->lut.i();
-        cols = box->pitch;
-    }
     // workspace: largest intermediate
     size_t need = (size_t)batch * rows1 * cols;
     {
@@ -435,9 +648,7 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
     HB_TRY(pl->ws[0].ensure(need * 8));
     if (d > 2) HB_TRY(pl->ws[1].ensure(need * 8));
     pl->n_timed = 0;
-    if (mask >> (d - 1) & 1) {
-        HB_TRY(forward_last_axis_parity(pl, L, d_f, L.np, batch * rows1, pl->ws[0].d(), cols, d, st, true));
-    } else {
+    {
         GemmArgs g;
         g.K = L.n; g.N = L.Pp;
         g.A = d_f; g.lda = L.np;
@@ -455,34 +666,6 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
     for (int a = d - 2; a >= 0; a--) {
         Axis& A = pl->ax[a];
         prefix /= A.n;
-        if (mask >> a & 1) {
-            // even / odd parts of the operand along x_a, then out[par block][cols] = W_par^T[m][h] * B_par[h][cols]:
-            // the even results fill rows [0, Pe), the odd ones rows [Pe, P) of the parity-sorted output
-            const Parity1D q = parity_dims(A);
-            HB_TRY(ensure_parity_tables(A, st));
-            const size_t half = (size_t)prefix * q.nh * cols;
-            HB_TRY(pl->parA.ensure(half * 8));
-            HB_TRY(pl->parB.ensure(half * 8));
-            HB_TRY(launch_axis_parity_split(pl->ws[cur].d(), (long long)A.n * cols, A.n, q.nh, cols, (int)prefix,
-                                            pl->parA.d(), pl->parB.d(), st));
-            for (int par = 0; par < 2; par++) {
-                GemmArgs g;
-                g.M = par ? q.Po : q.Pe; g.K = q.nh; g.N = (int)cols; g.batch = (int)prefix;
-                g.A = par ? A.pWoT.d() : A.pWeT.d(); g.lda = q.nhp; g.strideA = 0;
-                g.B = par ? pl->parB.d() : pl->parA.d(); g.ldb = cols; g.strideB = (long long)q.nh * cols;
-                if (a == 0) {
-                    g.C = d_coef; g.strideC = coef_stride; g.epi = EPI_LUT; g.lut = lut;
-                    g.row_stride = 1; g.row_offset = par ? q.Pe : 0;
-                } else {
-                    g.C = pl->ws[cur ^ 1].d() + (size_t)(par ? q.Pe : 0) * cols; g.ldc = cols;
-                    g.strideC = (long long)A.P * cols;
-                }
-                HB_TRY(timed_gemm(pl, g, 1 + a, st));
-            }
-            cols *= A.P;
-            cur ^= 1;
-            continue;
-        }
         GemmArgs g;
         g.M = A.P; g.K = A.n; g.N = (int)cols; g.batch = (int)prefix;
         g.A = A.wgtT.d(); g.lda = A.np; g.strideA = 0;
@@ -518,17 +701,9 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
         pl->n_timed = 0;
         return timed_gemm(pl, g, 11, st);
     }
+    if (const int mask = parity_mask(pl, batch)) return backward_parity(pl, mask, d_coef, coef_stride, batch, d_f, f_stride, st);
     Axis& L = pl->ax[d - 1];
-    const int mask = parity_mask(pl, batch, true);
-    const int* lut = pl->lut_box.i();
-    long long box_pitch = L.Pp, box_size = pl->box_size;
-    if (mask) {
-        hb_plan::SortedBox* box = nullptr;
-        HB_TRY(sorted_box(pl, mask, &box, st));
-        lut = box->lut.i();
-        box_pitch = box->pitch;
-        box_size = box->size;
-    }
+    const long long box_pitch = L.Pp, box_size = pl->box_size;
     size_t need = (size_t)batch * box_size;
     {
         long long c = L.np, prefix = (long long)batch * pl->box_rows;
@@ -541,14 +716,11 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
     }
     HB_TRY(pl->ws[0].ensure(need * 8));
     HB_TRY(pl->ws[1].ensure(need * 8));
-    // coefficients in set order -> zero-padded (parity-sorted) lexicographic box
-    HB_TRY(launch_gather_lut(d_coef, coef_stride, lut, pl->ws[0].d(), box_size, box_size, batch, st));
+    // coefficients in set order -> zero-padded lexicographic box
+    HB_TRY(launch_gather_lut(d_coef, coef_stride, pl->lut_box.i(), pl->ws[0].d(), box_size, box_size, batch, st));
     long long cols = L.np;
     pl->n_timed = 0;
-    if (mask >> (d - 1) & 1) {
-        HB_TRY(backward_last_axis_parity(pl, L, pl->ws[0].d(), box_pitch, batch * pl->box_rows, pl->ws[1].d(), cols,
-                                         10 + d, st, true));
-    } else {
+    {
         GemmArgs g;
         g.M = (int)(batch * pl->box_rows); g.K = L.P; g.N = L.np;
         g.A = pl->ws[0].d(); g.lda = box_pitch;
@@ -561,29 +733,6 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
     for (int a = d - 2; a >= 0; a--) {
         Axis& A = pl->ax[a];
         prefix /= A.P;
-        if (mask >> a & 1) {
-            // g_par[h][cols] = Phi_par[h][m] * cur[par block][cols] (even rows [0, Pe), odd rows [Pe, P) of the
-            // parity-sorted operand), then the butterfly out[lo+h] = g_e + g_o, out[n-1-lo-h] = g_e - g_o
-            const Parity1D q = parity_dims(A);
-            HB_TRY(ensure_parity_tables(A, st));
-            const size_t half = (size_t)prefix * q.nh * cols;
-            HB_TRY(pl->parA.ensure(half * 8));
-            HB_TRY(pl->parB.ensure(half * 8));
-            for (int par = 0; par < 2; par++) {
-                GemmArgs g;
-                g.M = q.nh; g.K = par ? q.Po : q.Pe; g.N = (int)cols; g.batch = (int)prefix;
-                g.A = par ? A.pPhiO.d() : A.pPhiE.d(); g.lda = par ? q.Pop : q.Pep; g.strideA = 0;
-                g.B = pl->ws[cur].d() + (size_t)(par ? q.Pe : 0) * cols; g.ldb = cols; g.strideB = (long long)A.P * cols;
-                g.C = par ? pl->parB.d() : pl->parA.d(); g.ldc = cols; g.strideC = (long long)q.nh * cols;
-                HB_TRY(timed_gemm(pl, g, 11 + a, st));
-            }
-            double* out = (a == 0) ? d_f : pl->ws[cur ^ 1].d();
-            const long long out_stride = (a == 0) ? f_stride : (long long)A.n * cols;
-            HB_TRY(launch_axis_parity_merge(pl->parA.d(), pl->parB.d(), A.n, q.nh, cols, (int)prefix, out, out_stride, st));
-            cols *= A.n;
-            cur ^= 1;
-            continue;
-        }
         GemmArgs g;
         g.M = A.n; g.K = A.P; g.N = (int)cols; g.batch = (int)prefix;
         g.A = A.plain.d(); g.lda = A.Pp; g.strideA = 0;

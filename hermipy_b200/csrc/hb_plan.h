@@ -69,6 +69,11 @@ struct Axis {
     //   pPhiE / pPhiO [nh][Pe|Po]  phi          inverse, other axes      (A operand)
     DevBuf pWe, pWo, pWeT, pWoT, pPe, pPo, pPhiE, pPhiO;
     bool par_tables = false;
+    // the same tables with both parities in ONE buffer of uniform shape (d >= 2 transforms run the even and the odd
+    // half of a stage as the two low-level batch entries of one GEMM launch); entry 1 (odd) is zero-padded to the
+    // shape of entry 0:  cW / cPhi [2][nh][Pep],  cWT / cPhiT [2][Pe][nhp]
+    DevBuf cW, cWT, cPhi, cPhiT;
+    bool cpar_tables = false;
 };
 
 }  // namespace hb

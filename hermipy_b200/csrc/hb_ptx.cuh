@@ -64,6 +64,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// 4-D variant: the GEMM maps are {contiguous, pitched, batch_lo, batch_hi} (two-level batch index).
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6}], [%2];"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor in the stream is still running; `grid_dependency_wait` blocks until the predecessor has
 // completed and its memory is visible (a no-op for a normal launch), `grid_launch_dependents` lets the successor

@@ -205,8 +205,10 @@ def test_varf_fourier_x_hermite_2d_band_path(core, ref, index_set):
         assert np.array_equal(A != 0, R != 0)
         assert rel_err(A, R) < TOL
         assert rel_err(core.varf(degree, f, [x, y], [w, v], do_fourier=[1, 0], index_set=index_set), R) < TOL
-        D = core.varfd(2, degree, 0, A, do_fourier=1, index_set=index_set)
-        assert np.array_equal(D, ref.varfd(2, degree, 0, A, do_fourier=1, index_set=index_set))
+        if index_set == "cube":   # on a triangle set the reference looks up sin -> cos one degree up, outside the
+            #                       set, and exits ("Element not found in hash table", lib.cpp:76-84)
+            D = core.varfd(2, degree, 0, A, do_fourier=1, index_set=index_set)
+            assert np.array_equal(D, ref.varfd(2, degree, 0, A, do_fourier=1, index_set=index_set))
 
 
 @pytest.mark.parametrize("index_set", SETS)
@@ -398,6 +400,33 @@ def test_transform_2d_parity_split(core, ref, force_transform_parity, index_set)
     want = ref.transform(degree, c, [x, y], [w, v], False, index_set=index_set)
     sw = np.sqrt(np.outer(w, v)).ravel()
     assert rel_err(back * sw, want * sw) < TOL
+
+
+def test_transform_parity_split_mixed_axes(core, ref, force_transform_parity):
+    """Axes that cannot be split stay in natural order next to split ones: a Fourier axis (outer and inner), and a
+    4-D grid (the one-pass split handles at most three axes)."""
+    xf, wf = _fourier_rule(16)
+    y, v = gauss_hermite(13)
+    for nodes, weights, four in (([xf, y], [wf, v], [1, 0]), ([y, xf], [v, wf], [0, 1])):
+        X, Y = np.meshgrid(*nodes, indexing="ij")
+        f = np.exp(np.cos(X if four[0] else Y)) * np.exp(-(Y if four[0] else X) ** 2 / 7) * (1 + 0.2 * X + 0.1 * Y)
+        c = core.transform(8, f, nodes, weights, True, do_fourier=four, index_set="cube")
+        assert rel_err(c, ref.transform(8, f.ravel(), nodes, weights, True, do_fourier=four, index_set="cube")) < TOL
+        back = core.transform(8, c, nodes, weights, False, do_fourier=four, index_set="cube")
+        want = ref.transform(8, c, nodes, weights, False, do_fourier=four, index_set="cube")
+        sw = np.sqrt(np.outer(weights[0], weights[1])).ravel()
+        assert rel_err(back * sw, want * sw) < TOL
+    rules = [gauss_hermite(n) for n in (7, 6, 5, 6)]
+    nodes, weights = [r[0] for r in rules], [r[1] for r in rules]
+    X = np.meshgrid(*nodes, indexing="ij")
+    f = np.exp(-(X[0] ** 2 + X[1] ** 2 + X[2] ** 2 + X[3] ** 2) / 8) * (1 + X[0] * X[3] - X[1] + 0.5 * X[2])
+    for index_set in ("triangle", "cube"):
+        c = core.transform(4, f, nodes, weights, True, index_set=index_set)
+        assert rel_err(c, ref.transform(4, f.ravel(), nodes, weights, True, index_set=index_set)) < TOL
+        back = core.transform(4, c, nodes, weights, False, index_set=index_set)
+        want = ref.transform(4, c, nodes, weights, False, index_set=index_set)
+        sw = np.sqrt(np.einsum("i,j,k,l->ijkl", *weights)).ravel()
+        assert rel_err(back * sw, want * sw) < TOL
 
 
 @pytest.mark.parametrize("index_set", ["triangle", "cube", "rectangle"])

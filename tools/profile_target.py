@@ -3,6 +3,7 @@
     python tools/profile_target.py c2        # 2 x (forward + inverse) C2 transform step, batch 17
     python tools/profile_target.py varf      # C2 cube varf: polynomial f (banded assembly) + dense f (Gram GEMM)
     python tools/profile_target.py c5        # one C5 forward+inverse over 8192 rows
+    python tools/profile_target.py c4        # 2 x (forward + inverse) 256^3 transform
     python tools/profile_target.py matvec    # y = A x on a 40401 x 40401 resident matrix (the C2 cube varf size)
     python tools/profile_target.py gemm M N K CFG   # three launches of one plain GEMM with tile configuration CFG
 """
@@ -48,6 +49,15 @@ elif which == "c5":
     f = torch.randn(8192, pl.grid_size, dtype=torch.float64, device="cuda")
     c = pl.forward(f)
     pl.backward(c)
+elif which == "c4":
+    x, w = gh(256)
+    pl = Plan(255, [x] * 3, [w] * 3, index_set="cube")
+    f = torch.randn(1, pl.grid_size, dtype=torch.float64, device="cuda")
+    c = pl.empty_coef(1)
+    g = pl.empty_grid(1)
+    for _ in range(2):
+        pl.forward(f, c)
+        pl.backward(c, g)
 elif which == "gemm":
     from hermipy_b200.plan import dgemm
     M, N, K, cfg = (int(v) for v in sys.argv[2:6])
