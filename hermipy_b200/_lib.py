@@ -35,6 +35,17 @@ class DegreeError(HermiteB200Error, ValueError):
     """n_polys matches no degree (the reference prints "Can't find x" and exits, lib.cpp:93-99)."""
 
 
+class GemmDesc(C.Structure):
+    """hb_gemm_desc of include/hermite_b200.h"""
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int), ("batch_lo", C.c_int),
+                ("a_mmajor", C.c_int),
+                ("A", C.c_void_p), ("lda", C.c_longlong), ("strideA", C.c_longlong), ("strideA_lo", C.c_longlong),
+                ("B", C.c_void_p), ("ldb", C.c_longlong), ("strideB", C.c_longlong), ("strideB_lo", C.c_longlong),
+                ("C", C.c_void_p), ("ldc", C.c_longlong), ("strideC", C.c_longlong), ("strideC_lo", C.c_longlong),
+                ("n_blocks", C.c_int), ("block_rows", C.c_int), ("row_offset", C.c_int), ("row_offset_lo", C.c_int),
+                ("blocks", C.POINTER(C.c_void_p))]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every declaration of include/hermite_b200.h appears here.
@@ -47,6 +58,7 @@ SIGNATURES = {
     "hb_index_list": (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_up, C.c_size_t]),
     "hb_triangle_index": (C.c_int, [c_up, C.c_int, c_up]),
     "hb_cube_index": (C.c_int, [c_up, C.c_int, c_up]),
+    "hb_index_positions": (C.c_int, [C.c_char_p, C.c_int, C.c_int, c_up, C.c_size_t, c_ip]),
     "hb_hermite_eval": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp]),
     "hb_discretize": (C.c_int, [C.c_char_p, C.c_int, c_ip, c_dp, c_dp, c_dp, c_dp, C.c_size_t]),
     "hb_plan_discretize": (C.c_int, [C.c_void_p, C.c_char_p, c_dp, c_dp, C.c_void_p, C.c_void_p]),
@@ -88,6 +100,11 @@ SIGNATURES = {
     "hb_dev_dgemm_scatter": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong,
                                        C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p), C.c_int,
                                        C.c_int, C.c_longlong, C.c_longlong, C.c_void_p]),
+    "hb_dev_dgemm_ex": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hb_dev_parity_pass": (C.c_int, [C.c_int, C.c_int, c_ip, c_ip, c_llp, c_llp, c_llp, C.c_longlong, C.c_longlong,
+                                     C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_plan_parity_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_llp, c_llp, c_llp, c_llp,
+                                       C.c_void_p]),
     "hb_dev_matvec": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hb_dev_varfd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_size_t, C.c_int,
                                C.c_char_p, C.c_void_p, C.c_longlong, C.c_void_p]),

@@ -71,6 +71,18 @@ def iterator_index(mult_ind, index_set="triangle"):
     return int(out.value)
 
 
+def iterator_positions(mult_inds, degree, index_set="triangle"):
+    """Positions of many multi-indices (count x dim) in the enumeration of the set; -1 where absent."""
+    _check_set(index_set)
+    m = np.ascontiguousarray(mult_inds, dtype=np.uint32)
+    if m.ndim != 2:
+        raise ValueError("mult_inds must be a (count, dim) array")
+    out = np.empty(m.shape[0], dtype=np.int32)
+    check(lib().hb_index_positions(index_set.encode(), m.shape[1], int(degree), m.ctypes.data_as(c_up), m.shape[0],
+                                   out.ctypes.data_as(c_ip)))
+    return out
+
+
 def iterator_size(dim, degree, index_set="triangle"):
     _check_set(index_set)
     out = C.c_longlong(0)

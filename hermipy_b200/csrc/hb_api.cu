@@ -201,6 +201,19 @@ int hb_cube_index(const uint32_t* m, int dim, uint32_t* index) {
     return HB_OK;
 }
 
+int hb_index_positions(const char* index_set, int dim, int degree, const uint32_t* m, size_t count, int32_t* pos) {
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    auto s = get_index_set(set, dim, degree);
+    if (!s || (count && (!m || !pos))) { set_error("index_positions: invalid (dim %d, degree %d)", dim, degree); return HB_ERR_INVALID; }
+    for (size_t i = 0; i < count; i++) {
+        bool inside = true;
+        for (int a = 0; a < dim; a++) inside = inside && m[i * dim + a] < s->extent[a];
+        pos[i] = inside ? s->position(m + i * dim) : -1;
+    }
+    return HB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 int hb_hermite_eval(const double* x, int n, int degree, double* out) {
     HB_TRY(check_device());
@@ -908,6 +921,58 @@ int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long l
     g.block_rows = block_rows;
     for (int i = 0; i < n_blocks; i++) g.blocks[i] = blocks[i];
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+int hb_dev_dgemm_ex(const hb_gemm_desc* q, void* stream) {
+    if (!q) return HB_ERR_INVALID;
+    GemmArgs g;
+    g.M = q->M; g.N = q->N; g.K = q->K; g.batch = q->batch; g.batch_lo = q->batch_lo > 0 ? q->batch_lo : 1;
+    g.A = q->A; g.lda = q->lda; g.strideA = q->strideA; g.strideA_lo = q->strideA_lo; g.a_mmajor = q->a_mmajor != 0;
+    g.B = q->B; g.ldb = q->ldb; g.strideB = q->strideB; g.strideB_lo = q->strideB_lo;
+    g.C = q->C; g.ldc = q->ldc; g.strideC = q->strideC; g.strideC_lo = q->strideC_lo;
+    if (q->n_blocks > 0) {
+        const long long last = (long long)q->row_offset + (long long)(g.batch_lo - 1) * q->row_offset_lo + q->M - 1;
+        if (q->n_blocks > 16 || q->block_rows < 1 || !q->blocks || q->row_offset < 0 || q->row_offset_lo < 0 ||
+            last >= (long long)q->n_blocks * q->block_rows) {
+            set_error("hb_dev_dgemm_ex: need 1..16 row blocks covering destination rows 0..%lld", last);
+            return HB_ERR_INVALID;
+        }
+        g.block_rows = q->block_rows; g.row_offset = q->row_offset; g.row_offset_lo = q->row_offset_lo;
+        g.C = q->blocks[0];
+        for (int i = 0; i < q->n_blocks; i++) g.blocks[i] = q->blocks[i];
+    }
+    return gemm_launch(g, static_cast<cudaStream_t>(stream));
+}
+int hb_dev_parity_pass(int merge, int d, const int* n, const int* split, const long long* nat_stride,
+                       const long long* srt_stride, const long long* srt_par, long long batch, long long nat_bstride,
+                       long long srt_bstride, int nat_pad_last, const double* in, double* out, void* stream) {
+    HB_TRY(check_device());
+    if (d < 1 || d > HB_MAX_DIM || !n || !split || !nat_stride || !srt_stride || !srt_par) return HB_ERR_INVALID;
+    ParityNDArgs a;
+    a.d = d;
+    for (int k = 0; k < d; k++) {
+        a.n[k] = n[k]; a.nh[k] = (n[k] + 1) / 2; a.split[k] = split[k] != 0;
+        a.nat_stride[k] = nat_stride[k]; a.srt_stride[k] = srt_stride[k]; a.srt_par[k] = srt_par[k];
+    }
+    a.batch = batch; a.nat_bstride = nat_bstride; a.srt_bstride = srt_bstride; a.nat_pad_last = nat_pad_last;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return merge ? launch_nd_parity_merge(a, in, out, st) : launch_nd_parity_split(a, in, out, st);
+}
+int hb_plan_parity_table(hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
+                         long long* ld, long long* stride, void* stream) {
+    if (axis < 0 || axis >= plan->dim) return HB_ERR_INVALID;
+    Axis& A = plan->ax[axis];
+    if (!A.symmetric_nodes) { set_error("hb_plan_parity_table: axis %d is not a bit-symmetric Hermite axis", axis); return HB_ERR_INVALID; }
+    HB_TRY(ensure_combined_parity_tables(A, static_cast<cudaStream_t>(stream)));
+    const int nh = (A.n + 1) / 2, Pe = (A.P + 1) / 2;
+    const long long nhp = even_up(nh), Pep = even_up(Pe);
+    switch (kind) {
+        case 0: *ptr = A.cW.d(); *rows = nh; *cols = Pe; *ld = Pep; *stride = nh * Pep; break;
+        case 1: *ptr = A.cWT.d(); *rows = Pe; *cols = nh; *ld = nhp; *stride = Pe * nhp; break;
+        case 2: *ptr = A.cPhi.d(); *rows = nh; *cols = Pe; *ld = Pep; *stride = nh * Pep; break;
+        case 3: *ptr = A.cPhiT.d(); *rows = Pe; *cols = nh; *ld = nhp; *stride = Pe * nhp; break;
+        default: return HB_ERR_INVALID;
+    }
+    return HB_OK;
 }
 int hb_dev_matvec(int M, int N, const double* A, long long lda, const double* x, double* y, void* stream) {
     HB_TRY(check_device());

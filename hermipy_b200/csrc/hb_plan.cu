@@ -395,7 +395,7 @@ static int parity_mask(const hb_plan* pl, int batch) {
     return mask;
 }
 
-static int ensure_combined_parity_tables(Axis& A, cudaStream_t st) {
+int ensure_combined_parity_tables(Axis& A, cudaStream_t st) {
     if (A.cpar_tables) return HB_OK;
     const Parity1D d = parity_dims(A);
     const size_t ik = (size_t)d.nh * d.Pep, ki = (size_t)d.Pe * d.nhp;

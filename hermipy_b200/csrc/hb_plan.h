@@ -130,6 +130,7 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
 int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
               long long row_end, cudaStream_t st);
 int ensure_triple_products(hb_plan* pl, cudaStream_t st);
+int ensure_combined_parity_tables(Axis& A, cudaStream_t st);
 // GEMM launch bracketed by events when pl->timing; tag: 1+axis forward, 11+axis backward, 21/22 varf stage 1/2
 int timed_gemm(hb_plan* pl, const GemmArgs& g, int tag, cudaStream_t st);
 void fourier_triple_products_host(int degree, int Pp, std::vector<double>& out);

@@ -231,6 +231,293 @@ class ShardedTransform:
         return graph, c, gout
 
 
+# ------------------------------------------------------------------------------------------------------
+# Parity-split sharded transform: the production path for symmetric (Gauss-Hermite) grids.
+class Gemm:
+    """One launch of the two-level-batch GEMM (hb_gemm_desc of include/hermite_b200.h) on torch tensors:
+    operand X is the flat tensor `X` from element offset `x_off` on.  `blocks` = [(tensor or device address,
+    element offset)] turns the store into the row-block scatter."""
+
+    def __init__(self, M, N, K, A, lda, B, ldb, C=None, ldc=0, a_off=0, b_off=0, c_off=0, batch=1, batch_lo=1,
+                 strideA=0, strideA_lo=0, strideB=0, strideB_lo=0, strideC=0, strideC_lo=0, blocks=None, block_rows=0,
+                 row_offset_lo=0):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+
+class DeviceOps:
+    """The CUDA implementation of the three primitives the sharded transform is composed of."""
+
+    def gemm(self, g):
+        import ctypes as C
+        from ._lib import GemmDesc, check, lib
+        from .plan import _stream
+        ptr = lambda t, off: (t.data_ptr() if hasattr(t, "data_ptr") else int(t)) + 8 * off
+        d = GemmDesc()
+        d.M, d.N, d.K, d.batch, d.batch_lo, d.a_mmajor = g.M, g.N, g.K, g.batch, g.batch_lo, 0
+        d.A, d.lda, d.strideA, d.strideA_lo = ptr(g.A, g.a_off), g.lda, g.strideA, g.strideA_lo
+        d.B, d.ldb, d.strideB, d.strideB_lo = ptr(g.B, g.b_off), g.ldb, g.strideB, g.strideB_lo
+        d.ldc, d.strideC, d.strideC_lo = g.ldc, g.strideC, g.strideC_lo
+        keep = None
+        if g.blocks:
+            keep = (C.c_void_p * len(g.blocks))(*[ptr(t, off) for t, off in g.blocks])
+            d.blocks = C.cast(keep, C.POINTER(C.c_void_p))
+            d.n_blocks, d.block_rows, d.row_offset, d.row_offset_lo = len(g.blocks), g.block_rows, 0, g.row_offset_lo
+            d.C = None
+        else:
+            d.C = ptr(g.C, g.c_off)
+        check(lib().hb_dev_dgemm_ex(C.byref(d), _stream()))
+
+    def parity_pass(self, merge, n, split, nat_stride, srt_stride, srt_par, src, dst, nat_pad_last=0):
+        import ctypes as C
+        from ._lib import c_ip, c_llp, check, lib
+        from .plan import _stream
+        ia = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        la = lambda v: np.ascontiguousarray(v, dtype=np.int64)
+        n_, sp_, ns_, ss_, sq_ = ia(n), ia(split), la(nat_stride), la(srt_stride), la(srt_par)
+        check(lib().hb_dev_parity_pass(int(merge), len(n), n_.ctypes.data_as(c_ip), sp_.ctypes.data_as(c_ip),
+                                       ns_.ctypes.data_as(c_llp), ss_.ctypes.data_as(c_llp), sq_.ctypes.data_as(c_llp),
+                                       1, 0, 0, int(nat_pad_last), src.data_ptr(), dst.data_ptr(), _stream()))
+
+
+def parity_tables(phi, wphi):
+    """Per-parity tables of one symmetric axis from phi[i][k], (w phi)[i][k] (layout only, no arithmetic):
+    cW / cPhi [2][nh][Pep] and cWT / cPhiT [2][Pe][nhp], odd entry zero-padded, as hb_plan_parity_table lays them
+    out.  Used by the CPU (gloo) tests; on the GPU the plan supplies the same tables (plan_parity_tables)."""
+    n, P = phi.shape
+    nh, Pe = (n + 1) // 2, (P + 1) // 2
+    nhp, Pep, lo = even_up(nh), even_up(Pe), n - nh
+    out = {}
+    for name, t in (("cW", wphi), ("cPhi", phi)):
+        a = torch.zeros((2, nh, Pep), dtype=t.dtype, device=t.device)
+        b = torch.zeros((2, Pe, nhp), dtype=t.dtype, device=t.device)
+        for par in range(2):
+            sub = t[lo:, par::2]
+            a[par, :, :sub.shape[1]] = sub
+            b[par, :sub.shape[1], :nh] = sub.t()
+        out[name], out[name + "T"] = a, b
+    return out
+
+
+def plan_parity_tables(plan):
+    """[{cW, cWT, cPhi, cPhiT}] per axis as torch views of the plan's device tables (no copy)."""
+    import ctypes as C
+    from ._lib import check, lib
+    from .plan import _stream
+    res = []
+    for a in range(plan.dim):
+        tabs = {}
+        for kind, name in enumerate(("cW", "cWT", "cPhi", "cPhiT")):
+            ptr, r, c, ld, st = C.c_void_p(), C.c_longlong(0), C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+            check(lib().hb_plan_parity_table(plan._h, a, kind, C.byref(ptr), C.byref(r), C.byref(c), C.byref(ld),
+                                             C.byref(st), _stream()))
+            tabs[name] = _tensor_from_ptr(ptr.value, 2 * r.value, ld.value).reshape(2, r.value, ld.value)
+        res.append(tabs)
+    return res
+
+
+class ShardedParityTransform:
+    """3-D transform on a symmetric (Gauss-Hermite) grid with the OUTER grid axis sharded over the ranks of
+    `group`, every axis contraction split by parity (half the flops), one exchange per direction.
+
+    Ownership.  The parity split pairs node x with -x, so rank r owns a SYMMETRIC pair of half-slabs of axis 0:
+    with nh0 = n0/2 and sh = nh0/g, the nodes n0/2 - (r+1) sh ... n0/2 - r sh - 1 and their mirror images
+    n0/2 + r sh ... n0/2 + (r+1) sh - 1 (`local_x0()` lists them; local array [2 sh][n1][n2 padded to even]).
+    Coefficients stay sharded: the parity-sorted box c[m0'][m1' in slice][m2'] where an index k' of a sorted axis
+    runs over the even basis functions first, then the odd ones, both blocks padded to the same size (`coef_index()`
+    maps the local block to basis indices; pad cells are -1 and hold zeros); the slice of rank r is rows
+    r Ps ... (r+1) Ps - 1 of the sorted axis 1.
+
+    Launch sequence per direction: one parity pass over the local grid values (all three axes at once), three GEMM
+    launches (even and odd halves are the two low-level batch entries of one launch), and the exchange, which is
+    the EPILOGUE of the GEMM that precedes it: that GEMM stores each row block straight into the destination
+    rank's buffer (NVLink peer memory through torch symmetric memory, `exchange="p2p"`, fenced by ONE device
+    barrier), or into a send buffer moved by one all_to_all_single (`exchange="nccl"`, also what the gloo tests
+    run).  All buffers are allocated once, so a round trip is a fixed launch sequence (see `capture`).
+    """
+
+    def __init__(self, n_pts, P, tables, group=None, ops=None, exchange="nccl"):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        assert len(n_pts) == 3 and len(P) == 3, "the parity-split sharded transform is 3-D"
+        self.n, self.P = [int(v) for v in n_pts], [int(v) for v in P]
+        g = self.world
+        assert self.n[0] % 2 == 0 and (self.n[0] // 2) % g == 0, \
+            "outer axis: an even number of nodes whose half divides evenly over the ranks"
+        self.ops = ops if ops is not None else DeviceOps()
+        self.tables = tables
+        t = tables[0]["cW"]
+        self.dev, self.dtype = t.device, t.dtype
+        self.exchange = exchange if g > 1 else "none"
+        n, Pn = self.n, self.P
+        self.nh = [(v + 1) // 2 for v in n]
+        self.Pe = [(v + 1) // 2 for v in Pn]
+        self.nhp = [even_up(v) for v in self.nh]
+        self.Pep = [even_up(v) for v in self.Pe]
+        self.sh = self.nh[0] // g
+        self.n2p = even_up(n[2])
+        self.G1, self.G2 = 2 * self.nh[1], 2 * self.nhp[2]
+        self.C0, self.C1, self.C2 = 2 * self.Pe[0], 2 * self.Pe[1], 2 * self.Pep[2]
+        self.Ps = -(-self.C1 // g)
+        self._bufs, self._symm, self._pending = {}, {}, set()
+
+    # -- layout -----------------------------------------------------------------------------------
+    def local_x0(self):
+        """global indices of the axis-0 nodes this rank owns, in local order"""
+        half, sh, r = self.n[0] // 2, self.sh, self.rank
+        return np.concatenate([np.arange(half - (r + 1) * sh, half - r * sh), np.arange(half + r * sh, half + (r + 1) * sh)])
+
+    def local_grid_shape(self):
+        return (2 * self.sh, self.n[1], self.n2p)
+
+    def local_coef_shape(self):
+        return (self.C0, self.Ps, self.C2)
+
+    def coef_index(self):
+        """(m0, m1, m2): basis index of every row / local slice row / column of the local coefficient block (-1 = pad)"""
+        def sorted_axis(P, blk):
+            out = np.full(2 * blk, -1, dtype=np.int64)
+            out[:(P + 1) // 2] = np.arange(0, P, 2)
+            out[blk:blk + P // 2] = np.arange(1, P, 2)
+            return out
+        m1 = np.full(self.world * self.Ps, -1, dtype=np.int64)
+        m1[:self.C1] = sorted_axis(self.P[1], self.Pe[1])
+        return (sorted_axis(self.P[0], self.Pe[0]), m1[self.rank * self.Ps:(self.rank + 1) * self.Ps],
+                sorted_axis(self.P[2], self.Pep[2]))
+
+    def _buf(self, name, size):
+        if name not in self._bufs:
+            self._bufs[name] = torch.zeros(size, dtype=self.dtype, device=self.dev)
+        return self._bufs[name]
+
+    def _symm_buf(self, name, size):
+        if name not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(size, dtype=self.dtype, device=self.dev)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self._symm[name] = (t, hdl)
+        return self._symm[name]
+
+    def _parity_args(self):
+        sh, n, S1 = self.sh, self.n, self.G1 * self.G2
+        return dict(n=[2 * sh, n[1], n[2]], split=[1, 1, 1], nat_stride=[n[1] * self.n2p, self.n2p, 1],
+                    # axis 0 interleaves parity and h ([h0][p0]) so that (h0, p0) is ONE uniformly strided batch index
+                    srt_stride=[2 * S1, self.G2, 1], srt_par=[S1, self.nh[1] * self.G2, self.nhp[2]])
+
+    # -- exchange fences (p2p) -----------------------------------------------------------------------
+    # A peer buffer may be overwritten once every rank has finished reading its previous contents.  Any barrier
+    # passed since those reads guarantees that (ranks run the same launch sequence in stream order), so a round
+    # trip needs ONE barrier per direction -- the one that publishes the stores -- and a second one only when the
+    # same direction runs twice in a row.
+    def _before_scatter(self, name, hdl):
+        if name in self._pending:
+            hdl.barrier(channel=0)
+            self._pending.clear()
+
+    def _after_scatter(self, name, hdl):
+        hdl.barrier(channel=1)
+        self._pending.clear()
+        self._pending.add(name)     # about to be read locally
+
+    # -- forward ----------------------------------------------------------------------------------
+    def forward(self, f):
+        g, r, sh, Ps, ops, T = self.world, self.rank, self.sh, self.Ps, self.ops, self.tables
+        nh, nhp, Pe, Pep, G1, G2, C2 = self.nh, self.nhp, self.Pe, self.Pep, self.G1, self.G2, self.C2
+        X0 = 2 * sh
+        fs = self._buf("fs", X0 * G1 * G2)
+        ops.parity_pass(0, src=f, dst=fs, **self._parity_args())
+        # axis 2: t1[(X0, X1)][p2 Pep2 + m'] = sum_h fs[(X0, X1)][p2 nhp2 + h] cW2[p2][h][m']
+        t1 = self._buf("t1", X0 * G1 * C2)
+        ops.gemm(Gemm(X0 * G1, Pe[2], nh[2], fs, G2, T[2]["cW"], Pep[2], t1, C2, batch_lo=2, strideA_lo=nhp[2],
+                      strideB_lo=nh[2] * Pep[2], strideC_lo=Pep[2]))
+        # axis 1 + exchange: sorted row m1' = p1 Pe1 + j of batch entry X0 = (h0l, p0) goes to rank m1' // Ps, which
+        # receives R[h0 = src sh + h0l][p0][m1' % Ps][C2]
+        blk = sh * 2 * Ps * C2
+        if self.exchange == "p2p":
+            recv, hdl = self._symm_buf("F", g * blk)
+            self._before_scatter("F", hdl)
+            blocks = [(int(hdl.buffer_ptrs[q]), r * blk) for q in range(g)]
+        else:
+            send = self._buf("F_send", g * blk)
+            blocks = [(send, q * blk) for q in range(g)]
+        ops.gemm(Gemm(Pe[1], C2, nh[1], T[1]["cWT"], nhp[1], t1, C2, ldc=C2, batch=X0, batch_lo=2,
+                      strideA_lo=Pe[1] * nhp[1], strideB=G1 * C2, strideB_lo=nh[1] * C2, strideC=Ps * C2,
+                      blocks=blocks, block_rows=Ps, row_offset_lo=Pe[1]))
+        if self.exchange == "p2p":
+            self._after_scatter("F", hdl)
+        elif self.exchange == "nccl":
+            recv = self._buf("F_recv", g * blk)
+            dist.all_to_all_single(recv, send, group=self.group)
+        else:
+            recv = send
+        # axis 0: c[p0 Pe0 + m'][Ps C2] = sum_h0 cWT0[p0][m'][h0] R[h0][p0][Ps C2]
+        cols = Ps * C2
+        c = self._buf("coef", self.C0 * cols)
+        ops.gemm(Gemm(Pe[0], cols, nh[0], T[0]["cWT"], nhp[0], recv, 2 * cols, c, cols, batch_lo=2,
+                      strideA_lo=Pe[0] * nhp[0], strideB_lo=cols, strideC_lo=Pe[0] * cols))
+        return c.view(self.C0, Ps, C2)
+
+    # -- backward ---------------------------------------------------------------------------------
+    def backward(self, c):
+        g, r, sh, Ps, ops, T = self.world, self.rank, self.sh, self.Ps, self.ops, self.tables
+        nh, nhp, Pe, Pep, G1, G2, C2 = self.nh, self.nhp, self.Pe, self.Pep, self.G1, self.G2, self.C2
+        X0, cols = 2 * sh, Ps * C2
+        c = c.reshape(-1)
+        # axis 0 + exchange: row h0 of parity p0 goes to rank h0 // sh, next to the slices of the other ranks:
+        # Y[h0l][p0][m1' = src Ps + j][C2]
+        if self.exchange == "p2p":
+            Y, hdl = self._symm_buf("B", X0 * g * cols)
+            self._before_scatter("B", hdl)
+            blocks = [(int(hdl.buffer_ptrs[q]), r * cols) for q in range(g)]
+            ldc, lo_stride = 2 * g * cols, g * cols
+        else:
+            send = self._buf("B_send", g * X0 * cols)
+            blocks = [(send, q * X0 * cols) for q in range(g)]
+            ldc, lo_stride = 2 * cols, cols
+        ops.gemm(Gemm(nh[0], cols, Pe[0], T[0]["cPhi"], Pep[0], c, cols, ldc=ldc, batch_lo=2,
+                      strideA_lo=nh[0] * Pep[0], strideB_lo=Pe[0] * cols, strideC_lo=lo_stride, blocks=blocks,
+                      block_rows=sh))
+        if self.exchange == "p2p":
+            self._after_scatter("B", hdl)
+        else:
+            if self.exchange == "nccl":
+                recv = self._buf("B_recv", g * X0 * cols)
+                dist.all_to_all_single(recv, send, group=self.group)
+            else:
+                recv = send
+            Y = self._buf("B_Y", X0 * g * cols)
+            Y.view(X0, g, cols).copy_(recv.view(g, X0, cols).permute(1, 0, 2))
+        # axis 1: u[X0][p1 nh1 + h][C2] = sum_m' cPhi1[p1][h][m'] Y[X0][p1 Pe1 + m'][C2]
+        u = self._buf("u", X0 * G1 * C2)
+        ops.gemm(Gemm(nh[1], C2, Pe[1], T[1]["cPhi"], Pep[1], Y, C2, u, C2, batch=X0, batch_lo=2,
+                      strideA_lo=nh[1] * Pep[1], strideB=g * cols, strideB_lo=Pe[1] * C2, strideC=G1 * C2,
+                      strideC_lo=nh[1] * C2))
+        # axis 2: v[(X0, X1)][p2 nhp2 + h] = sum_m' u[(X0, X1)][p2 Pep2 + m'] cPhiT2[p2][m'][h]
+        v = self._buf("v", X0 * G1 * G2)
+        ops.gemm(Gemm(X0 * G1, nh[2], Pe[2], u, C2, T[2]["cPhiT"], nhp[2], v, G2, batch_lo=2, strideA_lo=Pep[2],
+                      strideB_lo=Pe[2] * nhp[2], strideC_lo=nhp[2]))
+        out = self._buf("grid", X0 * self.n[1] * self.n2p)
+        ops.parity_pass(1, src=v, dst=out, nat_pad_last=self.n2p, **self._parity_args())
+        return out.view(X0, self.n[1], self.n2p)
+
+    def capture(self, f):
+        """Warm up (allocates every buffer), then capture forward(f) -> backward as one CUDA graph.
+        Returns (graph, coefficient tensor, grid tensor); graph.replay() re-runs the launch sequence."""
+        for _ in range(2):
+            c = self.forward(f)
+            gout = self.backward(c)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(self.group)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            c = self.forward(f)
+            gout = self.backward(c)
+        return graph, c, gout
+
+
 def plan_tables_as_tensors(plan):
     """Views of a Plan's per-axis device tables as torch CUDA tensors [(phi, w_phi)] (no copy)."""
     out = []

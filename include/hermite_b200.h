@@ -48,6 +48,9 @@ int hb_index_get_degree(const char* index_set, int dim, long long n_polys, int* 
 int hb_index_list(const char* index_set, int dim, int degree, uint32_t* out, size_t out_capacity /* entries */);
 int hb_triangle_index(const uint32_t* m, int dim, uint32_t* index);
 int hb_cube_index(const uint32_t* m, int dim, uint32_t* index);
+/* positions of `count` multi-indices (count x dim, row-major) in the enumeration of the set; -1 where the
+ * multi-index is not in the set (the reference looks one up at a time in its hash map, lib.cpp:76-84) */
+int hb_index_positions(const char* index_set, int dim, int degree, const uint32_t* m, size_t count, int32_t* pos);
 
 /* ---- Hermite functions by three-term recurrence ---------------------------------------------------
  * reference: hermite_eval (hermite.cpp:29-41).  out[i*(degree+1) + k] = He_k(x_i)/sqrt(k!). */
@@ -159,6 +162,35 @@ int hb_dev_dgemm(int M, int N, int K, int batch, const double* A, long long lda,
 int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long long lda, long long strideA,
                          int a_mmajor, const double* B, long long ldb, long long strideB, double* const* blocks,
                          int n_blocks, int block_rows, long long ldc, long long strideC, void* cuda_stream);
+/* The general form of the two calls above.  Two-level batch: batch * batch_lo GEMMs, entry (b_hi, b_lo) uses
+ * A + b_hi*strideA + b_lo*strideA_lo (likewise B, C); a stride of 0 shares the operand at that level.  The low
+ * level is how a parity-split transform stage runs its even and odd halves in one launch.  With n_blocks > 0 the
+ * output row r of entry (b_hi, b_lo) goes to destination row  d = row_offset + b_lo*row_offset_lo + r,  stored at
+ * blocks[d / block_rows] + (d % block_rows)*ldc + b_hi*strideC + b_lo*strideC_lo  (C is ignored). */
+typedef struct hb_gemm_desc {
+    int M, N, K, batch, batch_lo, a_mmajor;
+    const double* A; long long lda, strideA, strideA_lo;
+    const double* B; long long ldb, strideB, strideB_lo;
+    double* C;       long long ldc, strideC, strideC_lo;
+    int n_blocks, block_rows, row_offset, row_offset_lo;
+    double* const* blocks;
+} hb_gemm_desc;
+int hb_dev_dgemm_ex(const hb_gemm_desc* desc, void* cuda_stream);
+/* Parity split (merge = 0) / merge (merge = 1) of a d-dimensional grid function along up to three axes in one pass
+ * (reference: none -- the sum-factorised transform on a symmetric node set contracts even and odd parts
+ * separately).  Natural array: axis a has n[a] entries nat_stride[a] apart.  Sorted array: a split
+ * axis is indexed by (parity p, h), h < ceil(n[a]/2) counting the nodes x = n[a] - ceil(n[a]/2) + h, stored at
+ * h*srt_stride[a] + p*srt_par[a]; other axes keep their index.  nat_pad_last: the merge zero-fills the natural
+ * rows from n[d-1] up to this pitch. */
+int hb_dev_parity_pass(int merge, int d, const int* n, const int* split, const long long* nat_stride,
+                       const long long* srt_stride, const long long* srt_par, long long batch, long long nat_bstride,
+                       long long srt_bstride, int nat_pad_last, const double* in, double* out, void* cuda_stream);
+/* per-parity basis tables of a (symmetric, non-Fourier) axis, both parities in one buffer `stride` doubles apart,
+ * the odd entry zero-padded to the shape of the even one; nh = ceil(n/2) non-negative nodes, Pe = ceil(P/2):
+ * kind 0: w*phi [h][k'] (nh x Pe), 1: w*phi [k'][h] (Pe x nh), 2: phi [h][k'], 3: phi [k'][h].
+ * Returns HB_ERR_INVALID for an axis whose nodes / weights are not bit-symmetric. */
+int hb_plan_parity_table(hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
+                         long long* ld, long long* stride, void* cuda_stream);
 /* consumers of an assembled matrix that stays in HBM (reference: hermipy/varf.py:127-134 `Varf.__call__`,
  * the only contact the Krylov solvers of varf.py:170-237 have with the matrix): y = A x, A row-major M x N
  * with leading dimension lda (any parity), x and y device vectors.  HBM-bound, deterministic summation. */

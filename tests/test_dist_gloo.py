@@ -83,6 +83,68 @@ def test_sharded_3d_transform_world2():
         assert err_c < 1e-13 and pad == 0.0 and err_g < 1e-12, (rank, result[rank])
 
 
+# ---- the parity-split sharded transform (the production path on Gauss-Hermite grids) ----------------------------
+PN_PTS, PP = [8, 5, 6], [4, 5, 3]
+
+
+def _parity_worker(rank, world, port_no, f_all, c_ref, g_ref, result):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dist_cpu_ops import CpuOps
+        from hermipy_b200.dist import ShardedParityTransform, parity_tables
+        rules = [gauss_hermite(n) for n in PN_PTS]
+        tables = []
+        for (x, w), p in zip(rules, PP):
+            x, w = (x - x[::-1]) / 2, (w + w[::-1]) / 2
+            phi = port.hermite_eval(x, p - 1)
+            tables.append(parity_tables(torch.from_numpy(phi.copy()), torch.from_numpy(phi * w[:, None])))
+        T = ShardedParityTransform(PN_PTS, PP, tables, ops=CpuOps())
+        x0 = T.local_x0()
+        f = np.zeros(T.local_grid_shape())
+        f[..., :PN_PTS[2]] = f_all[x0]
+        errs = []
+        for _ in range(2):                       # twice: buffers are reused
+            c = T.forward(torch.from_numpy(f.copy()).reshape(-1)).numpy().copy()
+            m0, m1, m2 = T.coef_index()
+            want = np.where((m0[:, None, None] >= 0) & (m1[None, :, None] >= 0) & (m2[None, None, :] >= 0),
+                            c_ref[np.maximum(m0, 0)[:, None, None], np.maximum(m1, 0)[None, :, None], np.maximum(m2, 0)[None, None, :]], 0.0)
+            err_c = np.abs(c - want).max()
+            g = T.backward(torch.from_numpy(c)).numpy()
+            err_g = np.abs(g[..., :PN_PTS[2]] - g_ref[x0]).max()
+            pad = np.abs(g[..., PN_PTS[2]:]).max() if g.shape[-1] > PN_PTS[2] else 0.0
+            errs.append((float(err_c), float(err_g), float(pad)))
+        result[rank] = errs
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_sharded_parity_transform(world):
+    """Outer-axis sharded, parity-split 3-D transform: ownership of symmetric half-slabs, the parity-sorted sharded
+    coefficient box, block scatter + all-to-all, against the sum-factorised oracle restatement."""
+    rng = np.random.default_rng(7)
+    f = rng.standard_normal(PN_PTS)
+    rules = [gauss_hermite(n) for n in PN_PTS]
+    nodes = [(r[0] - r[0][::-1]) / 2 for r in rules]
+    weights = [(r[1] + r[1][::-1]) / 2 for r in rules]
+    deg = [p - 1 for p in PP]
+    c_ref = port.transform_sumfac(deg, f[None], nodes, weights, True)[0]
+    g_ref = port.transform_sumfac(deg, c_ref[None], nodes, weights, False)[0]
+    result = mp.get_context("spawn").Manager().dict()
+    if world == 1:
+        _parity_worker(0, 1, 0, f, c_ref, g_ref, result)
+    else:
+        mp.spawn(_parity_worker, args=(world, _free_port(), f, c_ref, g_ref, result), nprocs=world, join=True)
+    assert len(result) == world
+    for rank in range(world):
+        for err_c, err_g, pad in result[rank]:
+            assert err_c < 1e-13 and err_g < 1e-12 and pad == 0.0, (rank, result[rank])
+
+
 def test_sumfac_comparator_matches_reference_order_port():
     """The 'fair CPU' sum-factorised restatement equals the naive-loop restatement on a cube set."""
     rng = np.random.default_rng(6)
