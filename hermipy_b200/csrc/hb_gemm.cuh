@@ -257,6 +257,17 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         b_off[nj] = A_BYTES + (jn >> 1) * 2048 + t * 128 + ((((n_in >> 1) ^ t)) << 4) + (n_in & 1) * 8;
     }
 
+    // Releasing a stage.  The fragment loads (generic proxy, LDS) of a k-tile must have COMPLETED before the producer
+    // may let the TMA engine (async proxy) overwrite the stage.  An mbarrier.arrive placed right behind the k-tile
+    // does not guarantee that: nothing ties it to the DMMAs that consume the loaded registers, and ptxas schedules it
+    // above them -- measured as a few wrong operand elements per ~1e8 in the last k-steps of a tile whenever the
+    // producer was fast enough (the 4-consumer-warp configurations with 2 CTAs per SM).  The release of stage
+    // it - 1 is therefore issued behind the full-barrier WAIT of k-tile `it`: the spin loop is a scheduling boundary,
+    // every DMMA of k-tile it - 1 has been issued before it, and a DMMA only issues once its operand loads have
+    // returned.  In steady state the data of k-tile `it` is already there, so the stage is handed back as early as
+    // before; the last stage of a tile is released when the next tile starts (the producer has STAGES - 1 stages to
+    // prefetch into during the epilogue), and never after the last tile (nobody waits for it).
+    int pending_release = -1;
     int it = 0;   // k-tiles consumed so far by this CTA, over all of its tiles
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     int b_lo, b_hi, m_base, n_base;
@@ -272,6 +283,11 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     for (int kt = 0; kt < KT; kt++, it++) {
         const int s = it % STAGES;
         mbar_wait(bar_base + 8 * s, (it / STAGES) & 1);
+        if (pending_release >= 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + pending_release));
+        }
+        pending_release = s;
         if (kt == 0 && first_tile && threadIdx.x == 0) gemm_trace(p.trace, 1);   // [2] first operands landed
         const uint8_t* st = smem_gen + s * STAGE_BYTES;
 #pragma unroll
@@ -297,8 +313,6 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
                 for (int nj = 0; nj < NJ; nj++)
                     if (!RAGGED || nj < NJ - 1 || nj_full) dmma_8x8x4(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
     }
 
     // ---------------- epilogue ----------------

@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(384, 1)
         __threadfence_block();
         st_volatile(flags + 8 + g, 1);
     }
-    int it = 0, n_done = 0;
+    // a stage is released behind the full-barrier wait of the NEXT k-tile, never right behind its own DMMAs: see the
+    // comment on `pending_release` in hb_gemm.cuh (LDS of the stage must have completed before the TMA overwrites it)
+    int it = 0, n_done = 0, pending_release = -1;
     for (int n = 0;; n++) {
         group_sync(g);                                          // slot n & 1 is published; slot (n+1) & 1 is free
         const int ti = ld_volatile(flags + 4 + 2 * g + (n & 1));
@@ -211,6 +213,11 @@ __global__ void __launch_bounds__(384, 1)
             const int s = it % PP_STAGES;
             if (kt == KT / 2 && gt == 0) st_volatile(flags + 1 + g, 2 * n_done + 1);
             mbar_wait(full0 + 8 * s, (it / PP_STAGES) & 1);
+            if (pending_release >= 0) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * pending_release);
+            }
+            pending_release = s;
             const uint8_t* st = ring_gen + s * PP_STAGE_BYTES;
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
@@ -226,8 +233,6 @@ __global__ void __launch_bounds__(384, 1)
 #pragma unroll
                     for (int nj = 0; nj < NJ; nj++) dmma_8x8x4(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
         }
 
         // ---- hand the pipe over, then scatter ----

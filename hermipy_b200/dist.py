@@ -14,6 +14,8 @@ The host-side logic (partitioning, layouts, the exchange) also runs on CPU tenso
 backend so that it can be tested without GPUs: the tests inject a CPU stand-in for the GEMM (`gemm=`, defined
 in tests/test_dist_gloo.py); the package itself ships no CPU arithmetic.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -116,8 +118,10 @@ class ShardedTransform:
         return (self.P[0], self.Ps, *self.P[2:-1], self.Pp_last)
 
     # -- the exchange (grid axis 0 <-> coefficient axis 1) -------------------------------------------
-    def _peer_ptrs(self, hdl, byte_offset):
-        return [int(hdl.buffer_ptrs[r]) + byte_offset for r in range(self.world)]
+    def _peer_ptrs(self, hdl, byte_offset, t=None):
+        # a handle may describe a larger allocation that several tensors were carved from: offset of `t` in it
+        base = 0 if t is None else t.data_ptr() - int(hdl.buffer_ptrs[self.rank])
+        return [int(hdl.buffer_ptrs[r]) + base + byte_offset for r in range(self.world)]
 
     @staticmethod
     def _clip(block, A):
@@ -139,7 +143,7 @@ class ShardedTransform:
             from .plan import dgemm_scatter
             recv, hdl = self._symm_buf("fwd", g, s, Ps, rest)
             hdl.barrier(channel=0)               # every rank has finished reading its previous contents
-            blocks = self._peer_ptrs(hdl, self.rank * s * Ps * rest * 8)
+            blocks = self._peer_ptrs(hdl, self.rank * s * Ps * rest * 8, recv)
             A = self.wphiT[1]
             dgemm_scatter(self.P[1], rest, self.n_pts[1], A, A.stride(0), cur2, rest, blocks, Ps, rest, batch=s,
                           strideA=0, strideB=cur2.stride(0), strideC=Ps * rest)
@@ -192,7 +196,7 @@ class ShardedTransform:
             from .plan import dgemm_scatter
             Y, hdl = self._symm_buf("bwd", s, g * Ps, rest)
             hdl.barrier(channel=0)
-            blocks = self._peer_ptrs(hdl, self.rank * cols * 8)
+            blocks = self._peer_ptrs(hdl, self.rank * cols * 8, Y)
             A = self.phi[0]
             dgemm_scatter(self.n_pts[0], cols, self.P[0], A, A.stride(0), c2, c2.stride(0), blocks, s, g * cols)
             hdl.barrier(channel=1)
@@ -349,7 +353,7 @@ class ShardedParityTransform:
         self.tables = tables
         t = tables[0]["cW"]
         self.dev, self.dtype = t.device, t.dtype
-        self.exchange = exchange if g > 1 else "none"
+        self.exchange = exchange if (g > 1 or (exchange == "p2p" and dist.is_initialized())) else "none"
         n, Pn = self.n, self.P
         self.nh = [(v + 1) // 2 for v in n]
         self.Pe = [(v + 1) // 2 for v in Pn]
@@ -361,6 +365,7 @@ class ShardedParityTransform:
         self.C0, self.C1, self.C2 = 2 * self.Pe[0], 2 * self.Pe[1], 2 * self.Pep[2]
         self.Ps = -(-self.C1 // g)
         self._bufs, self._symm, self._pending = {}, {}, set()
+        self.always_fence = bool(int(os.environ.get("HB_DIST_ALWAYS_FENCE", "0")))   # developer switch
 
     # -- layout -----------------------------------------------------------------------------------
     def local_x0(self):
@@ -397,8 +402,14 @@ class ShardedParityTransform:
             t = symm_mem.empty(size, dtype=self.dtype, device=self.dev)
             t.zero_()
             hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            hdl.barrier(channel=0)     # no peer may store into this buffer before its owner's zero-fill has run
             self._symm[name] = (t, hdl)
         return self._symm[name]
+
+    def _peer_ptr(self, t, hdl, q):
+        """address of rank q's copy of the symmetric tensor `t` (a handle may describe a larger allocation that
+        several tensors were carved from: `buffer_ptrs` are then the block bases, not the tensors)"""
+        return int(hdl.buffer_ptrs[q]) + (t.data_ptr() - int(hdl.buffer_ptrs[self.rank]))
 
     def _parity_args(self):
         sh, n, S1 = self.sh, self.n, self.G1 * self.G2
@@ -412,7 +423,7 @@ class ShardedParityTransform:
     # trip needs ONE barrier per direction -- the one that publishes the stores -- and a second one only when the
     # same direction runs twice in a row.
     def _before_scatter(self, name, hdl):
-        if name in self._pending:
+        if name in self._pending or self.always_fence:
             hdl.barrier(channel=0)
             self._pending.clear()
 
@@ -438,7 +449,7 @@ class ShardedParityTransform:
         if self.exchange == "p2p":
             recv, hdl = self._symm_buf("F", g * blk)
             self._before_scatter("F", hdl)
-            blocks = [(int(hdl.buffer_ptrs[q]), r * blk) for q in range(g)]
+            blocks = [(self._peer_ptr(recv, hdl, q), r * blk) for q in range(g)]
         else:
             send = self._buf("F_send", g * blk)
             blocks = [(send, q * blk) for q in range(g)]
@@ -470,7 +481,7 @@ class ShardedParityTransform:
         if self.exchange == "p2p":
             Y, hdl = self._symm_buf("B", X0 * g * cols)
             self._before_scatter("B", hdl)
-            blocks = [(int(hdl.buffer_ptrs[q]), r * cols) for q in range(g)]
+            blocks = [(self._peer_ptr(Y, hdl, q), r * cols) for q in range(g)]
             ldc, lo_stride = 2 * g * cols, g * cols
         else:
             send = self._buf("B_send", g * X0 * cols)

@@ -1,5 +1,10 @@
-"""Parity at the full sizes of the BASELINE.json configs the oracle cannot run whole:
+"""Parity at the full sizes of the BASELINE.json configs:
 
+  C2  2-D transform, degree 200 per axis on the 401 x 401 grid, cube and triangle sets, forward and inverse, against
+      the compiled reference (its naive loop cut into row slabs over all host cores, tests/ref_pool.py) and against
+      the sum-factorised NumPy restatement.
+  C4  3-D transform: 32^3 nodes / degree 31 against the compiled reference; 256^3 / degree 255 (the bench size)
+      against the sum-factorised restatement, forward and inverse.
   C3  2-D varf, degree 400 per axis (triangle set: 80 601 x 80 601, 52 GB): the owned-row API computes the
       leading rows only; their leading block is the whole degree-40 matrix (the graded enumeration is nested),
       which the compiled reference produces in seconds; the rest of those rows is checked through the agreement
@@ -10,7 +15,7 @@ import numpy as np
 import pytest
 import scipy.special as sp
 
-from conftest import rel_err
+from conftest import gauss_hermite, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -93,3 +98,121 @@ def test_c5_batched_1d_degree_1000_rows_vs_reference(ref):
     got_c = plan.forward(plan.pack_grid(want_g)).cpu().numpy()[:, :1001]
     for k in range(len(rows)):
         assert rel_err(got_c[k], ref.transform(1000, want_g[k], [x], [w], True)) <= 1e-12
+
+
+def test_c3_varf_degree_400_whole_matrix(ref):
+    """The bench's C3 case at full size: the 80 601 x 80 601 (52 GB) triangle matrix of the dense f is assembled ONCE
+    (Gram form) and 64 entries drawn over the WHOLE matrix -- offsets beyond 2^32 doubles included -- are compared
+    with 80-bit quadrature sums; the LAST 600 rows (owned-row API) of the polynomial case agree between the
+    reference algebra (path P) and the Gram form."""
+    import torch
+    from hermipy_b200.plan import Plan
+    free = torch.cuda.mem_get_info()[0]
+    if free < 70e9:
+        pytest.skip("needs ~60 GB of free device memory (%.0f GB free)" % (free * 1e-9))
+    x, w = sp.roots_hermitenorm(801)
+    w = w / np.sqrt(2 * np.pi)
+    keep = w > 0
+    x, w = x[keep], w[keep]
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    V = bistable(X, Y)
+    E = np.exp(-3 * V / 10)
+    plan = Plan(400, [x, x], [w, w], index_set="triangle")
+    npol = plan.n_polys
+    A = torch.empty((npol, npol), dtype=torch.float64, device="cuda")
+    plan.varf(plan.pack_grid(E[None])[0], "gram", A)
+    torch.cuda.synchronize()
+    xl, wl = x.astype(np.longdouble), w.astype(np.longdouble)
+    phi = np.zeros((len(x), 401), dtype=np.longdouble)
+    phi[:, 0], phi[:, 1] = 1, xl
+    for k in range(1, 400):
+        phi[:, k + 1] = (xl * phi[:, k] - np.sqrt(np.longdouble(k)) * phi[:, k - 1]) / np.sqrt(np.longdouble(k + 1))
+    idx = np.array([(m0, g - m0) for g in range(401) for m0 in range(g + 1)])     # triangle order: graded, m0 ascending
+    rng = np.random.default_rng(33)
+    El = E.astype(np.longdouble)
+    rows = np.concatenate([rng.integers(0, npol, 48), rng.integers(npol - 2000, npol, 16)])
+    cols = np.concatenate([rng.integers(0, npol, 48), rng.integers(npol - 2000, npol, 16)])
+    assert (rows.astype(np.int64) * npol + cols).max() > 2 ** 32
+    got = A[torch.from_numpy(rows).cuda(), torch.from_numpy(cols).cuda()].cpu().numpy()
+    scale = float(A[:4096, :4096].abs().max().item())
+    for r, c, v in zip(rows, cols, got):
+        (m0, m1), (n0, n1) = idx[r], idx[c]
+        exact = float((wl * phi[:, m0] * phi[:, n0]) @ El @ (wl * phi[:, m1] * phi[:, n1]))
+        assert abs(v - exact) <= 1e-11 * max(1.0, scale), (r, c, v, exact)
+    # symmetric to the last bit, everywhere (checked on strided samples of the whole matrix)
+    probe = torch.arange(0, npol, 97, device="cuda")
+    sub = A[probe][:, probe]
+    assert torch.equal(sub, sub.T)
+    del A, sub
+    torch.cuda.empty_cache()
+    fV = plan.pack_grid(V[None])[0]
+    lo = npol - 600
+    P = plan.varf(fV, "reference", row_begin=lo, row_end=npol).cpu().numpy()
+    Q = plan.varf(fV, "gram", row_begin=lo, row_end=npol).cpu().numpy()
+    assert np.isfinite(P).all() and rel_err(Q, P) <= 1e-12
+    # zero pattern of the reference algebra: a degree-4 polynomial couples |m - n|_1 <= 4 only
+    nz = np.argwhere(P != 0)
+    assert np.abs(idx[lo + nz[:, 0]] - idx[nz[:, 1]]).sum(axis=1).max() <= 4
+
+
+@pytest.mark.parametrize("index_set", ["cube", "triangle"])
+def test_c2_full_size_transform_vs_reference(ref, core, index_set):
+    """BASELINE configs[1] at its real size (n = 401 per axis, degree 200), both directions, against the compiled
+    reference on all host cores and (cube) against the sum-factorised restatement."""
+    from oracle import port
+    from ref_pool import reference_transform_slabs
+    x, w = gauss_hermite(401)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    f = np.exp(-(X ** 2 + X * Y + Y ** 2) / 10)
+    c = core.transform(200, f, [x, x], [w, w], True, index_set=index_set)
+    c_ref = reference_transform_slabs(200, f, [x, x], [w, w], True, index_set)
+    assert c.shape == c_ref.shape and rel_err(c, c_ref) < 1e-12
+    back = core.transform(200, c_ref, [x, x], [w, w], False, index_set=index_set).reshape(401, 401)
+    back_ref = reference_transform_slabs(200, c_ref, [x, x], [w, w], False, index_set)
+    sw = np.sqrt(np.outer(w, w))                                      # discrete L2(w) norm, as in test_gpu_parity
+    assert rel_err(back * sw, back_ref * sw) < 1e-12
+    if index_set == "cube":
+        lex = port.transform_sumfac([200, 200], f[None], [x, x], [w, w], True)[0]
+        ind = core.iterator_list_indices(2, 200, "cube")
+        assert rel_err(c, lex[ind[:, 0], ind[:, 1]]) < 1e-12
+
+
+def test_c4_3d_transform_vs_reference_and_full_size(ref, core):
+    """BASELINE configs[3]: 32^3 nodes, degree 31 (cube) against the compiled reference; the bench size 256^3,
+    degree 255, against the sum-factorised restatement -- forward (all 16.8 M coefficients) and inverse."""
+    import torch
+    from hermipy_b200.plan import Plan
+    from oracle import port
+    from ref_pool import reference_transform_slabs
+    x, w = gauss_hermite(32)
+    X = np.meshgrid(x, x, x, indexing="ij")
+    f = sum(np.exp(-((X[0] - a) ** 2 + (X[1] - b) ** 2 + (X[2] - c) ** 2) / 6) for a, b, c in [(0, 0, 0), (1, -1, .5), (-2, .3, 1)])
+    c = core.transform(31, f, [x] * 3, [w] * 3, True, index_set="cube")
+    c_ref = reference_transform_slabs(31, f, [x] * 3, [w] * 3, True, "cube", rows_per_slab=1)
+    assert rel_err(c, c_ref) < 1e-12
+    back = core.transform(31, c_ref, [x] * 3, [w] * 3, False, index_set="cube").reshape(32, 32, 32)
+    back_ref = reference_transform_slabs(31, c_ref, [x] * 3, [w] * 3, False, "cube", rows_per_slab=1)
+    sw = np.sqrt(np.einsum("i,j,k->ijk", w, w, w))
+    assert rel_err(back * sw, back_ref * sw) < 1e-12
+    # full size: 32 Gaussians (SURVEY 8d), sum-factorised comparator
+    n = 256
+    x, w = gauss_hermite(n)
+    rng = np.random.default_rng(4)
+    f = np.zeros((n, n, n))
+    for _ in range(32):
+        a, b, cc = rng.uniform(-3, 3, 3)
+        s0 = rng.uniform(4, 12)
+        f += rng.standard_normal() * np.einsum("i,j,k->ijk", np.exp(-(x - a) ** 2 / s0), np.exp(-(x - b) ** 2 / s0), np.exp(-(x - cc) ** 2 / s0))
+    plan = Plan(n - 1, [x] * 3, [w] * 3, index_set="cube")
+    ft = plan.pack_grid(f[None])
+    ct = plan.forward(ft)
+    lex = port.transform_sumfac([n - 1] * 3, f[None], [x] * 3, [w] * 3, True)[0]
+    # set order -> lexicographic box through the library's own position map (bit-exact vs the reference, test_abi)
+    M = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 3)
+    pos = core.iterator_positions(M, n - 1, "cube")
+    got = ct[0, :plan.n_polys].cpu().numpy()[pos].reshape(n, n, n)
+    assert rel_err(got, lex) < 1e-12
+    gt = plan.unpack_grid(plan.backward(ct))[0]
+    back = port.transform_sumfac([n - 1] * 3, lex[None], [x] * 3, [w] * 3, False)[0]
+    sw = np.sqrt(np.einsum("i,j,k->ijk", w, w, w))
+    assert rel_err(gt * sw, back * sw) < 1e-12

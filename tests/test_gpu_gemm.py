@@ -79,3 +79,56 @@ def test_alignment_is_checked():
     C = torch.zeros((8, 8), dtype=torch.float64, device="cuda")
     with pytest.raises(HermiteB200Error):
         dgemm(8, 8, 7, A, 7, B, 8, C, 8)
+
+
+@pytest.mark.parametrize("cfg", list(range(N_CFGS)))
+def test_stage_release_waits_for_fragment_loads(cfg):
+    """Regression: short K (few k-tiles per tile), many tiles per CTA, repeated launches.  A stage of the TMA ring
+    must not be handed back to the producer before the fragment loads of its k-tile have completed; when it was
+    (mbarrier.arrive scheduled above the DMMAs consuming the loads), the 4-consumer-warp configurations returned a
+    handful of wrong entries in some launches -- every launch is checked, entry by entry."""
+    import torch
+    from hermipy_b200.plan import dgemm
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for (M, N, K, batch) in [(128, 256, 128, 512), (128, 4096, 128, 6)]:
+        A = torch.randn((batch, M, K), generator=g, dtype=torch.float64, device="cuda")
+        B = torch.randn((batch, K, N), generator=g, dtype=torch.float64, device="cuda")
+        want = torch.matmul(A, B)
+        os.environ["HB_GEMM_CFG"] = str(cfg)
+        try:
+            for rep in range(6):
+                C = torch.full((batch, M, N), float("nan"), dtype=torch.float64, device="cuda")
+                dgemm(M, N, K, A, K, B, N, C, N, batch=batch, strideA=M * K, strideB=K * N, strideC=M * N)
+                wrong = int(((C - want).abs() > 1e-10).sum() + (~torch.isfinite(C)).sum())
+                assert wrong == 0, (cfg, M, N, K, batch, rep, wrong)
+        finally:
+            os.environ["HB_GEMM_CFG"] = "-1"
+
+
+@pytest.mark.parametrize("cfg", [-1, 0, 2, 4, 8])
+def test_two_level_batch_and_row_block_scatter(cfg):
+    """hb_dev_dgemm_ex: batch * batch_lo GEMMs in one launch (per-level strides, a table shared across b_hi), plain
+    store and the row-block scatter with row_offset_lo, against torch.matmul."""
+    import torch
+    from hermipy_b200.dist import DeviceOps, Gemm
+    ops = DeviceOps()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    os.environ["HB_GEMM_CFG"] = str(cfg)
+    try:
+        for (M, N, K, nhi, nlo) in [(128, 256, 128, 40, 2), (101, 202, 50, 3, 2), (64, 130, 33, 5, 3)]:
+            Kp, Np = (K + 1) & ~1, (N + 1) & ~1
+            A = torch.randn((nlo, M, Kp), generator=g, dtype=torch.float64, device="cuda")
+            B = torch.randn((nhi, nlo, K, Np), generator=g, dtype=torch.float64, device="cuda")
+            want = torch.einsum("lmk,hlkn->hlmn", A[:, :, :K], B[..., :N])
+            C = torch.full((nhi, nlo, M, Np), float("nan"), dtype=torch.float64, device="cuda")
+            ops.gemm(Gemm(M, N, K, A, Kp, B, Np, C, Np, batch=nhi, batch_lo=nlo, strideA_lo=M * Kp, strideB=nlo * K * Np,
+                          strideB_lo=K * Np, strideC=nlo * M * Np, strideC_lo=M * Np))
+            assert (C[..., :N] - want).abs().max().item() < 1e-11
+            # scatter: destination row = l * M + m, dealt over nlo blocks of M rows: D[l][h][m][n]
+            D = torch.full((nlo, nhi, M, Np), float("nan"), dtype=torch.float64, device="cuda")
+            ops.gemm(Gemm(M, N, K, A, Kp, B, Np, ldc=Np, batch=nhi, batch_lo=nlo, strideA_lo=M * Kp, strideB=nlo * K * Np,
+                          strideB_lo=K * Np, strideC=M * Np, blocks=[(D, l * nhi * M * Np) for l in range(nlo)],
+                          block_rows=M, row_offset_lo=M))
+            assert (D.permute(1, 0, 2, 3)[..., :N] - want).abs().max().item() < 1e-11
+    finally:
+        os.environ["HB_GEMM_CFG"] = "-1"
