@@ -528,6 +528,53 @@ class ShardedParityTransform:
             gout = self.backward(c)
         return graph, c, gout
 
+    # -- host buffers (the end-to-end path: this rank's slab in, this rank's coefficient block out) --------
+    def forward_host(self, f_host, c_host):
+        """f_host: page-locked CPU tensor of local_grid_shape(); c_host: page-locked CPU tensor of local_coef_shape().
+        Upload, transform, download; returns after the coefficients have landed in c_host."""
+        dev_f = self._buf("host_f", int(np.prod(self.local_grid_shape()))).view(self.local_grid_shape())
+        dev_f.copy_(f_host, non_blocking=True)
+        c_host.copy_(self.forward(dev_f), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return c_host
+
+    def backward_host(self, c_host, f_host):
+        dev_c = self._buf("host_c", int(np.prod(self.local_coef_shape()))).view(self.local_coef_shape())
+        dev_c.copy_(c_host, non_blocking=True)
+        f_host.copy_(self.backward(dev_c), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return f_host
+
+    # -- the reference's enumeration -------------------------------------------------------------------
+    def set_positions(self, degree, index_set="cube"):
+        """(valid, pos): for every cell of the local coefficient block whether it holds a basis function of the
+        index set, and the position of that function in the reference's enumeration (iterators.cpp order)."""
+        key = ("pos", degree, index_set)
+        if key not in self._bufs:
+            from . import core
+            m0, m1, m2 = self.coef_index()
+            M0, M1, M2 = np.meshgrid(m0, m1, m2, indexing="ij")
+            inside = (M0 >= 0) & (M1 >= 0) & (M2 >= 0)
+            pos = np.full(inside.shape, -1, dtype=np.int64)
+            pos[inside] = core.iterator_positions(np.stack([M0[inside], M1[inside], M2[inside]], axis=1), degree, index_set)
+            valid = pos >= 0
+            self._bufs[key] = (torch.from_numpy(valid).to(self.dev), torch.from_numpy(pos[valid]).to(self.dev))
+        return self._bufs[key]
+
+    def gather_coefficients(self, c, degree, index_set="cube", n_polys=None):
+        """The sharded coefficient blocks as ONE vector in the reference's enumeration order, on every rank: each rank
+        places its block (disjoint positions) and one all-reduce over NVLink assembles the vector -- the only
+        collective of the transform path besides the exchange, and only for callers that want the whole vector."""
+        valid, pos = self.set_positions(degree, index_set)
+        if n_polys is None:
+            from . import core
+            n_polys = core.iterator_size(3, degree, index_set)
+        full = torch.zeros(n_polys, dtype=self.dtype, device=self.dev)
+        full[pos] = c[valid]
+        if self.world > 1:
+            dist.all_reduce(full, group=self.group)
+        return full
+
 
 def plan_tables_as_tensors(plan):
     """Views of a Plan's per-axis device tables as torch CUDA tensors [(phi, w_phi)] (no copy)."""
