@@ -460,6 +460,8 @@ def bench_c4(ctx):
                 f[..., :n] = torch.from_numpy(np.ascontiguousarray(g_host[x0])).cuda()
                 sw = torch.zeros_like(f)
                 sw[..., :n] = torch.from_numpy(np.sqrt(w[x0][:, None, None] * w[None, :, None] * w[None, None, :])).cuda()
+                c = T.forward(f)                  # first call per GEMM shape times candidate tile configurations
+                gout = T.backward(c)
                 lib.hb_launch_count(1)
                 c = T.forward(f)
                 gout = T.backward(c)

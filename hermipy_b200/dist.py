@@ -340,10 +340,12 @@ class ShardedParityTransform:
     run).  All buffers are allocated once, so a round trip is a fixed launch sequence (see `capture`).
     """
 
-    def __init__(self, n_pts, P, tables, group=None, ops=None, exchange="nccl"):
+    def __init__(self, n_pts, P, tables, group=None, ops=None, exchange="nccl", emulate=None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if emulate is not None:     # developer switch: the launch sequence of rank 0 of `emulate` ranks on ONE GPU, the
+            self.world, self.rank, exchange = int(emulate), 0, "none"   # exchange kept local (timing only, results wrong)
         assert len(n_pts) == 3 and len(P) == 3, "the parity-split sharded transform is 3-D"
         self.n, self.P = [int(v) for v in n_pts], [int(v) for v in P]
         g = self.world
@@ -353,7 +355,7 @@ class ShardedParityTransform:
         self.tables = tables
         t = tables[0]["cW"]
         self.dev, self.dtype = t.device, t.dtype
-        self.exchange = exchange if (g > 1 or (exchange == "p2p" and dist.is_initialized())) else "none"
+        self.exchange = exchange if (emulate is None and (g > 1 or (exchange == "p2p" and dist.is_initialized()))) else "none"
         n, Pn = self.n, self.P
         self.nh = [(v + 1) // 2 for v in n]
         self.Pe = [(v + 1) // 2 for v in Pn]
@@ -520,7 +522,7 @@ class ShardedParityTransform:
             c = self.forward(f)
             gout = self.backward(c)
         torch.cuda.synchronize()
-        if self.world > 1:
+        if self.world > 1 and dist.is_initialized():
             dist.barrier(self.group)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
