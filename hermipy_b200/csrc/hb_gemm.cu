@@ -231,6 +231,24 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         if (dyn && dyn[0] && dyn[0] != '-') cfg = atoi(dyn);
         else if (env && env[0]) cfg = atoi(env);
     }
+    // Row-block scatter (the destinations may be peer GPUs): staged bulk-store epilogue when the layout allows
+    // 16-byte runs (HB_GEMM_BULK=0 keeps the register epilogue).  Small tiles win here -- several rounds per SM, so
+    // that one tile's copies drain over NVLink under the next tile's main loop (tools/dist_variants.py).
+    if (a.block_rows > 0 && a.epi == EPI_STORE && !a.a_mmajor && p.col_stride == 1 && (a.N & 1) == 0 &&
+        (a.ldc & 1) == 0 && (a.strideC & 1) == 0 && (a.strideC_lo & 1) == 0) {
+        const char* off = getenv("HB_GEMM_BULK");             // read per call: tests compare the two epilogues
+        bool aligned = !(off && off[0] == '0');
+        for (int i = 0; i < GEMM_MAX_BLOCKS && aligned; i++)
+            aligned = (reinterpret_cast<uintptr_t>(a.blocks[i]) & 15) == 0;
+        if (aligned) {
+            static const int kBulkOf[kNumCfgs] = {6, 1, 2, 2, 7, 2, 6, 7, 2, 7};
+            const char* pick = getenv("HB_GEMM_BULK_CFG");
+            int bc = (cfg >= 0 && cfg < kNumCfgs) ? kBulkOf[cfg] : 1;
+            if (cfg < 0 && pick && pick[0]) bc = kBulkOf[std::max(0, std::min(kNumCfgs - 1, atoi(pick)))];
+            p.epi = EPI_BULK;
+            return gemm_dispatch_bulk_k(bc, a, p, stream);
+        }
+    }
     if (cfg < 0 || cfg >= kNumCfgs) cfg = tuned_cfg(a, p, stream);
     return dispatch(cfg, a, p, stream);
 }

@@ -28,6 +28,11 @@ enum EpilogueMode : int {
     EPI_LUT = 1,      // out[b*strideC + lut[row*N + col]] = v   (lut < 0: dropped)
     EPI_VARF2D = 2,   // stage 2 of the dense 2-D varf: scatter A[idx(m0,m1)][idx(n0,n1)]; handled by the persistent
                       // kernel of hb_varf_gemm.cu (this generic kernel has no instantiation for it)
+    EPI_BULK = 3,     // EPI_STORE through a shared-memory staging tile and bulk asynchronous copies: every row of a
+                      // warp's sub-tile leaves as ONE contiguous run of full 128-byte lines.  Chosen by the launcher
+                      // for the row-block scatter (peer-GPU destinations): NVLink moves full lines at several times
+                      // the rate of the 32-byte pieces the register epilogue emits, and the copies run under the
+                      // next tile's main loop.
 };
 
 constexpr int GEMM_MAX_BLOCKS = 16;
@@ -111,6 +116,12 @@ __device__ __forceinline__ void gemm_trace(long long* trace, int w) {
 template <int BM, int BN, int STAGES>
 constexpr int gemm_smem_bytes() {
     return STAGES * (BM + BN) * GEMM_BK * 8 + 1024 /*alignment slack*/ + 2 * STAGES * 8;
+}
+// EPI_BULK: one staging sub-tile per consumer warp, rows padded by 16 bytes (conflict-free 16-byte fragment stores)
+__host__ __device__ constexpr int gemm_stage_pitch(int WN) { return WN * 8 + 16; }
+template <int BM, int BN, int STAGES, int WARPS_M, int WARPS_N>
+constexpr int gemm_smem_bytes_bulk() {
+    return gemm_smem_bytes<BM, BN, STAGES>() + 16 + WARPS_M * WARPS_N * (BM / WARPS_M) * gemm_stage_pitch(BN / WARPS_N);
 }
 
 // Register budget.  A CTA is NCW consumer warps plus one producer WARP GROUP (4 warps, one of them active), so
@@ -352,6 +363,47 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
             }
         }
         if (first_tile && threadIdx.x == 0) gemm_trace(p.trace, 3);   // [4] this warp's epilogue issued
+        continue;   // next tile
+    }
+    if constexpr (EPI == EPI_BULK) {
+        // Staged store (launcher guarantees: K-contiguous A, unit column stride, even N, 16-byte aligned rows).
+        static_assert(!RAGGED && !A_MMAJOR && (NJ % 2) == 0, "bulk epilogue: whole 16-column groups per warp");
+        constexpr int WN = NJ * 8, PITCH = gemm_stage_pitch(WN);
+        const uint32_t stg = ((bar_base + 2 * STAGES * 8 + 15u) & ~15u) + warp * (WM * PITCH);
+        // the copies of this warp's previous tile must have read the staging buffer
+        if (!first_tile) {
+            if (lane < WM) bulk_wait_read();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int nj = 0; nj < NJ; nj++) {
+                const uint32_t o = stg + (8 * mi + rm) * PITCH + (16 * (nj >> 1) + 4 * (nj & 1) + 8 * (t & 1) + 2 * (t >> 1)) * 8;
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(o), "d"(acc[mi][nj][0] * p.alpha),
+                             "d"(acc[mi][nj][1] * p.alpha) : "memory");
+            }
+        fence_proxy_async();      // generic-proxy writes above -> visible to the bulk copies (async proxy) below
+        __syncwarp();
+        for (int r = lane; r < WM; r += 32) {
+            const int row = m_base + wm * WM + r;
+            const int col0 = n_base + 8 * jn0;
+            if (row < p.M && col0 < p.N) {
+                double* rowp;
+                if (p.block_rows) {
+                    const int drow = p.row_offset + b_lo * p.row_offset_lo + row;
+                    rowp = p.blocks[drow / p.block_rows] + (long long)(drow % p.block_rows) * p.ldc;
+                } else {
+                    rowp = p.C + (long long)row * p.ldc;
+                }
+                bulk_store_s2g(rowp + c_batch_off + col0, stg + r * PITCH, (uint32_t)min(WN, p.N - col0) * 8u);
+            }
+        }
+        if (lane < WM) {
+            bulk_commit();
+            if (last_tile) bulk_wait_all();
+        }
+        if (first_tile && threadIdx.x == 0) gemm_trace(p.trace, 3);
         continue;   // next tile
     }
     // Plain store.  Everything that depends only on the row (destination block, pitch, alignment) is resolved once

@@ -52,6 +52,15 @@ int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint
     X(8, 48, 208, 2, 4, 4, AM, 1, EPI)  \
     X(9, 32, 208, 2, 4, 4, AM, 1, EPI)
 
+// The bulk-store epilogue (EPI_BULK) carries a staging sub-tile per consumer warp in shared memory: same tiles, fewer
+// pipeline stages / resident CTAs where the two would not fit 227 KB.  Configuration ids as above (the others map to
+// the nearest of these in gemm_launch).
+#define HB_GEMM_BULK_CONFIGS(X, AM, EPI) \
+    X(1, 64, 64, 2, 2, 4, AM, 2, EPI)    \
+    X(2, 64, 128, 2, 2, 4, AM, 1, EPI)   \
+    X(6, 96, 128, 4, 2, 4, AM, 1, EPI)   \
+    X(7, 32, 128, 2, 2, 3, AM, 2, EPI)
+
 template <int BM, int BN, int WMc, int WNc, int ST, bool AM, int MINB, int EPI>
 static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
@@ -82,7 +91,7 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
     const DeviceInfo dev = current_device_info();
     const long long n_cta = std::min<long long>(n_tiles, (long long)dev.sms * MINB);   // persistent: one wave
     auto kern = dgemm_dmma_tma_kernel<BM, BN, WMc, WNc, ST, AM, MINB, EPI>;
-    constexpr int smem = gemm_smem_bytes<BM, BN, ST>();
+    constexpr int smem = EPI == EPI_BULK ? gemm_smem_bytes_bulk<BM, BN, ST, WMc, WNc>() : gemm_smem_bytes<BM, BN, ST>();
     // the > 48 KB dynamic shared memory opt-in is a per-device property of the function: one bit per device
     static std::atomic<unsigned long long> attr_set{0};
     if (!(attr_set.load(std::memory_order_relaxed) >> dev.index & 1)) {
@@ -116,5 +125,6 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
 int gemm_dispatch_store_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);  // A K-contiguous
 int gemm_dispatch_store_m(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);  // A M-contiguous
 int gemm_dispatch_lut_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);
+int gemm_dispatch_bulk_k(int cfg, const GemmArgs& a, const GemmParams& p, cudaStream_t stream);   // cfg in {1, 2, 6, 7}
 
 }  // namespace hb

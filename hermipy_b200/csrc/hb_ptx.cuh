@@ -75,6 +75,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// Bulk asynchronous copy shared -> global (no tensor map: one contiguous run; both addresses 16-byte aligned, size a
+// multiple of 16).  The destination is a generic global address: local HBM or peer memory mapped over NVLink.  The
+// TMA engine emits full-line writes, and the issuing warp does not wait for them.
+__device__ __forceinline__ void bulk_store_s2g(void* dst, uint32_t src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the sources of all committed groups have been read (the staging buffer may be overwritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all committed groups are complete (their writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor in the stream is still running; `grid_dependency_wait` blocks until the predecessor has
 // completed and its memory is visible (a no-op for a normal launch), `grid_launch_dependents` lets the successor

@@ -105,7 +105,7 @@ def test_stage_release_waits_for_fragment_loads(cfg):
             os.environ["HB_GEMM_CFG"] = "-1"
 
 
-@pytest.mark.parametrize("cfg", [-1, 0, 2, 4, 8])
+@pytest.mark.parametrize("cfg", [-1, 0, 1, 2, 4, 7, 8])
 def test_two_level_batch_and_row_block_scatter(cfg):
     """hb_dev_dgemm_ex: batch * batch_lo GEMMs in one launch (per-level strides, a table shared across b_hi), plain
     store and the row-block scatter with row_offset_lo, against torch.matmul."""
@@ -132,3 +132,35 @@ def test_two_level_batch_and_row_block_scatter(cfg):
             assert (D.permute(1, 0, 2, 3)[..., :N] - want).abs().max().item() < 1e-11
     finally:
         os.environ["HB_GEMM_CFG"] = "-1"
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 6, 7])
+def test_bulk_store_epilogue_equals_register_epilogue(cfg):
+    """The row-block scatter leaves through shared memory and bulk asynchronous copies (EPI_BULK) when the layout
+    allows 16-byte runs: same bits as the register epilogue (HB_GEMM_BULK=0), persistent CTAs with several tiles
+    each (the staging buffer is reused), edge tiles in M and N, and nothing written beyond column N."""
+    import torch
+    from hermipy_b200.dist import DeviceOps, Gemm
+    ops = DeviceOps()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    os.environ["HB_GEMM_CFG"] = str(cfg)
+    try:
+        for (M, N, K, nhi, nlo, ld) in [(128, 256, 128, 64, 2, 256), (200, 1000, 48, 7, 2, 1010), (72, 44, 130, 9, 1, 48)]:
+            Kp = (K + 1) & ~1
+            A = torch.randn((nlo, M, Kp), generator=g, dtype=torch.float64, device="cuda")
+            B = torch.randn((nhi, nlo, K, N), generator=g, dtype=torch.float64, device="cuda")
+            res = []
+            for bulk in ("1", "0"):
+                os.environ["HB_GEMM_BULK"] = bulk
+                D = torch.full((nlo, nhi, M, ld), float("nan"), dtype=torch.float64, device="cuda")
+                ops.gemm(Gemm(M, N, K, A, Kp, B, N, ldc=ld, batch=nhi, batch_lo=nlo, strideA_lo=M * Kp, strideB=nlo * K * N,
+                              strideB_lo=K * N, strideC=M * ld, blocks=[(D, l * nhi * M * ld) for l in range(nlo)],
+                              block_rows=M, row_offset_lo=M))
+                res.append(D)
+            want = torch.einsum("lmk,hlkn->lhmn", A[:, :, :K], B)
+            assert torch.equal(res[0][..., :N], res[1][..., :N])
+            assert (res[0][..., :N] - want).abs().max().item() < 1e-10
+            assert torch.isnan(res[0][..., N:]).all()
+    finally:
+        os.environ["HB_GEMM_CFG"] = "-1"
+        os.environ.pop("HB_GEMM_BULK", None)
