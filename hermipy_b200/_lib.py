@@ -43,7 +43,9 @@ class GemmDesc(C.Structure):
                 ("B", C.c_void_p), ("ldb", C.c_longlong), ("strideB", C.c_longlong), ("strideB_lo", C.c_longlong),
                 ("C", C.c_void_p), ("ldc", C.c_longlong), ("strideC", C.c_longlong), ("strideC_lo", C.c_longlong),
                 ("n_blocks", C.c_int), ("block_rows", C.c_int), ("row_offset", C.c_int), ("row_offset_lo", C.c_int),
-                ("blocks", C.POINTER(C.c_void_p))]
+                ("blocks", C.POINTER(C.c_void_p)),
+                ("signal_flags", C.POINTER(C.c_void_p)), ("n_signal", C.c_int), ("signal_state", C.c_void_p),
+                ("wait_flags", C.c_void_p), ("n_wait", C.c_int), ("wait_epoch", C.c_void_p)]
 
 
 _lib = None

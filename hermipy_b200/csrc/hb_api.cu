@@ -940,6 +940,18 @@ int hb_dev_dgemm_ex(const hb_gemm_desc* q, void* stream) {
         g.C = q->blocks[0];
         for (int i = 0; i < q->n_blocks; i++) g.blocks[i] = q->blocks[i];
     }
+    if (q->signal_state) {
+        if (q->n_signal < 0 || q->n_signal > 16 || (q->n_signal > 0 && !q->signal_flags)) {
+            set_error("hb_dev_dgemm_ex: 0..16 signal flags");
+            return HB_ERR_INVALID;
+        }
+        g.signal_state = q->signal_state; g.n_signal = q->n_signal;
+        for (int i = 0; i < q->n_signal; i++) g.signal_flags[i] = q->signal_flags[i];
+    }
+    if (q->wait_flags) {
+        if (q->n_wait < 0 || !q->wait_epoch) { set_error("hb_dev_dgemm_ex: wait_flags needs wait_epoch"); return HB_ERR_INVALID; }
+        g.wait_flags = q->wait_flags; g.n_wait = q->n_wait; g.wait_epoch = q->wait_epoch;
+    }
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
 int hb_dev_parity_pass(int merge, int d, const int* n, const int* split, const long long* nat_stride,

@@ -127,7 +127,7 @@ static int tuned_cfg(const GemmArgs& a, const GemmParams& p, cudaStream_t stream
     for (int i = 0; i < kNumCfgs; i++) { t[i] = model_us(a, i); order[i] = i; }
     std::sort(order, order + kNumCfgs, [&](int x, int y) { return t[x] < t[y]; });
     static const bool enabled = [] { const char* e = getenv("HB_GEMM_AUTOTUNE"); return !(e && e[0] == '0'); }();
-    if (!enabled || t[order[0]] > 150.0 || a.block_rows > 0 || a.epi == EPI_VARF2D) return order[0];
+    if (!enabled || t[order[0]] > 150.0 || a.block_rows > 0 || a.epi == EPI_VARF2D || a.signal_state) return order[0];
     // Timing replays the caller's GEMM ~19 times on the caller's operands: only safe when C aliases neither input
     // (an in-place product would be fed its own output on the second launch).  Overlapping calls take the model's pick.
     {
@@ -220,6 +220,9 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
     p.batch_lo = a.batch_lo; p.strideC_lo = a.strideC_lo;
     p.row_offset_lo = a.row_offset_lo; p.col_offset_lo = a.col_offset_lo;
     for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.blocks[i] = a.blocks[i];
+    p.wait_flags = a.wait_flags; p.wait_epoch = a.wait_epoch; p.n_wait = a.wait_flags ? a.n_wait : 0;
+    p.signal_state = a.signal_state; p.n_signal = a.signal_state ? a.n_signal : 0;
+    for (int i = 0; i < GEMM_MAX_BLOCKS; i++) p.signal_flags[i] = a.signal_flags[i];
     if (a.block_rows > 0 && (a.M + a.block_rows - 1) / a.block_rows > GEMM_MAX_BLOCKS) {
         set_error("gemm: at most %d destination row blocks", GEMM_MAX_BLOCKS);
         return HB_ERR_INVALID;

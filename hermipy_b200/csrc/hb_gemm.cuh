@@ -83,6 +83,13 @@ struct GemmParams {
     int col_stride, col_offset;   // EPI_STORE: column c is stored at col_offset + c * col_stride (1, 0 = plain)
     int row_stride, row_offset;   // EPI_LUT: GEMM row r is row row_offset + r * row_stride of the look-up table
     double* blocks[GEMM_MAX_BLOCKS];
+    // Exchange flags (hb_gemm_desc): consumer side -- the TMA producer waits for wait_flags[i] >= *wait_epoch before its
+    // first load; producer side -- the last CTA to finish bumps signal_state[0] and publishes it to the peers.
+    const unsigned long long* wait_flags;
+    const unsigned long long* wait_epoch;
+    int n_wait, n_signal;
+    unsigned long long* signal_state;
+    unsigned long long* signal_flags[GEMM_MAX_BLOCKS];
 };
 
 __device__ __forceinline__ long long global_ns() {
@@ -208,6 +215,16 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
         if (warp == NCW && lane == 0) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
+            if (p.wait_flags != nullptr) {
+                // an operand is being delivered by peer GPUs: wait for their completion flags (acquire, system scope),
+                // then order the TMA loads (async proxy) behind the acquire
+                const unsigned long long epoch = *reinterpret_cast<const volatile unsigned long long*>(p.wait_epoch);
+                for (int i = 0; i < p.n_wait; i++)
+                    while (ld_relaxed_sys(p.wait_flags + i) < epoch) {
+                    }
+                __threadfence_system();
+                fence_proxy_async_global();
+            }
 
             int it = 0;   // k-tiles issued so far by this CTA, over all of its tiles
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -468,6 +485,24 @@ __global__ void __launch_bounds__((WARPS_M* WARPS_N + 4) * 32, MIN_CTAS)
     }
     if (first_tile && threadIdx.x == 0) gemm_trace(p.trace, 3);   // [4] this warp's epilogue issued
     }   // tile loop
+    if (p.signal_state != nullptr) {
+        // Publish "this rank's stores have landed" to the peers.  The consumer warps meet at a named barrier (the
+        // producer group has exited; bulk copies were waited for by their issuing lanes), one thread fences system-wide
+        // -- cumulative over everything the barrier ordered before it -- and counts the CTA in; the last CTA of the grid
+        // bumps the epoch, fences once more and writes the epoch to this rank's slot on every peer.
+        asm volatile("bar.sync 1, %0;" ::"n"(NCW * 32) : "memory");
+        if (threadIdx.x == 0) {
+            unsigned int* done = reinterpret_cast<unsigned int*>(p.signal_state + 1);
+            __threadfence_system();
+            if (atomicAdd(done, 1u) == gridDim.x - 1) {
+                const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(p.signal_state) + 1;
+                *reinterpret_cast<volatile unsigned long long*>(p.signal_state) = epoch;
+                *reinterpret_cast<volatile unsigned int*>(done) = 0u;
+                __threadfence_system();
+                for (int i = 0; i < p.n_signal; i++) st_relaxed_sys(p.signal_flags[i], epoch);
+            }
+        }
+    }
 }
 
 }  // namespace hb

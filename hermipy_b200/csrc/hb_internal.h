@@ -38,6 +38,13 @@ struct GemmArgs {
     int col_stride = 1, col_offset = 0;   // EPI_STORE: column c goes to col_offset + c*col_stride
     int row_stride = 1, row_offset = 0;   // EPI_LUT: GEMM row r uses look-up-table row row_offset + r*row_stride
     int group_m = 1;                 // tile rows per rasterisation group (L2 locality of big GEMMs)
+    // exchange flags (see hb_gemm_desc in include/hermite_b200.h)
+    unsigned long long* signal_flags[16] = {nullptr};
+    int n_signal = 0;
+    unsigned long long* signal_state = nullptr;
+    const unsigned long long* wait_flags = nullptr;
+    int n_wait = 0;
+    const unsigned long long* wait_epoch = nullptr;
     int cfg = -1;  // -1 auto (cost model), else index into the tile-configuration table of hb_gemm.cu
 };
 

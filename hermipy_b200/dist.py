@@ -244,7 +244,9 @@ class Gemm:
 
     def __init__(self, M, N, K, A, lda, B, ldb, C=None, ldc=0, a_off=0, b_off=0, c_off=0, batch=1, batch_lo=1,
                  strideA=0, strideA_lo=0, strideB=0, strideB_lo=0, strideC=0, strideC_lo=0, blocks=None, block_rows=0,
-                 row_offset_lo=0):
+                 row_offset_lo=0, signal=None, wait=None):
+        # signal = ([peer flag addresses], local state address): the last CTA publishes "stores landed" to the peers;
+        # wait = (local flags address, count, local epoch address): the kernel waits for the peers' flags first
         self.__dict__.update(locals())
         del self.__dict__["self"]
 
@@ -270,6 +272,12 @@ class DeviceOps:
             d.C = None
         else:
             d.C = ptr(g.C, g.c_off)
+        keep2 = None
+        if g.signal is not None:
+            keep2 = (C.c_void_p * len(g.signal[0]))(*g.signal[0])
+            d.signal_flags, d.n_signal, d.signal_state = C.cast(keep2, C.POINTER(C.c_void_p)), len(g.signal[0]), g.signal[1]
+        if g.wait is not None:
+            d.wait_flags, d.n_wait, d.wait_epoch = g.wait
         check(lib().hb_dev_dgemm_ex(C.byref(d), _stream()))
 
     def parity_pass(self, merge, n, split, nat_stride, srt_stride, srt_par, src, dst, nat_pad_last=0):
@@ -368,6 +376,11 @@ class ShardedParityTransform:
         self.Ps = -(-self.C1 // g)
         self._bufs, self._symm, self._pending = {}, {}, set()
         self.always_fence = bool(int(os.environ.get("HB_DIST_ALWAYS_FENCE", "0")))   # developer switch
+        # p2p: the exchange is fenced by ONE symmetric-memory barrier kernel between the scatter GEMM and its consumer.
+        # HB_DIST_FUSED_FLAGS=1 replaces it by completion flags written by the scatter GEMM's last CTA and awaited by
+        # the consumer GEMM's first operand load (no kernel in between); measured on 2 GPUs it is the slower of the
+        # two (561 vs 550 us per round trip, 542 with no fence at all), so it is off by default.
+        self.fused_flags = bool(int(os.environ.get("HB_DIST_FUSED_FLAGS", "0")))
 
     # -- layout -----------------------------------------------------------------------------------
     def local_x0(self):
@@ -408,6 +421,24 @@ class ShardedParityTransform:
             self._symm[name] = (t, hdl)
         return self._symm[name]
 
+    def _exchange_flags(self, slot):
+        """(signal, wait) arguments of the scatter GEMM / its consumer for exchange `slot` (0 forward, 1 backward):
+        flags[slot][src] lives in symmetric memory on every rank, the epoch / CTA counters in local memory."""
+        g, r = self.world, self.rank
+        if "flags" not in self._symm:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(2 * g, dtype=torch.int64, device=self.dev)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            hdl.barrier(channel=0)
+            self._symm["flags"] = (t, hdl)
+            self._bufs["flag_state"] = torch.zeros(4, dtype=torch.int64, device=self.dev)
+        flags, hdl = self._symm["flags"]
+        state = self._bufs["flag_state"]
+        signal = ([self._peer_ptr(flags, hdl, q) + 8 * (slot * g + r) for q in range(g)], state.data_ptr() + 16 * slot)
+        wait = (flags.data_ptr() + 8 * slot * g, g, state.data_ptr() + 16 * slot)
+        return signal, wait
+
     def _peer_ptr(self, t, hdl, q):
         """address of rank q's copy of the symmetric tensor `t` (a handle may describe a larger allocation that
         several tensors were carved from: `buffer_ptrs` are then the block bases, not the tensors)"""
@@ -430,7 +461,8 @@ class ShardedParityTransform:
             self._pending.clear()
 
     def _after_scatter(self, name, hdl):
-        hdl.barrier(channel=1)
+        if not self.fused_flags:
+            hdl.barrier(channel=1)
         self._pending.clear()
         self._pending.add(name)     # about to be read locally
 
@@ -448,16 +480,19 @@ class ShardedParityTransform:
         # axis 1 + exchange: sorted row m1' = p1 Pe1 + j of batch entry X0 = (h0l, p0) goes to rank m1' // Ps, which
         # receives R[h0 = src sh + h0l][p0][m1' % Ps][C2]
         blk = sh * 2 * Ps * C2
+        signal = wait = None
         if self.exchange == "p2p":
             recv, hdl = self._symm_buf("F", g * blk)
             self._before_scatter("F", hdl)
             blocks = [(self._peer_ptr(recv, hdl, q), r * blk) for q in range(g)]
+            if self.fused_flags:
+                signal, wait = self._exchange_flags(0)
         else:
             send = self._buf("F_send", g * blk)
             blocks = [(send, q * blk) for q in range(g)]
         ops.gemm(Gemm(Pe[1], C2, nh[1], T[1]["cWT"], nhp[1], t1, C2, ldc=C2, batch=X0, batch_lo=2,
                       strideA_lo=Pe[1] * nhp[1], strideB=G1 * C2, strideB_lo=nh[1] * C2, strideC=Ps * C2,
-                      blocks=blocks, block_rows=Ps, row_offset_lo=Pe[1]))
+                      blocks=blocks, block_rows=Ps, row_offset_lo=Pe[1], signal=signal))
         if self.exchange == "p2p":
             self._after_scatter("F", hdl)
         elif self.exchange == "nccl":
@@ -469,7 +504,7 @@ class ShardedParityTransform:
         cols = Ps * C2
         c = self._buf("coef", self.C0 * cols)
         ops.gemm(Gemm(Pe[0], cols, nh[0], T[0]["cWT"], nhp[0], recv, 2 * cols, c, cols, batch_lo=2,
-                      strideA_lo=Pe[0] * nhp[0], strideB_lo=cols, strideC_lo=Pe[0] * cols))
+                      strideA_lo=Pe[0] * nhp[0], strideB_lo=cols, strideC_lo=Pe[0] * cols, wait=wait))
         return c.view(self.C0, Ps, C2)
 
     # -- backward ---------------------------------------------------------------------------------
@@ -480,18 +515,21 @@ class ShardedParityTransform:
         c = c.reshape(-1)
         # axis 0 + exchange: row h0 of parity p0 goes to rank h0 // sh, next to the slices of the other ranks:
         # Y[h0l][p0][m1' = src Ps + j][C2]
+        signal = wait = None
         if self.exchange == "p2p":
             Y, hdl = self._symm_buf("B", X0 * g * cols)
             self._before_scatter("B", hdl)
             blocks = [(self._peer_ptr(Y, hdl, q), r * cols) for q in range(g)]
             ldc, lo_stride = 2 * g * cols, g * cols
+            if self.fused_flags:
+                signal, wait = self._exchange_flags(1)
         else:
             send = self._buf("B_send", g * X0 * cols)
             blocks = [(send, q * X0 * cols) for q in range(g)]
             ldc, lo_stride = 2 * cols, cols
         ops.gemm(Gemm(nh[0], cols, Pe[0], T[0]["cPhi"], Pep[0], c, cols, ldc=ldc, batch_lo=2,
                       strideA_lo=nh[0] * Pep[0], strideB_lo=Pe[0] * cols, strideC_lo=lo_stride, blocks=blocks,
-                      block_rows=sh))
+                      block_rows=sh, signal=signal))
         if self.exchange == "p2p":
             self._after_scatter("B", hdl)
         else:
@@ -506,7 +544,7 @@ class ShardedParityTransform:
         u = self._buf("u", X0 * G1 * C2)
         ops.gemm(Gemm(nh[1], C2, Pe[1], T[1]["cPhi"], Pep[1], Y, C2, u, C2, batch=X0, batch_lo=2,
                       strideA_lo=nh[1] * Pep[1], strideB=g * cols, strideB_lo=Pe[1] * C2, strideC=G1 * C2,
-                      strideC_lo=nh[1] * C2))
+                      strideC_lo=nh[1] * C2, wait=wait))
         # axis 2: v[(X0, X1)][p2 nhp2 + h] = sum_m' u[(X0, X1)][p2 Pep2 + m'] cPhiT2[p2][m'][h]
         v = self._buf("v", X0 * G1 * G2)
         ops.gemm(Gemm(X0 * G1, nh[2], Pe[2], u, C2, T[2]["cPhiT"], nhp[2], v, G2, batch_lo=2, strideA_lo=Pep[2],

@@ -174,6 +174,17 @@ typedef struct hb_gemm_desc {
     double* C;       long long ldc, strideC, strideC_lo;
     int n_blocks, block_rows, row_offset, row_offset_lo;
     double* const* blocks;
+    /* Exchange flags (optional; all zero = off): device-side completion signalling for a GEMM whose epilogue stores
+     * into peer GPUs, so that no separate barrier kernel sits between it and its consumer.
+     * Producer side: when the whole grid has finished -- its stores performed and fenced system-wide -- the last CTA
+     * increments the 64-bit epoch counter signal_state[0] (local memory; signal_state[1] is scratch, both start at
+     * zero) and writes the new epoch to every signal_flags[i], i < n_signal (peer addresses: this rank's slot in each
+     * peer's flag array).  Consumer side: before its first operand load the kernel waits until every
+     * wait_flags[i], i < n_wait (local memory, written by the peers) has reached the epoch stored at wait_epoch
+     * (local memory: the signal_state[0] of this rank's own producer launch of the same exchange, which precedes the
+     * consumer in stream order).  The epochs live in device memory, so a captured CUDA graph replays correctly. */
+    unsigned long long* const* signal_flags; int n_signal; unsigned long long* signal_state;
+    const unsigned long long* wait_flags;    int n_wait;   const unsigned long long* wait_epoch;
 } hb_gemm_desc;
 int hb_dev_dgemm_ex(const hb_gemm_desc* desc, void* cuda_stream);
 /* Parity split (merge = 0) / merge (merge = 1) of a d-dimensional grid function along up to three axes in one pass

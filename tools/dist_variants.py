@@ -32,15 +32,28 @@ class CfgOps(DeviceOps):
             os.environ.pop("HB_GEMM_CFG", None)
 
 
-class NoBarrier(ShardedParityTransform):
+class BarrierKernels(ShardedParityTransform):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.fused_flags = False
+
+
+class FusedFlags(ShardedParityTransform):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.fused_flags = True
+
+
+class NoSync(ShardedParityTransform):
+    """neither flags nor barriers (timing only)"""
+    def _exchange_flags(self, slot):
+        return None, None
+
     def _before_scatter(self, name, hdl):
         pass
 
-    def _after_scatter(self, name, hdl):
-        pass
 
-
-class LocalStores(ShardedParityTransform):
+class LocalStores(BarrierKernels):
     def _peer_ptr(self, t, hdl, q):
         return t.data_ptr()
 
@@ -65,12 +78,12 @@ def run(label, cls=ShardedParityTransform, **kw):
     dist.barrier()
 
 
-run("baseline")
-for cfg in (1, 2, 7, 6):
-    run("scatter GEMMs cfg %d" % cfg, scatter_cfg=cfg)
-for cfg in (0, 1, 2, 6):
-    run("plain GEMMs cfg %d" % cfg, plain_cfg=cfg)
-run("no barriers (timing only)", cls=NoBarrier)
+run("baseline (bulk stores, barrier kernels)")
+run("fused flags instead of barrier kernels", cls=FusedFlags)
+os.environ["HB_GEMM_BULK"] = "0"
+run("register epilogue (HB_GEMM_BULK=0)")
+os.environ.pop("HB_GEMM_BULK")
+run("scatter GEMMs bulk cfg 7", scatter_cfg=7)
+run("no flags, no barriers (timing only)", cls=NoSync)
 run("stores kept local (timing only)", cls=LocalStores)
-run("local stores, no barriers (timing only)", cls=type("LN", (NoBarrier, LocalStores), {}))
 dist.destroy_process_group()
