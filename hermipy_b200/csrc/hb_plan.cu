@@ -175,7 +175,30 @@ int plan_create(hb_plan** out, int dim, const int* n_pts, int degree, const doub
             while (A.slots.size() % 8) A.slots.push_back(-1);
             return (count + 7) / 8;
         };
-        if (A.fourier) {
+        // Only the axis whose contraction is halved by parity (axis 0 of the 2-D Gram varf) needs its slots sorted by
+        // parity; on the other axis natural order keeps consecutive basis indices -- consecutive output positions --
+        // next to each other inside a tile (contiguous runs instead of every second entry).
+        // Which one: sets enumerated along an axis (cube, rectangle) gain from natural order (C2 cube stage 2: 39 GB ->
+        // 31 GB of DRAM traffic, 17.1 -> 16.4 ms); graded sets (triangle, cross) run along anti-diagonals, where both
+        // axes must step alike (sorted on both: C3 triangle 97 ms against 109 ms).  HB_VARF_SORT_ALL_AXES=0/1 overrides.
+        bool natural_axis1 = false;
+        if (dim == 2 && a == 1 && !A.fourier) {
+            const int P0 = (int)iset->extent[0], P1 = (int)iset->extent[1];
+            auto pos = [&](int i, int j) { return (i < 0 || j < 0 || i >= P0 || j >= P1) ? -1 : iset->lex_to_pos[(size_t)i * P1 + j]; };
+            long long along_axis = 0, along_diag = 0;
+            for (int i = 0; i < P0; i++)
+                for (int j = 0; j < P1; j++) {
+                    const int v = pos(i, j);
+                    if (v < 0) continue;
+                    along_axis += (pos(i, j + 1) == v + 1) + (pos(i + 1, j) == v + 1);
+                    along_diag += (pos(i + 1, j - 1) == v + 1) + (pos(i - 1, j + 1) == v + 1);
+                }
+            natural_axis1 = along_axis > along_diag;
+            const char* e = getenv("HB_VARF_SORT_ALL_AXES");
+            if (e && e[0]) natural_axis1 = e[0] == '0';
+        }
+        pl->varf_natural_axis1 = natural_axis1;
+        if (A.fourier || natural_axis1) {
             A.nb_even = add_group(0, 1);
         } else {
             A.nb_even = add_group(0, 2);
@@ -917,6 +940,7 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     g2.blkrange = static_cast<const int2*>(pl->blkrange.p);
     g2.P0 = P0; g2.Pp0 = nb0; g2.P1 = P1; g2.Pp1 = nb1;
     g2.b_koff_odd = parity_seg; g2.nb_even0 = pl->ax[0].nb_even;
+    g2.group_m = pl->varf_natural_axis1 ? 3 : 2;   // base-block squares of the tile order (varf_tile_list; measured)
     const bool full = (row_begin == 0 && row_end == pl->n_polys);
     g2.row_begin = (int)row_begin; g2.row_end = full ? 0x7fffffff : (int)row_end;
     g2.symmetric = full ? 1 : 0;
@@ -1099,7 +1123,8 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
         const long long plane = (long long)(N + 1) * pl->TPp;
         for (int a = 0; a < 2; a++) {
             if (pl->TB_ok[a]) continue;
-            if (a == 1 && pl->ax[1].fourier == pl->ax[0].fourier && pl->ax[1].P == pl->ax[0].P) continue;  // shares TB[0]
+            if (a == 1 && pl->ax[1].fourier == pl->ax[0].fourier && pl->ax[1].P == pl->ax[0].P &&
+                pl->ax[1].slots == pl->ax[0].slots) continue;  // same basis, same slot order: shares TB[0]
             const int nb = pl->ax[a].nb;
             const double* T = pl->ax[a].fourier ? pl->Tf.d() : pl->T.d();
             HB_TRY(pl->TB[a].ensure((size_t)(2 * N + 1) * nb * nb * 64 * 8));

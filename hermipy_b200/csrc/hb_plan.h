@@ -79,6 +79,7 @@ struct Axis {
 }  // namespace hb
 
 struct hb_plan {
+    bool varf_natural_axis1 = false;   // dim 2: slots of axis 1 in natural order (see plan_create)
     int dim = 0, degree = 0, set = 0;
     std::shared_ptr<const hb::IndexSet> iset;
     std::vector<hb::Axis> ax;

@@ -341,18 +341,21 @@ __global__ void __launch_bounds__(384, 1)
 
 }  // namespace
 
-// List of needed tiles in the order they are handed out: row tiles in G x G squares of (bm0, bn0), and for every
-// column tile the whole square back to back, so that a square keeps its part of the left table in L2 while the
-// right table streams, and tiles whose 64-byte runs are neighbours in the output (adjacent n0 blocks for the direct
-// entries, adjacent m0 blocks for the mirrored ones) run close together in time.
-// What the order does NOT fix: the runs start on 16-byte but mostly not on 32-byte boundaries, and ncu shows 26 GB
-// read + 26 GB written for the 13 GB matrix of C2/cube (read-modify-write of partial sectors); squares of 2..13,
-// groups of 16 consecutive row tiles, orders binned by output super-blocks, streaming stores and L2 eviction hints
-// all land within 5 % of each other (15.6-16.7 ms).  The scatter pattern itself is dictated by the reference's
-// enumeration order; wider runs would need 128-row tiles (two n0 blocks per tile).
+// List of needed tiles in the order they are handed out.
+// Axis 0 is parity-sorted (even basis indices first), so the 8 indices of a block are 2 apart: the entries a tile
+// writes along m0 / n0 are every SECOND double of the output -- half of each 32-byte sector; the other half belongs
+// to the partner block of the other parity (block b + nb_even).  A sector whose halves reach L2 far apart in time is
+// evicted half-written and completed by a DRAM read-modify-write: ncu showed 26 GB read + 26 GB written for the 13 GB
+// matrix of C2/cube.  Tiles are therefore listed in FAMILIES that complete each other's sectors -- for base blocks
+// (i, j): (i,j), (i,j'), (i',j), (i',j') and, in symmetric mode, their transposed family, whose mirrored entries land
+// in the same rows -- back to back, so that the dynamic scheduler runs them at the same time on neighbouring groups
+// and the halves merge in L2.  Families are walked in G x G squares of base blocks, and for every column tile the whole
+// square back to back, so that a square keeps its part of the left table in L2 while the right table streams.
 int varf_tile_list(const GemmArgs& a, const std::vector<int>& blkrange, std::vector<int>& out) {
     const int tiles_n = (a.N + PP_BN - 1) / PP_BN;
-    static const int G = [] { const char* e = getenv("HB_VARF_GROUP"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
+    static const int G_env = [] { const char* e = getenv("HB_VARF_GROUP"); return e && atoi(e) > 0 ? atoi(e) : 0; }();
+    const int G = G_env > 0 ? G_env : (a.group_m > 1 ? a.group_m : 4);
+    static const bool families = [] { const char* e = getenv("HB_VARF_FAMILIES"); return !(e && e[0] == '0'); }();
     out.clear();
     auto needed = [&](int bm0, int bn0, int tn) {
         if (a.symmetric && bm0 > bn0) return false;
@@ -366,12 +369,21 @@ int varf_tile_list(const GemmArgs& a, const std::vector<int>& blkrange, std::vec
         }
         return false;
     };
-    for (int m0 = 0; m0 < a.Pp0; m0 += G)
-        for (int n0 = 0; n0 < a.Pp0; n0 += G)
+    // base blocks: the even-parity blocks [0, nbe); partner(b) = the odd-parity block over the same index range
+    const int nbe = (families && a.nb_even0 > 0 && a.nb_even0 < a.Pp0) ? a.nb_even0 : a.Pp0;
+    auto partner = [&](int b) { return b + nbe < a.Pp0 ? b + nbe : -1; };
+    auto emit = [&](int x, int y, int tn) {
+        if (x >= 0 && y >= 0 && needed(x, y, tn)) { out.push_back(x * a.Pp0 + y); out.push_back(tn); }
+    };
+    for (int m0 = 0; m0 < nbe; m0 += G)
+        for (int n0 = a.symmetric ? m0 : 0; n0 < nbe; n0 += G)
             for (int tn = 0; tn < tiles_n; tn++)
-                for (int i = m0; i < std::min(m0 + G, a.Pp0); i++)
-                    for (int j = n0; j < std::min(n0 + G, a.Pp0); j++)
-                        if (needed(i, j, tn)) { out.push_back(i * a.Pp0 + j); out.push_back(tn); }
+                for (int i = m0; i < std::min(m0 + G, nbe); i++)
+                    for (int j = (a.symmetric && n0 == m0) ? i : n0; j < std::min(n0 + G, nbe); j++) {
+                        const int ip = partner(i), jp = partner(j);
+                        emit(i, j, tn); emit(i, jp, tn); emit(ip, j, tn); emit(ip, jp, tn);
+                        if (a.symmetric && i != j) { emit(j, i, tn); emit(j, ip, tn); emit(jp, i, tn); emit(jp, ip, tn); }
+                    }
     return HB_OK;
 }
 
