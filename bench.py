@@ -714,6 +714,14 @@ def bench_c2_varf(ctx, plan, x, w, X, Y):
         ms_poly = max_over_ranks(time_steps(torch, lambda: vplan.varf(fV, "reference", out), vs, 1, flush, barrier)) / vs
         kept, path = vplan.varf_info()
         ref_poly = out.clone() if args.check else None
+        # the same matrix as CSR straight from the band of retained triple products (no dense buffer, no zero-fill);
+        # host-timed: the call returns nnz, i.e. it ends with a device -> host read
+        vplan.varf_sparse(fV, fetch=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(vs):
+            nnz_sp = vplan.varf_sparse(fV, fetch=False)
+        ms_sparse = (time.perf_counter() - t0) / vs * 1e3
         ms_gram = max_over_ranks(time_steps(torch, lambda: vplan.varf(fE, "gram", out), vs, 1, flush, barrier)) / vs
         vplan.set_timing(True)
         vplan.varf(fE, "gram", out)
@@ -735,6 +743,10 @@ def bench_c2_varf(ctx, plan, x, w, X, Y):
                              "bound": "hbm", "achieved_gbs": 8.0 * npol ** 2 / ms_poly * 1e-6,
                              "peak_gbs": peaks.get("hbm_gbs"),
                              "frac": 8.0 * npol ** 2 / ms_poly * 1e-6 / peaks.get("hbm_gbs")},
+            "assembly_ms_polynomial_f_sparse": ms_sparse,
+            "polynomial_f_sparse": {"mode": "CSR emitted from the band (candidates -> radix sort -> indptr/indices/data), "
+                                            "device-resident result; host-timed including the final nnz read",
+                                    "nnz": int(nnz_sp), "csr_bytes": int(12 * nnz_sp + 8 * (npol + 1))},
             "assembly_ms_dense_f": ms_gram,
             "dense_f": {"mode": "Gram form, two-stage FP64 tensor-core contraction on 8x8-blocked pair tables "
                                 "(persistent stage-2 kernel); symmetric half computed and mirrored; contraction "

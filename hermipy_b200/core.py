@@ -7,12 +7,13 @@ core.py:29-66 of the reference).  Invalid input raises an exception where the re
 print a message and exit() the interpreter.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 import scipy.sparse as ss
 
 from . import _lib
-from ._lib import c_dp, c_ip, c_up, check, lib
+from ._lib import c_dp, c_ip, c_llp, c_up, check, lib
 
 VARF_MODE = {"reference": _lib.VARF_REFERENCE, "gram": _lib.VARF_GRAM}
 
@@ -204,40 +205,80 @@ def varf(degree, fgrid, nodes, weights, sparse=False, do_fourier=None, index_set
         check(lib().hb_varf(dim, _ip(n_pts), degree, _dp(f), _dp(nd), _dp(wt), _ip(four), index_set.encode(),
                             VARF_MODE[mode], _dp(out), n))
         return out
-    nnz = C.c_longlong(0)
-    check(lib().hb_varf_sp(dim, _ip(n_pts), degree, _dp(f), _dp(nd), _dp(wt), _ip(four), index_set.encode(),
-                           VARF_MODE[mode], C.byref(nnz)))
-    indptr = np.zeros(n + 1, dtype=np.int64)
-    indices = np.zeros(max(nnz.value, 1), dtype=np.int32)
-    data = np.zeros(max(nnz.value, 1))
+    with _SP_LOCK:
+        nnz = C.c_longlong(0)
+        check(lib().hb_varf_sp(dim, _ip(n_pts), degree, _dp(f), _dp(nd), _dp(wt), _ip(four), index_set.encode(),
+                               VARF_MODE[mode], C.byref(nnz)))
+        return _fetch_csr(n, n, nnz.value)
+
+
+# The library keeps ONE sparse result per process: a *_sp call and the fetch of its result form one critical section.
+_SP_LOCK = threading.Lock()
+
+
+def _fetch_csr(rows, cols, nnz):
+    indptr = np.zeros(rows + 1, dtype=np.int64)
+    indices = np.zeros(max(nnz, 1), dtype=np.int32)
+    data = np.zeros(max(nnz, 1))
     check(lib().hb_sparse_fetch(indptr.ctypes.data_as(_lib.c_llp), _ip(indices), _dp(data)))
-    return ss.csr_matrix((data[:nnz.value], indices[:nnz.value], indptr), shape=(n, n))
+    return ss.csr_matrix((data[:nnz], indices[:nnz], indptr), shape=(rows, cols))
+
+
+def _csr_arrays(m):
+    """(indptr int64, indices int32, data float64) of a matrix in canonical CSR form (format conversion on the host,
+    no arithmetic: a dense factor is scanned for its non-zeros as the reference's to_spmat does, sparse.cpp:44-58)"""
+    m = m if isinstance(m, ss.csr_matrix) else ss.csr_matrix(np.asarray(m, dtype=np.float64))
+    if not m.has_canonical_format:
+        m = m.copy()
+        m.sum_duplicates()
+    return (np.ascontiguousarray(m.indptr, dtype=np.int64), np.ascontiguousarray(m.indices, dtype=np.int32),
+            np.ascontiguousarray(m.data, dtype=np.float64))
 
 
 def varfd(dim, degree, direction, var, do_fourier=0, index_set="triangle"):
-    sparse = isinstance(var, ss.csr_matrix)
-    v = _d(var.toarray() if sparse else var)
+    if isinstance(var, ss.csr_matrix):      # stored entries in, stored entries out (varf.cpp:290-376)
+        indptr, indices, data = _csr_arrays(var)
+        n = var.shape[0]
+        with _SP_LOCK:
+            nnz = C.c_longlong(0)
+            check(lib().hb_varfd_sp(int(dim), int(degree), int(direction), indptr.ctypes.data_as(_lib.c_llp), _ip(indices),
+                                    _dp(data), n, int(do_fourier), index_set.encode(), C.byref(nnz)))
+            return _fetch_csr(n, n, nnz.value)
+    v = _d(var)
     out = np.zeros_like(v)
     check(lib().hb_varfd(int(dim), int(degree), int(direction), _dp(v), v.shape[0], int(do_fourier),
                          index_set.encode(), _dp(out)))
-    return ss.csr_matrix(out) if sparse else out
+    return out
 
 
 def _tensorize_call(arrays, dirs_list, index_set, sparse):
-    arrays = [_d(a.toarray() if isinstance(a, ss.csr_matrix) else a) for a in arrays]
     k = len(arrays)
-    matrices = arrays[0].ndim == 2
+    matrices = len(arrays[0].shape) == 2
     lens = _i([a.shape[0] for a in arrays])
     dflat = _i(np.concatenate([np.asarray(d, dtype=np.int32) for d in dirs_list]))
     dlens = _i([len(d) for d in dirs_list])
     dim = int(dlens.sum())
     degree = iterator_get_degree(len(dirs_list[0]), arrays[0].shape[0], index_set)
     n = iterator_size(dim, degree, index_set)
+    any_sparse = any(isinstance(a, ss.csr_matrix) for a in arrays)
+    if matrices and (sparse or any_sparse):
+        # sparse factors or a sparse result: pairs of stored entries, never an n x n buffer (tensorize.cpp:197-283)
+        trip = [_csr_arrays(a) for a in arrays]
+        p_ptr = (c_llp * k)(*[t[0].ctypes.data_as(c_llp) for t in trip])
+        p_ind = (c_ip * k)(*[_ip(t[1]) for t in trip])
+        p_dat = (c_dp * k)(*[_dp(t[2]) for t in trip])
+        with _SP_LOCK:
+            rows, nnz = C.c_longlong(0), C.c_longlong(0)
+            check(lib().hb_tensorize_mats_sp(k, p_ptr, p_ind, p_dat, _ip(lens), _ip(dflat), _ip(dlens), index_set.encode(),
+                                             C.byref(rows), C.byref(nnz)))
+            res = _fetch_csr(n, n, nnz.value)
+        return res if sparse else res.toarray()      # sparse factors, dense result requested
+    arrays = [_d(a) for a in arrays]
     ptrs = (c_dp * k)(*[_dp(a) for a in arrays])
     if matrices:
         out = np.zeros((n, n))
         check(lib().hb_tensorize_mats(k, ptrs, _ip(lens), _ip(dflat), _ip(dlens), index_set.encode(), _dp(out), n))
-        return ss.csr_matrix(out) if sparse else out
+        return out
     out = np.zeros(n)
     check(lib().hb_tensorize_vecs(k, ptrs, _ip(lens), _ip(dflat), _ip(dlens), index_set.encode(), _dp(out), n))
     return out
@@ -260,11 +301,13 @@ def tensorize(inp, dim=None, direction=None, sparse=False, index_set="triangle")
             return np.prod(inp)
         return _tensorize_call(inp, [[i] for i in range(len(inp))], index_set, sparse)
     assert dim is not None and direction is not None
-    a = _d(inp.toarray() if isinstance(inp, ss.csr_matrix) else inp)
+    a = inp if isinstance(inp, ss.csr_matrix) else _d(inp)
     # tensorize_vec_id / tensorize_mat_id (tensorize.cpp:145-152, 373-381): identity factors elsewhere
-    if a.ndim == 1:
+    if len(a.shape) == 1:
         unit = np.zeros(len(a))
         unit[0] = 1.0
+    elif sparse or isinstance(a, ss.csr_matrix):
+        unit = ss.identity(a.shape[0], format="csr")
     else:
         unit = np.eye(a.shape[0])
     factors = [unit] * dim
@@ -278,17 +321,24 @@ def project(inp, dim, directions, index_set="triangle"):
     sparse = isinstance(inp, ss.csr_matrix)
     if isinstance(inp, list):
         inp = np.asarray(inp, dtype=float)
-    a = _d(inp.toarray() if sparse else inp)
     dirs = _i(directions)
-    degree = iterator_get_degree(dim, a.shape[0], index_set)
+    degree = iterator_get_degree(dim, inp.shape[0], index_set)
     n = iterator_size(len(dirs), degree, index_set)
+    if sparse:      # stored entries in, stored entries out (project.cpp:78-109)
+        indptr, indices, data = _csr_arrays(inp)
+        with _SP_LOCK:
+            rows, nnz = C.c_longlong(0), C.c_longlong(0)
+            check(lib().hb_project_mat_sp(indptr.ctypes.data_as(_lib.c_llp), _ip(indices), _dp(data), inp.shape[0], int(dim),
+                                          _ip(dirs), len(dirs), index_set.encode(), C.byref(rows), C.byref(nnz)))
+            return _fetch_csr(n, n, nnz.value)
+    a = _d(inp)
     if a.ndim == 1:
         out = np.zeros(n)
         check(lib().hb_project_vec(_dp(a), len(a), int(dim), _ip(dirs), len(dirs), index_set.encode(), _dp(out), n))
         return out
     out = np.zeros((n, n))
     check(lib().hb_project_mat(_dp(a), a.shape[0], int(dim), _ip(dirs), len(dirs), index_set.encode(), _dp(out), n))
-    return ss.csr_matrix(out) if sparse else out
+    return out
 
 
 def inner(s1, s2, d1, d2, index_set="triangle"):

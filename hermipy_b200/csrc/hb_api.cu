@@ -102,10 +102,10 @@ int cached_plan(hb_plan** out, int dim, const int* n_pts, int degree, const doub
 std::mutex g_call_mutex;
 DevBuf g_in, g_out, g_stage, g_stage_coef, g_aux[HB_MAX_FACTORS], g_auxi[HB_MAX_FACTORS];
 
-// last sparse result
-DevBuf g_sp_indptr, g_sp_indices, g_sp_data, g_sp_rownnz;
-long long g_sp_rows = 0, g_sp_nnz = 0;
-std::vector<long long> g_sp_indptr_host;
+// last sparse result of the process (the host-pointer calls are serialised by g_call_mutex; a caller that uses
+// several threads pairs each *_sp call with its hb_sparse_fetch under its own lock, as hermipy_b200/core.py does)
+CsrResult g_sp;
+DevBuf g_sp_rownnz, g_sp_in[3 * HB_MAX_FACTORS], g_sp_lex;
 
 int upload_grid(const hb_plan* pl, const double* f, int batch, double* dst) {
     // flat host->device copy, then re-pitch on the device (a pitched H2D copy of short rows is 2.4x slower)
@@ -572,39 +572,69 @@ int hb_varf(int dim, const int* n_pts, int degree, const double* f, const double
     return HB_OK;
 }
 
+// dense device matrix (n x n, pitch ld) -> g_sp, exact zeros dropped (sparse.cpp:44-58)
+static int compact_dense_to_csr(const double* A, int n, long long ld) {
+    HB_TRY(g_sp_rownnz.ensure((size_t)n * 8));
+    HB_TRY(launch_count_nnz(A, ld, n, n, static_cast<long long*>(g_sp_rownnz.p), 0));
+    std::vector<long long> rn(n), ip(n + 1, 0);
+    HB_CUDA(cudaMemcpyAsync(rn.data(), g_sp_rownnz.p, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    for (int i = 0; i < n; i++) ip[i + 1] = ip[i] + rn[i];
+    g_sp.rows = n;
+    g_sp.nnz = ip[n];
+    HB_TRY(g_sp.indptr.ensure((size_t)(n + 1) * 8));
+    HB_TRY(g_sp.indices.ensure(std::max<size_t>(g_sp.nnz, 1) * 4));
+    HB_TRY(g_sp.data.ensure(std::max<size_t>(g_sp.nnz, 1) * 8));
+    HB_CUDA(cudaMemcpyAsync(g_sp.indptr.p, ip.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(launch_fill_csr(A, ld, n, n, static_cast<long long*>(g_sp.indptr.p), g_sp.indices.i(), g_sp.data.d(), 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
 int hb_varf_sp(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
                const int* do_fourier, const char* index_set, int mode, long long* nnz) {
     std::lock_guard<std::mutex> lock(g_call_mutex);
     hb_plan* pl = nullptr;
-    HB_TRY(varf_to_device(&pl, dim, n_pts, degree, f, nodes, weights, do_fourier, index_set, mode));
-    const int n = (int)pl->n_polys;
-    HB_TRY(g_sp_rownnz.ensure((size_t)n * 8));
-    HB_TRY(launch_count_nnz(g_out.d(), n, n, n, static_cast<long long*>(g_sp_rownnz.p), 0));
-    std::vector<long long> rn(n);
-    HB_CUDA(cudaMemcpyAsync(rn.data(), g_sp_rownnz.p, (size_t)n * 8, cudaMemcpyDeviceToHost, 0));
-    HB_CUDA(cudaStreamSynchronize(0));
-    g_sp_indptr_host.assign(n + 1, 0);
-    for (int i = 0; i < n; i++) g_sp_indptr_host[i + 1] = g_sp_indptr_host[i] + rn[i];
-    g_sp_rows = n;
-    g_sp_nnz = g_sp_indptr_host[n];
-    HB_TRY(g_sp_indptr.ensure((size_t)(n + 1) * 8));
-    HB_TRY(g_sp_indices.ensure(std::max<size_t>(g_sp_nnz, 1) * 4));
-    HB_TRY(g_sp_data.ensure(std::max<size_t>(g_sp_nnz, 1) * 8));
-    HB_CUDA(cudaMemcpyAsync(g_sp_indptr.p, g_sp_indptr_host.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
-    HB_TRY(launch_fill_csr(g_out.d(), n, n, n, static_cast<long long*>(g_sp_indptr.p), g_sp_indices.i(),
-                           g_sp_data.d(), 0));
-    HB_CUDA(cudaStreamSynchronize(0));
-    *nnz = g_sp_nnz;
+    HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
+    HB_TRY(g_in.ensure((size_t)pl->grid_size * 8));
+    HB_TRY(upload_grid(pl, f, 1, g_in.d()));
+    g_sp.rows = -1;
+    // polynomial-like f: the band of retained triple products goes straight to CSR, no n_polys^2 buffer
+    if (mode == HB_VARF_REFERENCE) HB_TRY(plan_varf_csr(pl, g_in.d(), 0, pl->n_polys, g_sp, 0));
+    if (g_sp.rows < 0) {
+        HB_TRY(g_out.ensure((size_t)pl->n_polys * pl->n_polys * 8));
+        HB_TRY(plan_varf(pl, g_in.d(), mode, g_out.d(), pl->n_polys, 0, pl->n_polys, 0));
+        HB_TRY(compact_dense_to_csr(g_out.d(), (int)pl->n_polys, pl->n_polys));
+    }
+    *nnz = g_sp.nnz;
+    return HB_OK;
+}
+
+int hb_plan_varf_sp(hb_plan* plan, const double* d_f, int mode, long long row_begin, long long row_end, long long* nnz,
+                    void* stream) {
+    if (!plan || !nnz) return HB_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (row_begin < 0) row_begin = 0;
+    if (row_end > plan->n_polys) row_end = plan->n_polys;
+    g_sp.rows = -1;
+    if (mode == HB_VARF_REFERENCE) HB_TRY(plan_varf_csr(plan, d_f, row_begin, row_end, g_sp, st));
+    if (g_sp.rows < 0) {
+        set_error("hb_plan_varf_sp: f is not polynomial-like (no narrow band of retained triple products); assemble the "
+                  "dense row block with hb_plan_varf");
+        return HB_ERR_INVALID;
+    }
+    *nnz = g_sp.nnz;
     return HB_OK;
 }
 
 int hb_sparse_fetch(long long* indptr, int* indices, double* data) {
     std::lock_guard<std::mutex> lock(g_call_mutex);
-    if (g_sp_rows <= 0) { set_error("hb_sparse_fetch: no sparse result"); return HB_ERR_INVALID; }
-    memcpy(indptr, g_sp_indptr_host.data(), (size_t)(g_sp_rows + 1) * 8);
-    if (g_sp_nnz) {
-        HB_CUDA(cudaMemcpy(indices, g_sp_indices.p, (size_t)g_sp_nnz * 4, cudaMemcpyDeviceToHost));
-        HB_CUDA(cudaMemcpy(data, g_sp_data.p, (size_t)g_sp_nnz * 8, cudaMemcpyDeviceToHost));
+    if (g_sp.rows < 0) { set_error("hb_sparse_fetch: no sparse result"); return HB_ERR_INVALID; }
+    HB_CUDA(cudaMemcpy(indptr, g_sp.indptr.p, (size_t)(g_sp.rows + 1) * 8, cudaMemcpyDeviceToHost));
+    if (g_sp.nnz) {
+        HB_CUDA(cudaMemcpy(indices, g_sp.indices.p, (size_t)g_sp.nnz * 4, cudaMemcpyDeviceToHost));
+        HB_CUDA(cudaMemcpy(data, g_sp.data.p, (size_t)g_sp.nnz * 8, cudaMemcpyDeviceToHost));
     }
     return HB_OK;
 }
@@ -774,6 +804,152 @@ int hb_project_vec(const double* input, size_t len, int dim, const int* dirs, in
 int hb_project_mat(const double* input, size_t n, int dim, const int* dirs, int n_dirs, const char* index_set,
                    double* out, size_t n_out) {
     return project_impl(input, n, dim, dirs, n_dirs, index_set, true, out, n_out);
+}
+
+// ---- CSR inputs, CSR result (no dense intermediate) -----------------------------------------------------
+static int upload_csr(int slot, int n, const long long* indptr, const int* indices, const double* data) {
+    const long long nnz = indptr[n];
+    HB_TRY(g_sp_in[3 * slot].ensure((size_t)(n + 1) * 8));
+    HB_TRY(g_sp_in[3 * slot + 1].ensure(std::max<size_t>(nnz, 1) * 4));
+    HB_TRY(g_sp_in[3 * slot + 2].ensure(std::max<size_t>(nnz, 1) * 8));
+    HB_CUDA(cudaMemcpyAsync(g_sp_in[3 * slot].p, indptr, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, 0));
+    if (nnz) {
+        HB_CUDA(cudaMemcpyAsync(g_sp_in[3 * slot + 1].p, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, 0));
+        HB_CUDA(cudaMemcpyAsync(g_sp_in[3 * slot + 2].p, data, (size_t)nnz * 8, cudaMemcpyHostToDevice, 0));
+    }
+    return HB_OK;
+}
+
+int hb_tensorize_mats_sp(int k, const long long* const* indptr, const int* const* indices, const double* const* data,
+                         const int* sizes, const int* dirs_flat, const int* dir_lens, const char* index_set,
+                         long long* n_out, long long* nnz) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    if (k < 1 || k > HB_MAX_FACTORS) { set_error("tensorize: between 1 and %d factors supported", HB_MAX_FACTORS); return HB_ERR_INVALID; }
+    int dim = 0;
+    std::vector<std::vector<int>> dirs(k);
+    for (int j = 0, off = 0; j < k; j++) {
+        dirs[j].assign(dirs_flat + off, dirs_flat + off + dir_lens[j]);
+        off += dir_lens[j];
+        dim += dir_lens[j];
+    }
+    std::vector<char> seen(dim, 0);
+    for (auto& dj : dirs)
+        for (int v : dj) {
+            if (v < 0 || v >= dim) { set_error("Missing direction, exiting ..."); return HB_ERR_INVALID; }
+            if (seen[v]) { set_error("The same direction appears twice, exiting ..."); return HB_ERR_INVALID; }
+            seen[v] = 1;
+        }
+    int degree = 0;
+    if (index_get_degree(set, dir_lens[0], sizes[0], &degree)) {
+        set_error("Can't find a degree with %d polynomials in dimension %d", sizes[0], dir_lens[0]);
+        return HB_ERR_DEGREE;
+    }
+    auto full = get_index_set(set, dim, degree);
+    if (!full) return HB_ERR_INVALID;
+    // strides of the lexicographic box of the full set (axis 0 slowest)
+    std::vector<long long> stride(dim, 1);
+    for (int a = dim - 2; a >= 0; a--) stride[a] = stride[a + 1] * full->extent[a + 1];
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    SpTensorizeArgs a;
+    a.k = k; a.n_out = (int)full->size;
+    for (int j = 0; j < k; j++) {
+        auto sub = get_index_set(set, dir_lens[j], degree);
+        if (!sub || (int)sub->size != sizes[j]) {
+            set_error("Size of input does not match dimension! Expected dimension: %u Actual dimension: %d",
+                      sub ? sub->size : 0u, sizes[j]);
+            return HB_ERR_INVALID;
+        }
+        HB_TRY(upload_csr(j, sizes[j], indptr[j], indices[j], data[j]));
+        std::vector<int> map = restriction_map(*full, dirs[j], *sub);
+        std::vector<long long> col_lex(sub->size, 0);
+        for (uint32_t c = 0; c < sub->size; c++)
+            for (int i = 0; i < dir_lens[j] && col_lex[c] >= 0; i++) {
+                const uint32_t v = sub->list[(size_t)c * dir_lens[j] + i];
+                // a component beyond the bounding box of the full set (the rectangle sets differ per axis): no such column
+                if (v >= full->extent[dirs[j][i]]) col_lex[c] = -1;
+                else col_lex[c] += (long long)v * stride[dirs[j][i]];
+            }
+        HB_TRY(g_auxi[j].ensure(map.size() * 4));
+        HB_TRY(g_aux[j].ensure(col_lex.size() * 8));
+        HB_CUDA(cudaMemcpyAsync(g_auxi[j].p, map.data(), map.size() * 4, cudaMemcpyHostToDevice, 0));
+        HB_CUDA(cudaMemcpyAsync(g_aux[j].p, col_lex.data(), col_lex.size() * 8, cudaMemcpyHostToDevice, 0));
+        HB_CUDA(cudaStreamSynchronize(0));   // temporaries
+        a.indptr[j] = static_cast<const long long*>(g_sp_in[3 * j].p);
+        a.indices[j] = g_sp_in[3 * j + 1].i();
+        a.data[j] = g_sp_in[3 * j + 2].d();
+        a.map[j] = g_auxi[j].i();
+        a.col_lex[j] = static_cast<const long long*>(g_aux[j].p);
+    }
+    HB_TRY(g_sp_lex.ensure(full->lex_to_pos.size() * 4));
+    HB_CUDA(cudaMemcpyAsync(g_sp_lex.p, full->lex_to_pos.data(), full->lex_to_pos.size() * 4, cudaMemcpyHostToDevice, 0));
+    a.lex_to_pos = g_sp_lex.i();
+    HB_TRY(tensorize_csr(a, g_sp, 0));
+    *n_out = g_sp.rows;
+    *nnz = g_sp.nnz;
+    return HB_OK;
+}
+
+int hb_project_mat_sp(const long long* indptr, const int* indices, const double* data, size_t n_in, int dim,
+                      const int* dirs, int n_dirs, const char* index_set, long long* n_out, long long* nnz) {
+    HB_TRY(check_device());
+    const int set = set_or_err(index_set);
+    if (set < 0) return HB_ERR_INDEX_SET;
+    if (n_dirs < 1 || n_dirs > dim) return HB_ERR_INVALID;
+    int degree = 0;
+    if (index_get_degree(set, dim, (long long)n_in, &degree)) {
+        set_error("Can't find a degree with %zu polynomials in dimension %d", n_in, dim);
+        return HB_ERR_DEGREE;
+    }
+    auto full = get_index_set(set, dim, degree);
+    auto sub = get_index_set(set, n_dirs, degree);
+    if (!full || !sub) return HB_ERR_INVALID;
+    // position in the sub-set of every ALIGNED multi-index of the full set (zero outside dirs), -1 otherwise
+    std::vector<int> to_sub(full->size, -1);
+    std::vector<uint32_t> m(dim);
+    for (uint32_t i = 0; i < sub->size; i++) {
+        std::fill(m.begin(), m.end(), 0u);
+        for (int j = 0; j < n_dirs; j++) {
+            if (dirs[j] < 0 || dirs[j] >= dim) return HB_ERR_INVALID;
+            m[dirs[j]] = sub->list[(size_t)i * n_dirs + j];
+        }
+        const int p = full->position(m.data());
+        if (p >= 0) to_sub[p] = (int)i;
+    }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(upload_csr(0, (int)n_in, indptr, indices, data));
+    HB_TRY(g_auxi[0].ensure(to_sub.size() * 4));
+    HB_CUDA(cudaMemcpyAsync(g_auxi[0].p, to_sub.data(), to_sub.size() * 4, cudaMemcpyHostToDevice, 0));
+    HB_TRY(relabel_csr((int)n_in, indptr[n_in], static_cast<const long long*>(g_sp_in[0].p), g_sp_in[1].i(), g_sp_in[2].d(),
+                       g_auxi[0].i(), g_auxi[0].i(), nullptr, sub->size, g_sp, 0));
+    *n_out = g_sp.rows;
+    *nnz = g_sp.nnz;
+    return HB_OK;
+}
+
+int hb_varfd_sp(int dim, int degree, int direction, const long long* indptr, const int* indices, const double* data,
+                size_t n_polys, int do_fourier, const char* index_set, long long* nnz) {
+    HB_TRY(check_device());
+    std::vector<int> src;
+    std::vector<double> fac;
+    HB_TRY(varfd_column_map(dim, degree, direction, n_polys, do_fourier, index_set, src, fac));
+    // forward form of the map: stored column c of the input lands in column dst[c] with the factor of that column
+    const int n = (int)n_polys;
+    std::vector<int> dst(n, -1);
+    std::vector<double> dfac(n, 0.0);
+    for (int j = 0; j < n; j++)
+        if (src[j] >= 0) { dst[src[j]] = j; dfac[src[j]] = fac[j]; }
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    HB_TRY(upload_csr(0, n, indptr, indices, data));
+    HB_TRY(g_auxi[0].ensure((size_t)n * 4));
+    HB_TRY(g_aux[0].ensure((size_t)n * 8));
+    HB_CUDA(cudaMemcpyAsync(g_auxi[0].p, dst.data(), (size_t)n * 4, cudaMemcpyHostToDevice, 0));
+    HB_CUDA(cudaMemcpyAsync(g_aux[0].p, dfac.data(), (size_t)n * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(relabel_csr(n, indptr[n], static_cast<const long long*>(g_sp_in[0].p), g_sp_in[1].i(), g_sp_in[2].d(), nullptr,
+                       g_auxi[0].i(), g_aux[0].d(), n, g_sp, 0));
+    *nnz = g_sp.nnz;
+    return HB_OK;
 }
 
 int hb_inner(const double* s1, size_t n1, const double* s2, size_t n2, const int* dirs1, int nd1, const int* dirs2,

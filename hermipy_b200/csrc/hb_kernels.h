@@ -84,6 +84,9 @@ struct VarfBandArgs {
     long long width_total;    // prod (2*amax+1)
     const int* lut_box;       // padded lexicographic box -> position (-1 absent)
 };
+struct CsrResult;
+// the band of launch_varf_band as a CSR result (rows relative to a.row_begin), no dense matrix (hb_sparse.cu)
+int varf_band_csr(const VarfSparseArgs& a, const VarfBandArgs& b, CsrResult& out, cudaStream_t s);
 int launch_varf_band(const VarfSparseArgs& a, const VarfBandArgs& b, double* out, cudaStream_t s,
                      bool zero_filled = false);   // zero_filled: the caller has already cleared the rows
 

@@ -1035,8 +1035,11 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
 }
 
 // The reference's algebra (varf.cpp:164-269).
+// `csr` != nullptr: sparse output.  When the retained alpha leave a narrow band the band is emitted straight as CSR
+// (csr->rows = number of owned rows) and d_out is not touched; otherwise csr->rows = -1 and nothing has been
+// assembled (the caller falls back to a dense assembly + compaction).
 static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long long ldo, long long row_begin,
-                          long long row_end, cudaStream_t st) {
+                          long long row_end, cudaStream_t st, CsrResult* csr = nullptr) {
     const int d = pl->dim, N = pl->degree;
     HB_TRY(ensure_triple_products(pl, st));
     // Hf = transform at degree 2N on the same kind of index set (varf.cpp:181)
@@ -1061,7 +1064,7 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     // starts now on a side stream and the band kernel waits for it.  (A wrong guess only costs the wait.)
     const long long fill_rows = row_end - row_begin;
     static const bool early_fill_enabled = [] { const char* e = getenv("HB_VARF_EARLY_FILL"); return !(e && e[0] == '0'); }();
-    const bool early_fill = early_fill_enabled && pl->last_path == 2 && fill_rows > 0;
+    const bool early_fill = early_fill_enabled && pl->last_path == 2 && fill_rows > 0 && csr == nullptr;
     if (early_fill) {
         if (!pl->fill_stream) {
             HB_CUDA(cudaStreamCreateWithFlags(&pl->fill_stream, cudaStreamNonBlocking));
@@ -1111,6 +1114,8 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     const int n_kept = (int)kept_val.size();
     pl->last_n_kept = n_kept;
     const bool dense = (d == 2 && n_kept > 96);
+    if (csr) csr->rows = -1;
+    if (csr && dense) return HB_OK;
     pl->last_path = dense ? 1 : 0;
     if (dense) {
         const int E0 = (int)p2->iset->extent[0], E1 = (int)p2->iset->extent[1];
@@ -1173,10 +1178,22 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     if (b.width_total * 4 <= pl->n_polys) {
         b.width_total = 1;
         for (int k = 0; k < d; k++) b.width_total *= 2 * b.amax[k] + 1;
+        if (csr) return varf_band_csr(a, b, *csr, st);
         pl->last_path = 2;
         return launch_varf_band(a, b, d_out, st, /*zero_filled=*/early_fill);
     }
+    if (csr) return HB_OK;   // no narrow band: dense assembly + compaction
     return launch_varf_sparse(a, d_out, st);
+}
+
+int plan_varf_csr(hb_plan* pl, const double* d_f, long long row_begin, long long row_end, CsrResult& out, cudaStream_t st) {
+    out.rows = -1;
+    if (row_begin < 0) row_begin = 0;
+    if (row_end > pl->n_polys) row_end = pl->n_polys;
+    if (row_end <= row_begin) return HB_OK;
+    HB_TRY(ensure_varf_tables(pl, st));
+    pl->n_timed = 0;
+    return varf_reference(pl, d_f, nullptr, pl->n_polys, row_begin, row_end, st, &out);
 }
 
 int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,

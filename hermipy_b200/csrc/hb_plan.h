@@ -76,6 +76,28 @@ struct Axis {
     bool cpar_tables = false;
 };
 
+// A device-resident CSR result and the scratch it is built from (hb_sparse.cu): candidates (keys = row << 32 | column,
+// ~0 dropped; vals), their sorted copies (keys_sorted; data doubles as the value array of the result), indptr (int64,
+// rows + 1), indices (int32).
+struct CsrResult {
+    DevBuf keys, vals, keys_sorted, data, indices, indptr, offsets, temp, scalars;
+    long long rows = -1, nnz = 0;
+};
+int csr_from_candidates(long long n_rows, long long n_cand, CsrResult& out, cudaStream_t st);
+struct SpTensorizeArgs {
+    int k, n_out;
+    const long long* indptr[8];
+    const int* indices[8];
+    const double* data[8];
+    const int* map[8];            // full-set position -> row of factor j
+    const long long* col_lex[8];  // column of factor j -> its contribution to the lexicographic box offset
+    const int* lex_to_pos;        // box offset -> position in the full set (-1 outside)
+};
+int tensorize_csr(const SpTensorizeArgs& a, CsrResult& out, cudaStream_t st);
+int relabel_csr(int n_rows_in, long long nnz_in, const long long* indptr, const int* indices, const double* data,
+                const int* row_map, const int* col_map, const double* col_fac, long long n_rows_out, CsrResult& out,
+                cudaStream_t st);
+
 }  // namespace hb
 
 struct hb_plan {
@@ -128,6 +150,9 @@ int plan_forward(hb_plan* pl, const double* d_f, long long f_stride, int batch, 
                  long long coef_stride, cudaStream_t st);
 int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int batch, double* d_f,
                   long long f_stride, cudaStream_t st);
+// reference-algebra varf as CSR without a dense matrix when the retained alpha leave a narrow band (polynomial f);
+// out.rows = -1 when they do not (nothing assembled: use plan_varf + a compaction)
+int plan_varf_csr(hb_plan* pl, const double* d_f, long long row_begin, long long row_end, CsrResult& out, cudaStream_t st);
 int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
               long long row_end, cudaStream_t st);
 int ensure_triple_products(hb_plan* pl, cudaStream_t st);

@@ -115,6 +115,23 @@ class Plan:
                                  out.stride(0), row_begin, row_end, _stream()))
         return out
 
+    def varf_sparse(self, f, row_begin=0, row_end=None, fetch=True):
+        """Rows [row_begin,row_end) of the reference-algebra varf of a polynomial-like f as a scipy CSR matrix (rows
+        relative to row_begin), assembled from the band of retained triple products: no n_polys^2 buffer.  Row sharding
+        of a sparse matrix = one call per rank with its own range.  fetch=False returns only nnz (timing)."""
+        import scipy.sparse as ss
+        row_end = self.n_polys if row_end is None else row_end
+        nnz = C.c_longlong(0)
+        check(lib().hb_plan_varf_sp(self._h, f.data_ptr(), 0, row_begin, row_end, C.byref(nnz), _stream()))
+        if not fetch:
+            return nnz.value
+        rows = row_end - row_begin
+        indptr = np.zeros(rows + 1, dtype=np.int64)
+        indices = np.zeros(max(nnz.value, 1), dtype=np.int32)
+        data = np.zeros(max(nnz.value, 1))
+        check(lib().hb_sparse_fetch(indptr.ctypes.data_as(_lib.c_llp), indices.ctypes.data_as(c_ip), data.ctypes.data_as(c_dp)))
+        return ss.csr_matrix((data[:nnz.value], indices[:nnz.value], indptr), shape=(rows, self.n_polys))
+
     def discretize(self, body, translation=None, dilation=None, out=None):
         """Evaluate the C expression `body` (in v[i]) on this plan's grid, directly in device layout."""
         out = self.empty_grid(1)[0] if out is None else out

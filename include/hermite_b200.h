@@ -95,10 +95,26 @@ int hb_varf(int dim, const int* n_pts, int degree, const double* f, const double
             const int* do_fourier, const char* index_set, int mode, double* out, size_t n_polys);
 /* reference: varf_sp(...) -> sparse_matrix + row_col_val (module.cpp:102,133; sparse.cpp:28-43).
  * Two-step: hb_varf_sp computes and returns nnz; hb_sparse_fetch copies the CSR arrays of the last
- * sparse result of this thread (indptr has n_rows+1 entries). */
+ * sparse result of this process (indptr has n_rows+1 entries).  For polynomial-like f (few retained alpha: a
+ * narrow band of triple products per row) the band is emitted straight as CSR -- no n_polys^2 buffer, no
+ * zero-fill; otherwise the dense matrix is assembled on the device and compacted. */
 int hb_varf_sp(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
                const int* do_fourier, const char* index_set, int mode, long long* nnz);
 int hb_sparse_fetch(long long* indptr, int* indices, double* data);
+/* Sparse in, sparse out: the spmat instantiations of the reference (tensorize.cpp:197-283 folded over the factors
+ * :286-332; project.cpp:78-109; varfd varf.cpp:290-376).  Inputs are CSR triplets (indptr int64 with n+1 entries,
+ * indices int32, data); the result is CSR with sorted columns and exact zeros dropped (sparse.cpp:52), left on the
+ * device like the result of hb_varf_sp: *nnz (and *n_out, its number of rows) are returned, hb_sparse_fetch copies
+ * it out.  Work and memory are proportional to the stored entries, never to n_polys^2.
+ * The sparse result is ONE per process ("last result"): pair each call with its hb_sparse_fetch under a lock when
+ * several host threads use the library. */
+int hb_tensorize_mats_sp(int k, const long long* const* indptr, const int* const* indices, const double* const* data,
+                         const int* sizes, const int* dirs_flat, const int* dir_lens, const char* index_set,
+                         long long* n_out, long long* nnz);
+int hb_project_mat_sp(const long long* indptr, const int* indices, const double* data, size_t n_polys, int dim,
+                      const int* dirs, int n_dirs, const char* index_set, long long* n_out, long long* nnz);
+int hb_varfd_sp(int dim, int degree, int direction, const long long* indptr, const int* indices, const double* data,
+                size_t n_polys, int do_fourier, const char* index_set, long long* nnz);
 /* reference: varfd(dim, degree, direction, var, do_fourier, index_set) (module.cpp:103-104, varf.cpp:290-456) */
 int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_polys, int do_fourier,
              const char* index_set, double* out);
@@ -143,6 +159,11 @@ int hb_plan_discretize(hb_plan* plan, const char* body, const double* translatio
  * (row-major, pitch ldo >= n_polys); row sharding across GPUs = one call per rank with its own range. */
 int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
                  long long row_end, void* cuda_stream);
+/* the owned rows [row_begin,row_end) of the reference-algebra varf as CSR (rows relative to row_begin), for
+ * polynomial-like f only (HB_ERR_INVALID otherwise); result fetched with hb_sparse_fetch.  Row sharding of a
+ * sparse matrix across GPUs = one call per rank with its own range. */
+int hb_plan_varf_sp(hb_plan* plan, const double* d_f, int mode, long long row_begin, long long row_end,
+                    long long* nnz, void* cuda_stream);
 /* device-side timing (CUDA events on the launch stream) of every GEMM launch of the last hb_plan_*
  * call, for roofline reporting.  tag: 1+axis forward stage, 11+axis backward stage, 21/22 varf stage
  * 1/2; padded_flops = 2*M*N*K*batch the launch was asked for (table padding included). */
