@@ -68,6 +68,14 @@ SIGNATURES = {
                                C.c_size_t]),
     "hb_transform_batch": (C.c_int, [C.c_int, c_ip, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_char_p,
                                      c_dp, C.c_size_t]),
+    "hb_transform_weighted": (C.c_int, [C.c_int, c_ip, C.c_int, C.c_int, c_dp, C.c_char_p, C.c_char_p, c_dp, c_dp, c_dp,
+                                        c_dp, c_ip, C.c_char_p, c_dp, C.c_size_t]),
+    "hb_eval_weighted": (C.c_int, [C.c_int, c_ip, C.c_int, c_dp, C.c_size_t, c_dp, c_dp, c_dp, C.c_char_p, c_dp, c_dp, c_ip,
+                                   C.c_char_p, c_dp, C.c_size_t]),
+    "hb_varf_function": (C.c_int, [C.c_int, c_ip, C.c_int, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_char_p, C.c_int,
+                                   c_dp, C.c_size_t]),
+    "hb_varf_function_sp": (C.c_int, [C.c_int, c_ip, C.c_int, C.c_char_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_char_p,
+                                      C.c_int, c_llp]),
     "hb_integrate": (C.c_int, [C.c_int, c_ip, c_dp, c_dp, c_dp, c_ip, c_dp]),
     "hb_triple_products": (C.c_int, [C.c_int, c_dp]),
     "hb_triple_products_fourier": (C.c_int, [C.c_int, c_dp]),

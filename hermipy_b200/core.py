@@ -179,6 +179,70 @@ def transform_batch(degree, fgrids, nodes, weights, forward, do_fourier=None, in
     return out
 
 
+def transform_weighted(degree, function, factor, nodes, weights, translation, dilation, do_fourier=None,
+                       index_set="triangle"):
+    """Coefficients of function / factor (hermipy/quad.py:287-306) in ONE device pass: `function` is a grid array
+    (one function, or a batch of shape (batch, n_points)) or a C expression in v[i]; `factor` a C expression or None;
+    expressions are evaluated on the device at translation + dilation @ node, the division
+    f / (factor == 0 ? 1e-300 : factor) is a device kernel, and only the inputs and the coefficients cross PCIe."""
+    n_pts, nd, wt = _grid(nodes, weights)
+    dim = len(n_pts)
+    n_grid = int(np.prod(n_pts))
+    n_polys = iterator_size(dim, int(degree), index_set)
+    tr, di = _d(translation).ravel(), _d(dilation).reshape(dim, dim)
+    fac = None if factor is None else str(factor).encode()
+    if isinstance(function, str):
+        f_arr, f_body, batch, single = None, function.encode(), 1, True
+    else:
+        f_arr = _d(function)
+        single = f_arr.size == n_grid and (f_arr.ndim != 2 or f_arr.shape[0] != 1 or n_grid == 1)
+        f_arr = f_arr.reshape(-1, n_grid)
+        f_body, batch = None, f_arr.shape[0]
+    out = np.zeros((batch, n_polys))
+    check(lib().hb_transform_weighted(dim, _ip(n_pts), int(degree), batch, None if f_arr is None else _dp(f_arr), f_body,
+                                      fac, _dp(nd), _dp(wt), _dp(tr), _dp(di), _ip(_fourier(do_fourier, dim)),
+                                      index_set.encode(), _dp(out), n_polys))
+    return out[0] if single else out
+
+
+def eval_weighted(degree, coeffs, factor, eval_nodes, nodes, weights, translation, dilation, do_fourier=None,
+                  index_set="triangle"):
+    """Values of a series on `eval_nodes` times `factor` (a C expression, or None) evaluated on `nodes` at
+    translation + dilation @ node (hermipy/quad.py:316-328), without leaving the device in between."""
+    n_pts, nd, wt = _grid(nodes, weights)
+    dim = len(n_pts)
+    ev = _d(np.concatenate([_d(n).ravel() for n in eval_nodes]))
+    c = _d(coeffs).ravel()
+    tr, di = _d(translation).ravel(), _d(dilation).reshape(dim, dim)
+    out = np.zeros(int(np.prod(n_pts)))
+    check(lib().hb_eval_weighted(dim, _ip(n_pts), int(degree), _dp(c), len(c), _dp(ev), _dp(nd), _dp(wt),
+                                 None if factor is None else str(factor).encode(), _dp(tr), _dp(di),
+                                 _ip(_fourier(do_fourier, dim)), index_set.encode(), _dp(out), out.size))
+    return out
+
+
+def varf_function(degree, function, nodes, weights, translation, dilation, sparse=False, do_fourier=None,
+                  index_set="triangle", mode="reference"):
+    """core.varf of a function given as a C expression in v[i]: evaluated on the device grid, never on the host."""
+    n_pts, nd, wt = _grid(nodes, weights)
+    dim = len(n_pts)
+    degree = int(degree)
+    n = iterator_size(dim, degree, index_set)
+    tr, di = _d(translation).ravel(), _d(dilation).reshape(dim, dim)
+    four = _fourier(do_fourier, dim)
+    body = str(function).encode()
+    if not sparse:
+        out = np.zeros((n, n))
+        check(lib().hb_varf_function(dim, _ip(n_pts), degree, body, _dp(tr), _dp(di), _dp(nd), _dp(wt), _ip(four),
+                                     index_set.encode(), VARF_MODE[mode], _dp(out), n))
+        return out
+    with _SP_LOCK:
+        nnz = C.c_longlong(0)
+        check(lib().hb_varf_function_sp(dim, _ip(n_pts), degree, body, _dp(tr), _dp(di), _dp(nd), _dp(wt), _ip(four),
+                                        index_set.encode(), VARF_MODE[mode], C.byref(nnz)))
+        return _fetch_csr(n, n, nnz.value)
+
+
 def triple_products(degree):
     out = np.zeros((2 * degree + 1, degree + 1, degree + 1))
     check(lib().hb_triple_products(int(degree), _dp(out)))
@@ -358,7 +422,8 @@ def inner(s1, s2, d1, d2, index_set="triangle"):
 def _decorate():
     from .cache import cache
     from .stats import debug, log_stats
-    names = ("discretize", "integrate", "transform", "triple_products", "triple_products_fourier", "varf", "varfd",
+    names = ("discretize", "integrate", "transform", "transform_weighted", "eval_weighted", "varf_function",
+             "triple_products", "triple_products_fourier", "varf", "varfd",
              "tensorize", "project", "inner", "iterator_get_degree", "iterator_index", "iterator_size",
              "iterator_list_indices")
     for name in names:

@@ -122,6 +122,25 @@ int upload_grid(const hb_plan* pl, const double* f, int batch, double* dst) {
     return HB_OK;
 }
 
+// body evaluated at translation + dilation @ node on the plan's grid, into the padded device layout
+int plan_discretize(hb_plan* plan, const char* body, const double* translation, const double* dilation, double* d_f,
+                    cudaStream_t st) {
+    if (!plan->nodes_cat.p) {   // nodes of all axes, concatenated on the device (built on first use)
+        size_t tot = 0;
+        for (const Axis& A : plan->ax) tot += A.n;
+        HB_TRY(plan->nodes_cat.ensure(tot * 8));
+        size_t off = 0;
+        for (const Axis& A : plan->ax) {
+            HB_CUDA(cudaMemcpyAsync(plan->nodes_cat.d() + off, A.x.p, (size_t)A.n * 8, cudaMemcpyDeviceToDevice, st));
+            off += A.n;
+        }
+    }
+    std::vector<int> n_pts;
+    for (const Axis& A : plan->ax) n_pts.push_back(A.n);
+    return discretize_device(body, plan->dim, n_pts.data(), plan->nodes_cat.d(), translation, dilation, d_f,
+                             plan->ax[plan->dim - 1].np, st);
+}
+
 int set_or_err(const char* index_set) {
     const int set = index_set_from_name(index_set);
     if (set < 0) set_error("Invalid index set!");
@@ -495,6 +514,77 @@ int hb_transform(int dim, const int* n_pts, int degree, const double* f, const d
     return hb_transform_batch(dim, n_pts, degree, 1, f, nodes, weights, do_fourier, forward, index_set, out, out_len);
 }
 
+// ---- the object API's transform / eval / varf without host arithmetic or extra PCIe trips ------------------
+// (reference: hermipy/quad.py:287-342.  There the function and the factor of the quadrature are discretised, divided
+// or multiplied with NumPy on the host, and only then handed to the C++ transform.)
+int hb_transform_weighted(int dim, const int* n_pts, int degree, int batch, const double* f, const char* f_body,
+                          const char* factor_body, const double* nodes, const double* weights, const double* translation,
+                          const double* dilation, const int* do_fourier, const char* index_set, double* out,
+                          size_t out_len_each) {
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    hb_plan* pl = nullptr;
+    HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
+    if (batch < 1) return HB_OK;
+    if ((f == nullptr) == (f_body == nullptr) || (f_body && batch != 1)) {
+        set_error("transform_weighted: give grid values OR one expression");
+        return HB_ERR_INVALID;
+    }
+    if (out_len_each != (size_t)pl->n_polys) { set_error("transform_weighted: out_len %zu != n_polys %lld", out_len_each, pl->n_polys); return HB_ERR_INVALID; }
+    const long long gs = pl->grid_size, cs = even_up(pl->n_polys);
+    HB_TRY(g_in.ensure((size_t)batch * gs * 8));
+    HB_TRY(g_out.ensure((size_t)batch * cs * 8));
+    if (f) {
+        HB_TRY(upload_grid(pl, f, batch, g_in.d()));
+    } else {
+        HB_CUDA(cudaMemsetAsync(g_in.p, 0, (size_t)gs * 8, 0));
+        HB_TRY(plan_discretize(pl, f_body, translation, dilation, g_in.d(), 0));
+    }
+    if (factor_body) {
+        HB_TRY(g_aux[0].ensure((size_t)gs * 8));
+        HB_CUDA(cudaMemsetAsync(g_aux[0].p, 0, (size_t)gs * 8, 0));
+        HB_TRY(plan_discretize(pl, factor_body, translation, dilation, g_aux[0].d(), 0));
+        HB_TRY(launch_pointwise(0, g_in.d(), gs, g_aux[0].d(), g_in.d(), gs, gs, batch, 0));
+    }
+    HB_TRY(plan_forward(pl, g_in.d(), gs, batch, g_out.d(), cs, 0));
+    HB_CUDA(cudaMemcpy2DAsync(out, (size_t)pl->n_polys * 8, g_out.p, (size_t)cs * 8, (size_t)pl->n_polys * 8, batch,
+                              cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
+int hb_eval_weighted(int dim, const int* n_pts, int degree, const double* coeffs, size_t n_polys, const double* eval_nodes,
+                     const double* nodes, const double* weights, const char* factor_body, const double* translation,
+                     const double* dilation, const int* do_fourier, const char* index_set, double* out, size_t out_len) {
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    hb_plan* pl = nullptr;
+    HB_TRY(cached_plan(&pl, dim, n_pts, degree, eval_nodes, weights, do_fourier, index_set));
+    const Axis& L = pl->ax[dim - 1];
+    const long long gs = pl->grid_size, n_grid = pl->grid_rows * L.n;
+    if (n_polys != (size_t)pl->n_polys || out_len != (size_t)n_grid) {
+        set_error("eval_weighted: %zu coefficients / %zu values, expected %lld / %lld", n_polys, out_len, pl->n_polys, n_grid);
+        return HB_ERR_INVALID;
+    }
+    HB_TRY(g_in.ensure((size_t)even_up(pl->n_polys) * 8));
+    HB_TRY(g_out.ensure((size_t)gs * 8));
+    HB_CUDA(cudaMemcpyAsync(g_in.p, coeffs, n_polys * 8, cudaMemcpyHostToDevice, 0));
+    HB_TRY(plan_backward(pl, g_in.d(), even_up(pl->n_polys), 1, g_out.d(), gs, 0));
+    if (factor_body) {
+        // the factor lives on the quadrature's OWN nodes (the plan above sits on the mapped nodes of the series)
+        size_t tot = 0;
+        for (int a = 0; a < dim; a++) tot += n_pts[a];
+        HB_TRY(g_aux[1].ensure(tot * 8));
+        HB_TRY(g_aux[0].ensure((size_t)gs * 8));
+        HB_CUDA(cudaMemcpyAsync(g_aux[1].p, nodes, tot * 8, cudaMemcpyHostToDevice, 0));
+        HB_CUDA(cudaMemsetAsync(g_aux[0].p, 0, (size_t)gs * 8, 0));
+        HB_TRY(discretize_device(factor_body, dim, n_pts, g_aux[1].d(), translation, dilation, g_aux[0].d(), L.np, 0));
+        HB_TRY(launch_pointwise(1, g_out.d(), gs, g_aux[0].d(), g_out.d(), gs, gs, 1, 0));
+    }
+    HB_CUDA(cudaMemcpy2DAsync(out, (size_t)L.n * 8, g_out.p, (size_t)L.np * 8, (size_t)L.n * 8, (size_t)pl->grid_rows,
+                              cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+
 int hb_integrate(int dim, const int* n_pts, const double* f, const double* nodes, const double* weights,
                  const int* do_fourier, double* result) {
     // transform.cpp:170-181: degree-0 triangle transform, times sqrt(2 pi) per Fourier axis
@@ -550,14 +640,22 @@ static int triple_products_impl(int degree, bool fourier, double* out) {
 int hb_triple_products(int degree, double* out) { return triple_products_impl(degree, false, out); }
 int hb_triple_products_fourier(int degree, double* out) { return triple_products_impl(degree, true, out); }
 
+// grid values of the varf argument on the device: uploaded, or evaluated from an expression (no host round trip)
+static int varf_input(hb_plan* pl, const double* f, const char* f_body, const double* translation, const double* dilation) {
+    HB_TRY(g_in.ensure((size_t)pl->grid_size * 8));
+    if (f) return upload_grid(pl, f, 1, g_in.d());
+    HB_CUDA(cudaMemsetAsync(g_in.p, 0, (size_t)pl->grid_size * 8, 0));
+    return plan_discretize(pl, f_body, translation, dilation, g_in.d(), 0);
+}
+
 static int varf_to_device(hb_plan** plp, int dim, const int* n_pts, int degree, const double* f, const double* nodes,
-                          const double* weights, const int* do_fourier, const char* index_set, int mode) {
+                          const double* weights, const int* do_fourier, const char* index_set, int mode,
+                          const char* f_body = nullptr, const double* translation = nullptr, const double* dilation = nullptr) {
     hb_plan* pl = nullptr;
     HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
     *plp = pl;
-    HB_TRY(g_in.ensure((size_t)pl->grid_size * 8));
     HB_TRY(g_out.ensure((size_t)pl->n_polys * pl->n_polys * 8));
-    HB_TRY(upload_grid(pl, f, 1, g_in.d()));
+    HB_TRY(varf_input(pl, f, f_body, translation, dilation));
     return plan_varf(pl, g_in.d(), mode, g_out.d(), pl->n_polys, 0, pl->n_polys, 0);
 }
 
@@ -591,13 +689,43 @@ static int compact_dense_to_csr(const double* A, int n, long long ld) {
     return HB_OK;
 }
 
+static int varf_sp_impl(int dim, const int* n_pts, int degree, const double* f, const char* f_body,
+                        const double* translation, const double* dilation, const double* nodes, const double* weights,
+                        const int* do_fourier, const char* index_set, int mode, long long* nnz);
+
 int hb_varf_sp(int dim, const int* n_pts, int degree, const double* f, const double* nodes, const double* weights,
                const int* do_fourier, const char* index_set, int mode, long long* nnz) {
+    return varf_sp_impl(dim, n_pts, degree, f, nullptr, nullptr, nullptr, nodes, weights, do_fourier, index_set, mode, nnz);
+}
+
+/* varf of a function given as an expression in v[i] (evaluated on the device at translation + dilation @ node):
+ * what Quad.varf('expr') needs, without discretising on the host first (quad.py:308-328) */
+int hb_varf_function(int dim, const int* n_pts, int degree, const char* f_body, const double* translation,
+                     const double* dilation, const double* nodes, const double* weights, const int* do_fourier,
+                     const char* index_set, int mode, double* out, size_t n_polys) {
+    if (!f_body) return HB_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    hb_plan* pl = nullptr;
+    HB_TRY(varf_to_device(&pl, dim, n_pts, degree, nullptr, nodes, weights, do_fourier, index_set, mode, f_body, translation, dilation));
+    if (n_polys != (size_t)pl->n_polys) { set_error("varf: n_polys %zu != %lld", n_polys, pl->n_polys); return HB_ERR_INVALID; }
+    HB_CUDA(cudaMemcpyAsync(out, g_out.p, n_polys * n_polys * 8, cudaMemcpyDeviceToHost, 0));
+    HB_CUDA(cudaStreamSynchronize(0));
+    return HB_OK;
+}
+int hb_varf_function_sp(int dim, const int* n_pts, int degree, const char* f_body, const double* translation,
+                        const double* dilation, const double* nodes, const double* weights, const int* do_fourier,
+                        const char* index_set, int mode, long long* nnz) {
+    if (!f_body) return HB_ERR_INVALID;
+    return varf_sp_impl(dim, n_pts, degree, nullptr, f_body, translation, dilation, nodes, weights, do_fourier, index_set, mode, nnz);
+}
+
+static int varf_sp_impl(int dim, const int* n_pts, int degree, const double* f, const char* f_body,
+                        const double* translation, const double* dilation, const double* nodes, const double* weights,
+                        const int* do_fourier, const char* index_set, int mode, long long* nnz) {
     std::lock_guard<std::mutex> lock(g_call_mutex);
     hb_plan* pl = nullptr;
     HB_TRY(cached_plan(&pl, dim, n_pts, degree, nodes, weights, do_fourier, index_set));
-    HB_TRY(g_in.ensure((size_t)pl->grid_size * 8));
-    HB_TRY(upload_grid(pl, f, 1, g_in.d()));
+    HB_TRY(varf_input(pl, f, f_body, translation, dilation));
     g_sp.rows = -1;
     // polynomial-like f: the band of retained triple products goes straight to CSR, no n_polys^2 buffer
     if (mode == HB_VARF_REFERENCE) HB_TRY(plan_varf_csr(pl, g_in.d(), 0, pl->n_polys, g_sp, 0));
@@ -1040,22 +1168,7 @@ int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long
 
 int hb_plan_discretize(hb_plan* plan, const char* body, const double* translation, const double* dilation,
                        double* d_f, void* stream) {
-    // nodes of all axes, concatenated on the device (built on first use)
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!plan->nodes_cat.p) {
-        size_t tot = 0;
-        for (const Axis& A : plan->ax) tot += A.n;
-        HB_TRY(plan->nodes_cat.ensure(tot * 8));
-        size_t off = 0;
-        for (const Axis& A : plan->ax) {
-            HB_CUDA(cudaMemcpyAsync(plan->nodes_cat.d() + off, A.x.p, (size_t)A.n * 8, cudaMemcpyDeviceToDevice, st));
-            off += A.n;
-        }
-    }
-    std::vector<int> n_pts;
-    for (const Axis& A : plan->ax) n_pts.push_back(A.n);
-    return discretize_device(body, plan->dim, n_pts.data(), plan->nodes_cat.d(), translation, dilation, d_f,
-                             plan->ax[plan->dim - 1].np, st);
+    return plan_discretize(plan, body, translation, dilation, d_f, static_cast<cudaStream_t>(stream));
 }
 int hb_plan_set_timing(hb_plan* plan, int on) { plan->timing = on != 0; plan->n_timed = 0; return HB_OK; }
 int hb_plan_timing_count(const hb_plan* plan) { return plan->n_timed; }

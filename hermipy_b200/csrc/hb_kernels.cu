@@ -773,6 +773,31 @@ int launch_inner(const double* s1, const double* s2, const int* ind1, const int*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weighting / scaling steps of the object API (reference: hermipy/quad.py:287-328, NumPy on the host there), batch
+// rows of `n` entries against ONE factor row: op 0  out = a / (b == 0 ? 1e-300 : b)   (quad.py:299: the factor of the
+// quadrature divides the function before the transform; 1e-300 stands in where the factor underflowed), op 1
+// out = a * b (quad.py:328).  Same IEEE operations as the NumPy expressions, so the results are bit-identical.
+__global__ void pointwise_kernel(int op, const double* __restrict__ a, long long a_stride, const double* __restrict__ b,
+                                 double* __restrict__ out, long long o_stride, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double bv = b[i];
+    const double av = a[(long long)blockIdx.y * a_stride + i];
+    out[(long long)blockIdx.y * o_stride + i] = op == 0 ? __ddiv_rn(av, bv == 0.0 ? 1e-300 : bv) : __dmul_rn(av, bv);
+}
+int launch_pointwise(int op, const double* a, long long a_stride, const double* b, double* out, long long o_stride,
+                     long long n, int batch, cudaStream_t s) {
+    if (n <= 0 || batch <= 0) return HB_OK;
+    for (int b0 = 0; b0 < batch; b0 += kMaxGridY) {
+        const int nb = batch - b0 < kMaxGridY ? batch - b0 : kMaxGridY;
+        dim3 grid((unsigned)cdiv(n, 256), nb);
+        pointwise_kernel<<<grid, 256, 0, s>>>(op, a + (long long)b0 * a_stride, a_stride, b, out + (long long)b0 * o_stride,
+                                             o_stride, n);
+    }
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Dense -> CSR compaction (exact zeros dropped, as the reference's to_spmat does, sparse.cpp:44-58).
 __global__ void count_nnz_kernel(const double* __restrict__ A, long long ld, int n_cols, long long* row_nnz) {
     const int r = blockIdx.x;

@@ -62,6 +62,9 @@ int launch_tensorize(const TensorizeArgs& a, bool matrices, double* out, int n_o
 int launch_project(const double* in, int n_in, const int* sel, bool matrix, double* out, int n_out, cudaStream_t s);
 int launch_varfd(const double* var, long long ldv, const int* src, const double* fac, double* out, long long ldo,
                  int rows, int n, cudaStream_t s);
+// out[b][i] = a[b][i] / (f[i] == 0 ? 1e-300 : f[i]) (op 0) or a[b][i] * f[i] (op 1): weighting steps of the object API
+int launch_pointwise(int op, const double* a, long long a_stride, const double* b, double* out, long long o_stride,
+                     long long n, int batch, cudaStream_t s);
 // y = A x for a row-major M x N matrix resident in HBM (hb_matvec.cu)
 int launch_matvec(int M, int N, const double* A, long long lda, const double* x, double* y, cudaStream_t s);
 

@@ -233,12 +233,16 @@ class Quad:
     @stats.log_stats()
     def transform(self, function, degree, index_set="triangle", significant=0, tensorize=None):
         """Forward transform: coefficients of function / factor in the basis of this quadrature."""
+        # one device pass: the function (unless given as grid values) and the factor are evaluated on the GPU grid,
+        # divided there and transformed; only the coefficients come back (hermipy/quad.py:287-306 does these steps
+        # with NumPy on the host)
         if not isinstance(function, np.ndarray):
-            function = self.discretize(Function(function, dirs=self.position.dirs))
-        factor = self.discretize(self.factor)
-        mapped = function / (1e-300 * (factor == 0) + factor)
-        coeffs = core.transform(degree, mapped, self.nodes, self.weights, forward=True,
-                                do_fourier=self.do_fourier, index_set=index_set)
+            function = Function(function, dirs=self.position.dirs).ccode()
+        else:
+            function = np.asarray(function, float).ravel()
+        coeffs = core.transform_weighted(degree, function, self.factor.ccode(), self.nodes, self.weights,
+                                         self.position.mean, self.position.factor, do_fourier=self.do_fourier,
+                                         index_set=index_set)
         return Series(coeffs, self.position, factor=self.factor, index_set=index_set, significant=significant)
 
     def transform_batch(self, functions, degree, index_set="triangle"):
@@ -246,10 +250,10 @@ class Quad:
         call; returns a list of Series.  No reference equivalent (the reference loops in Python)."""
         functions = np.asarray(functions, float)
         functions = functions.reshape(functions.shape[0], -1)
-        factor = self.discretize(self.factor)
-        mapped = functions / (1e-300 * (factor == 0) + factor)
-        coeffs = core.transform_batch(degree, mapped, self.nodes, self.weights, True,
-                                      do_fourier=self.do_fourier, index_set=index_set)
+        coeffs = core.transform_weighted(degree, functions, self.factor.ccode(), self.nodes, self.weights,
+                                         self.position.mean, self.position.factor, do_fourier=self.do_fourier,
+                                         index_set=index_set)
+        coeffs = np.atleast_2d(coeffs)
         return [Series(c, self.position, factor=self.factor, index_set=index_set) for c in coeffs]
 
     def eval(self, series):
@@ -263,9 +267,10 @@ class Quad:
         if la.norm(scaling - np.diag(np.diag(scaling)), 2) > 1e-8:
             raise ValueError("Incompatible covariance matrices")
         mapped_nodes = [np.asarray(n) * scaling[i][i] + translation[i] for i, n in enumerate(self.nodes)]
-        values = core.transform(series.degree, series.coeffs, mapped_nodes, self.weights, forward=False,
-                                do_fourier=self.do_fourier, index_set=series.index_set)
-        return values * self.discretize(series.factor)
+        factor = series.factor if isinstance(series.factor, Function) else Function(series.factor, dirs=self.position.dirs)
+        return core.eval_weighted(series.degree, series.coeffs, factor.ccode(), mapped_nodes, self.nodes, self.weights,
+                                  self.position.mean, self.position.factor, do_fourier=self.do_fourier,
+                                  index_set=series.index_set)
 
     @tensorize_at(1)
     @stats.debug()
@@ -274,6 +279,13 @@ class Quad:
         """Matrix of the multiplication operator u -> f u in the basis of this quadrature.  `resident=True`
         leaves the (dense) matrix in HBM and returns a `ResidentVarf` (hermipy_b200/resident.py)."""
         sparse = settings['sparse'] if sparse is None else sparse
+        if not isinstance(f_grid, np.ndarray) and not resident:
+            # the expression is evaluated on the device grid and assembled there: no grid values cross PCIe
+            f = f_grid if isinstance(f_grid, Function) else Function(f_grid, dirs=self.position.dirs)
+            matrix = core.varf_function(degree, f.ccode(), self.nodes, self.weights, self.position.mean,
+                                        self.position.factor, sparse=sparse, do_fourier=self.do_fourier,
+                                        index_set=index_set)
+            return Varf(matrix, self.position, factor=self.factor, index_set=index_set)
         if not isinstance(f_grid, np.ndarray):
             f_grid = self.discretize(f_grid)
         if resident:

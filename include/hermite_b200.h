@@ -115,6 +115,28 @@ int hb_project_mat_sp(const long long* indptr, const int* indices, const double*
                       const int* dirs, int n_dirs, const char* index_set, long long* n_out, long long* nnz);
 int hb_varfd_sp(int dim, int degree, int direction, const long long* indptr, const int* indices, const double* data,
                 size_t n_polys, int do_fourier, const char* index_set, long long* nnz);
+/* The object API's transform / eval / varf in ONE call each, so that the weighting steps run as device kernels and
+ * nothing but the inputs and the result crosses PCIe (reference: hermipy/quad.py:287-342, where the function and the
+ * factor of the quadrature are discretised, divided / multiplied with NumPy and only then handed to hermite_cpp).
+ * Expressions are C in v[i] (Function.ccode()), evaluated at translation + dilation @ node.
+ *   hb_transform_weighted: coefficients of  f / factor  (f: batch grid functions on the host, or ONE expression;
+ *                          factor_body may be NULL = 1; the division is f / (factor == 0 ? 1e-300 : factor), quad.py:299)
+ *   hb_eval_weighted:      values of the series on eval_nodes (the quadrature's nodes mapped into the frame of the
+ *                          series) times the factor evaluated on the quadrature's own nodes (quad.py:316-328)
+ *   hb_varf_function[_sp]: hb_varf[_sp] of an expression */
+int hb_transform_weighted(int dim, const int* n_pts, int degree, int batch, const double* f, const char* f_body,
+                          const char* factor_body, const double* nodes, const double* weights, const double* translation,
+                          const double* dilation, const int* do_fourier, const char* index_set, double* out,
+                          size_t out_len_each);
+int hb_eval_weighted(int dim, const int* n_pts, int degree, const double* coeffs, size_t n_polys, const double* eval_nodes,
+                     const double* nodes, const double* weights, const char* factor_body, const double* translation,
+                     const double* dilation, const int* do_fourier, const char* index_set, double* out, size_t out_len);
+int hb_varf_function(int dim, const int* n_pts, int degree, const char* f_body, const double* translation,
+                     const double* dilation, const double* nodes, const double* weights, const int* do_fourier,
+                     const char* index_set, int mode, double* out, size_t n_polys);
+int hb_varf_function_sp(int dim, const int* n_pts, int degree, const char* f_body, const double* translation,
+                        const double* dilation, const double* nodes, const double* weights, const int* do_fourier,
+                        const char* index_set, int mode, long long* nnz);
 /* reference: varfd(dim, degree, direction, var, do_fourier, index_set) (module.cpp:103-104, varf.cpp:290-456) */
 int hb_varfd(int dim, int degree, int direction, const double* var, size_t n_polys, int do_fourier,
              const char* index_set, double* out);

@@ -55,7 +55,51 @@ def _with_variant(fn):
     return call
 
 
+def _grid_points(nodes, translation, dilation):
+    mesh = np.meshgrid(*[np.asarray(n, float) for n in nodes], indexing="ij")
+    pts = np.stack([m.ravel() for m in mesh], axis=1)
+    return np.asarray(translation, float).ravel() + pts @ np.asarray(dilation, float).reshape(len(nodes), len(nodes)).T
+
+
+def _expr(body, nodes, translation, dilation):
+    return ref.discretize(body, nodes, translation, dilation, variant=_VARIANT)
+
+
+def _transform_weighted(degree, function, factor, nodes, weights, translation, dilation, do_fourier=None,
+                        index_set="triangle"):
+    """host restatement of hermipy/quad.py:287-306 on the reference's own transform (test infrastructure)"""
+    n_grid = int(np.prod([len(n) for n in nodes]))
+    if isinstance(function, str):
+        f, single = _expr(function, nodes, translation, dilation)[None], True
+    else:
+        f = np.asarray(function, float)
+        single = f.size == n_grid and (f.ndim != 2 or f.shape[0] != 1 or n_grid == 1)
+        f = f.reshape(-1, n_grid)
+    if factor is not None:
+        fac = _expr(factor, nodes, translation, dilation)
+        f = f / (1e-300 * (fac == 0) + fac)
+    out = np.stack([ref.transform(degree, row, nodes, weights, True, do_fourier=do_fourier, index_set=index_set,
+                                  variant=_VARIANT) for row in f])
+    return out[0] if single else out
+
+
+def _eval_weighted(degree, coeffs, factor, eval_nodes, nodes, weights, translation, dilation, do_fourier=None,
+                   index_set="triangle"):
+    values = ref.transform(degree, coeffs, eval_nodes, weights, False, do_fourier=do_fourier, index_set=index_set,
+                           variant=_VARIANT)
+    return values if factor is None else values * _expr(factor, nodes, translation, dilation)
+
+
+def _varf_function(degree, function, nodes, weights, translation, dilation, sparse=False, do_fourier=None,
+                   index_set="triangle", mode="reference"):
+    return _varf(degree, _expr(function, nodes, translation, dilation), nodes, weights, sparse=sparse,
+                 do_fourier=do_fourier, index_set=index_set)
+
+
 PATCHES = {
+    "transform_weighted": _transform_weighted,
+    "eval_weighted": _eval_weighted,
+    "varf_function": _varf_function,
     "discretize": _with_variant(ref.discretize),
     "integrate": _with_variant(ref.integrate),
     "transform": _with_variant(ref.transform),
