@@ -773,6 +773,40 @@ int launch_inner(const double* s1, const double* s2, const int* ind1, const int*
 }
 
 // ------------------------------------------------------------------------------------------------
+// Last step of the d-dimensional dense varf (d >= 3, hb_plan.cu: varf_dense_nd): the contraction leaves the full
+// pair-space array full[(m_0,n_0)]...[(m_{d-1},n_{d-1})] (pair (m_a, n_a) at m_a * Pp_a + n_a); the matrix entry
+// A[r][c] is the cell addressed by the multi-indices of row r and column c.
+struct VarfGatherArgs {
+    int dim, n_polys, row_begin;
+    int Pp[HB_MAX_DIM];
+    long long stride[HB_MAX_DIM];   // of the pair index of axis a in `full`
+    const int* midx;
+};
+__global__ void varf_gather_nd_kernel(VarfGatherArgs a, const double* __restrict__ full, double* __restrict__ out,
+                                      long long ldo) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = a.row_begin + blockIdx.y;
+    if (c >= a.n_polys) return;
+    long long cell = 0;
+    for (int d = 0; d < a.dim; d++)
+        cell += ((long long)a.midx[(long long)r * a.dim + d] * a.Pp[d] + a.midx[(long long)c * a.dim + d]) * a.stride[d];
+    out[(long long)blockIdx.y * ldo + c] = full[cell];
+}
+int launch_varf_gather_nd(int dim, int n_polys, int row_begin, int row_end, const int* Pp, const long long* stride,
+                          const int* midx, const double* full, double* out, long long ldo, cudaStream_t s) {
+    VarfGatherArgs a;
+    a.dim = dim; a.n_polys = n_polys; a.midx = midx;
+    for (int d = 0; d < dim; d++) { a.Pp[d] = Pp[d]; a.stride[d] = stride[d]; }
+    for (int r0 = row_begin; r0 < row_end; r0 += kMaxGridY) {
+        const int nr = row_end - r0 < kMaxGridY ? row_end - r0 : kMaxGridY;
+        a.row_begin = r0;
+        dim3 grid(cdiv(n_polys, 128), nr);
+        varf_gather_nd_kernel<<<grid, 128, 0, s>>>(a, full, out + (long long)(r0 - row_begin) * ldo, ldo);
+    }
+    return launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weighting / scaling steps of the object API (reference: hermipy/quad.py:287-328, NumPy on the host there), batch
 // rows of `n` entries against ONE factor row: op 0  out = a / (b == 0 ? 1e-300 : b)   (quad.py:299: the factor of the
 // quadrature divides the function before the transform; 1e-300 stands in where the factor underflowed), op 1

@@ -62,6 +62,9 @@ int launch_tensorize(const TensorizeArgs& a, bool matrices, double* out, int n_o
 int launch_project(const double* in, int n_in, const int* sel, bool matrix, double* out, int n_out, cudaStream_t s);
 int launch_varfd(const double* var, long long ldv, const int* src, const double* fac, double* out, long long ldo,
                  int rows, int n, cudaStream_t s);
+// A[r][c] = full[sum_a (m_a(r) * Pp_a + n_a(c)) * stride_a]  (d-dimensional dense varf, last step)
+int launch_varf_gather_nd(int dim, int n_polys, int row_begin, int row_end, const int* Pp, const long long* stride,
+                          const int* midx, const double* full, double* out, long long ldo, cudaStream_t s);
 // out[b][i] = a[b][i] / (f[i] == 0 ? 1e-300 : f[i]) (op 0) or a[b][i] * f[i] (op 1): weighting steps of the object API
 int launch_pointwise(int op, const double* a, long long a_stride, const double* b, double* out, long long o_stride,
                      long long n, int batch, cudaStream_t s);

@@ -973,11 +973,83 @@ static int varf_dense_2d(hb_plan* pl, const double* coef, long long ld_coef, int
     return rc;
 }
 
+// Dense varf in d >= 3 dimensions: the contraction  A = sum_k in[k_0..k_{d-1}] prod_a tab_a[k_a][(m_a, n_a)]  taken one
+// axis at a time, last axis first -- d GEMM launches on the FP64 tensor cores -- into the full pair-space array
+// full[(m_0,n_0)]..[(m_{d-1},n_{d-1})], from which the rows of the matrix are gathered.  `in` is the grid function
+// (Gram form: k = nodes, tables psi_m psi_n) or the box of retained transform coefficients (reference algebra,
+// varf.cpp:236-262: k = alpha, tables T[alpha][m][n]); tab[a] is [K_a][C_a] with C_a = P_a * Pp_a.  The pair space
+// holds prod P_a^2 cells -- n_polys^2 for the cube, (d!)^2 times that for a triangle -- so this path is for the
+// moderate degrees d >= 3 is used at (checked against the memory that is free).
+static int varf_dense_nd(hb_plan* pl, const double* in, long long in_ld, const int* K, const double* const* tab,
+                         const long long* tab_ld, const int* Pp, double* d_out, long long ldo, long long row_begin, long long row_end,
+                         cudaStream_t st) {
+    const int d = pl->dim, L = d - 1;
+    long long C[HB_MAX_DIM] = {0}, in_rows = 1;
+    for (int a = 0; a < d; a++) C[a] = (long long)pl->ax[a].P * Pp[a];
+    for (int a = 0; a < L; a++) in_rows *= K[a];
+    // largest intermediate: [K_0..K_{a-1}][C_a..C_{d-1}]
+    long long need = 0, sz = in_rows * C[L];
+    need = sz;
+    for (int a = L - 1; a >= 0; a--) { sz = sz / K[a] * C[a]; need = std::max(need, sz); }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t have = pl->ws[0].bytes + pl->ws[1].bytes;
+    if ((double)need * 16.0 > (double)free_b + (double)have - 1e9) {
+        set_error("varf (dim %d, degree %d): the pair space of the dense assembly needs 2 x %.1f GB", d, pl->degree, need * 8e-9);
+        return HB_ERR_NOMEM;
+    }
+    HB_TRY(pl->ws[0].ensure((size_t)need * 8));
+    HB_TRY(pl->ws[1].ensure((size_t)need * 8));
+    {
+        GemmArgs g;
+        g.M = (int)in_rows; g.K = K[L]; g.N = (int)C[L];
+        g.A = in; g.lda = in_ld;
+        g.B = tab[L]; g.ldb = tab_ld[L];
+        g.C = pl->ws[0].d(); g.ldc = C[L];
+        HB_TRY(timed_gemm(pl, g, 21, st));
+    }
+    int cur = 0;
+    long long prefix = in_rows, cols = C[L];
+    for (int a = L - 1; a >= 0; a--) {
+        prefix /= K[a];
+        GemmArgs g;
+        g.M = (int)C[a]; g.K = K[a]; g.N = (int)cols; g.batch = (int)prefix;
+        g.A = tab[a]; g.lda = tab_ld[a]; g.a_mmajor = true; g.strideA = 0;
+        g.B = pl->ws[cur].d(); g.ldb = cols; g.strideB = (long long)K[a] * cols;
+        g.C = pl->ws[cur ^ 1].d(); g.ldc = cols; g.strideC = C[a] * cols;
+        HB_TRY(timed_gemm(pl, g, 22, st));
+        cols *= C[a];
+        cur ^= 1;
+    }
+    long long stride[HB_MAX_DIM];
+    stride[L] = 1;
+    for (int a = L - 1; a >= 0; a--) stride[a] = stride[a + 1] * C[a + 1];
+    return launch_varf_gather_nd(d, (int)pl->n_polys, (int)row_begin, (int)row_end, Pp, stride, pl->midx.i(),
+                                 pl->ws[cur].d(), d_out, ldo, st);
+}
+
 static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ldo, long long row_begin,
                      long long row_end, cudaStream_t st) {
     if (pl->dim > 2) {
-        set_error("HB_VARF_GRAM supports dim <= 2 (got %d)", pl->dim);
-        return HB_ERR_INVALID;
+        // psi_m psi_n tables per axis (psi = sqrt(w) phi: overflow-free), then d GEMM stages + gather
+        const int d = pl->dim;
+        int K[HB_MAX_DIM], Pp[HB_MAX_DIM];
+        long long tab_ld[HB_MAX_DIM];
+        const double* tab[HB_MAX_DIM];
+        if (pl->pairN.size() != (size_t)d) pl->pairN.resize(d);
+        for (int a = 0; a < d; a++) {
+            Axis& A = pl->ax[a];
+            if (!A.psi.p) {
+                HB_TRY(A.psi.ensure_zero((size_t)A.n * A.Pp * 8, st));
+                HB_TRY(launch_psi_table(A.x.d(), A.w.d(), A.n, A.P, A.fourier, A.psi.d(), A.Pp, st));
+            }
+            if (!pl->pairN[a].p) {
+                HB_TRY(pl->pairN[a].ensure((size_t)A.n * A.P * A.Pp * 8));
+                HB_TRY(launch_pair_table(A.psi.d(), A.Pp, nullptr, A.n, A.P, A.Pp, pl->pairN[a].d(), st));
+            }
+            K[a] = A.n; Pp[a] = A.Pp; tab[a] = pl->pairN[a].d(); tab_ld[a] = (long long)A.P * A.Pp;
+        }
+        return varf_dense_nd(pl, d_f, pl->ax[d - 1].np, K, tab, tab_ld, Pp, d_out, ldo, row_begin, row_end, st);
     }
     // pair products are formed from psi = sqrt(w) phi (overflow-free), not from w * phi * phi
     for (Axis& A : pl->ax) {
@@ -1116,6 +1188,43 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     const bool dense = (d == 2 && n_kept > 96);
     if (csr) csr->rows = -1;
     if (csr && dense) return HB_OK;
+    // d >= 3 with many alpha kept: the same contraction, one GEMM per axis on the triple-product tables, when its pair
+    // space fits (the one-thread-per-entry kernel below walks every kept alpha for every entry)
+    const char* nd_gemm = getenv("HB_VARF_ND_GEMM");      // developer switch (tests compare the two assemblies)
+    if (d >= 3 && n_kept > 96 && !csr && !(nd_gemm && nd_gemm[0] == '0')) {
+        bool hermite_only = true;
+        double cells = 1;
+        for (int a = 0; a < d; a++) {
+            hermite_only = hermite_only && !pl->ax[a].fourier;
+            cells *= (double)pl->ax[a].P * pl->TPp;
+        }
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (hermite_only && cells * 16.0 < (double)free_b * 0.5) {
+            std::vector<long long> ext(d);
+            long long box = 1;
+            for (int a = 0; a < d; a++) ext[a] = (long long)p2->iset->extent[a];
+            const long long ld_last = even_up(ext[d - 1]);
+            for (int a = 0; a + 1 < d; a++) box *= ext[a];
+            std::vector<double> Hc((size_t)(box * ld_last), 0.0);
+            for (int t = 0; t < n_kept; t++) {
+                long long cell = 0;
+                for (int a = 0; a < d; a++) cell = cell * (a == d - 1 ? ld_last : ext[a]) + kept_alpha[(size_t)t * d + a];
+                Hc[(size_t)cell] = kept_val[t];
+            }
+            HB_TRY(pl->Hc.ensure(Hc.size() * 8));
+            HB_CUDA(cudaMemcpyAsync(pl->Hc.p, Hc.data(), Hc.size() * 8, cudaMemcpyHostToDevice, st));
+            HB_CUDA(cudaStreamSynchronize(st));
+            int K[HB_MAX_DIM], Pp[HB_MAX_DIM];
+            long long tab_ld[HB_MAX_DIM];
+            const double* tab[HB_MAX_DIM];
+            for (int a = 0; a < d; a++) {
+                K[a] = (int)ext[a]; Pp[a] = pl->TPp; tab[a] = pl->T.d(); tab_ld[a] = (long long)(N + 1) * pl->TPp;
+            }
+            pl->last_path = 3;
+            return varf_dense_nd(pl, pl->Hc.d(), ld_last, K, tab, tab_ld, Pp, d_out, ldo, row_begin, row_end, st);
+        }
+    }
     pl->last_path = dense ? 1 : 0;
     if (dense) {
         const int E0 = (int)p2->iset->extent[0], E1 = (int)p2->iset->extent[1];

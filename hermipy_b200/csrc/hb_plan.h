@@ -120,6 +120,7 @@ struct hb_plan {
     int Tdeg = -1, TPp = 0;
     hb::DevBuf T, Tf;           // triple products [2N+1][N+1][TPp] (Hermite / Fourier)
     hb::DevBuf midx, blkpos, blkperm, blkperm2, blkrange, Hf, Hc, G, kept_alpha, kept_val, pair[2], tmp;
+    std::vector<hb::DevBuf> pairN;  // d >= 3 Gram varf: psi_m psi_n per axis, [n_a][P_a * Pp_a]
     hb::DevBuf pairB[2], TB[2];     // blocked pair tables (dim 2 dense varf): Gram / triple products per axis
     hb::DevBuf fsplit;              // even / odd parts of f along axis 0 (parity-halved Gram contraction)
     bool pairB_ok[2] = {false, false}, TB_ok[2] = {false, false};

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C ABI, via hermipy_b200.core) against the
 compiled reference (oracle/_ref) on identical seeded inputs.  Tolerances: 1e-12 norm-wise relative
 for FP64 results (BASELINE.json north_star), bit-exact for index maps."""
+import os
+
 import numpy as np
 import pytest
 
@@ -489,3 +491,56 @@ def test_transform_batch_respects_strides_and_padding(force_transform_parity):
     plan.backward(coef[:, :plan.coef_stride], grid[:, :plan.grid_size])
     hg = grid.cpu().numpy()
     assert (hg[:, plan.grid_size:] == sentinel).all() and (hg[:, :37] != sentinel).all()
+
+
+def test_varf_3d_dense_gram_and_many_alpha(core, ref):
+    """Dense varf in three dimensions (varf.cpp:164-269 is dimension-generic): the Gram form of a non-polynomial f
+    against 80-bit quadrature sums; for a polynomial f the Gram form, the reference algebra and the reference agree to
+    1e-12; a smooth f that keeps many alpha takes the GEMM-per-axis path of the reference algebra (path 3) and agrees
+    with the one-thread-per-entry assembly."""
+    import torch
+    from hermipy_b200.plan import Plan
+    n, deg = 18, 12
+    x, w = gauss_hermite(n)
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    nodes, weights = [x] * 3, [w] * 3
+    for index_set in ("triangle", "cube"):
+        d = deg if index_set == "triangle" else 5
+        idx = core.iterator_list_indices(3, d, index_set)
+        # non-polynomial f, Gram form, against extended-precision sums on sampled entries
+        E = np.exp(-(X ** 2 + Y ** 2 + Z ** 2) / 9) * (1 + 0.3 * X * Z)
+        G = core.varf(d, E, nodes, weights, index_set=index_set, mode="gram")
+        xl, wl = x.astype(np.longdouble), w.astype(np.longdouble)
+        phi = np.zeros((n, d + 1), dtype=np.longdouble)
+        phi[:, 0] = 1
+        if d > 0:
+            phi[:, 1] = xl
+        for k in range(1, d):
+            phi[:, k + 1] = (xl * phi[:, k] - np.sqrt(np.longdouble(k)) * phi[:, k - 1]) / np.sqrt(np.longdouble(k + 1))
+        El = E.astype(np.longdouble)
+        rng = np.random.default_rng(8)
+        scale = np.abs(G).max()
+        for r, c in zip(rng.integers(0, len(idx), 40), rng.integers(0, len(idx), 40)):
+            a, b = idx[r], idx[c]
+            t0, t1, t2 = (wl * phi[:, a[0]] * phi[:, b[0]]), (wl * phi[:, a[1]] * phi[:, b[1]]), (wl * phi[:, a[2]] * phi[:, b[2]])
+            exact = float(np.einsum("i,j,k,ijk->", t0, t1, t2, El))
+            assert abs(G[r, c] - exact) <= 1e-12 * scale, (index_set, r, c)
+        assert np.array_equal(G, G.T) or rel_err(G, G.T) <= 1e-15
+        # polynomial f: Gram == reference algebra == reference
+        V = X * X * Y - Z ** 2 + 0.5 * X * Z + 1
+        want = ref.varf(d, V, nodes, weights, index_set=index_set)
+        assert rel_err(core.varf(d, V, nodes, weights, index_set=index_set, mode="gram"), want) <= 1e-12
+        assert rel_err(core.varf(d, V, nodes, weights, index_set=index_set), want) <= 1e-12
+    # many alpha kept in the reference algebra: GEMM-per-axis path against the entry-wise assembly of the same algebra
+    plan = Plan(5, nodes, weights, index_set="triangle")
+    f = plan.pack_grid(np.exp(-(X ** 2 + Y ** 2 + Z ** 2) / 30 + 0.2 * X + 0.1 * Y - 0.15 * Z)[None])[0]
+    A = plan.varf(f, "reference").cpu().numpy()
+    kept, path = plan.varf_info()
+    assert kept > 96 and path == 3
+    os.environ["HB_VARF_ND_GEMM"] = "0"
+    try:
+        B = plan.varf(f, "reference").cpu().numpy()
+        assert plan.varf_info()[1] == 0
+    finally:
+        os.environ.pop("HB_VARF_ND_GEMM")
+    assert rel_err(A, B) <= 1e-12
