@@ -685,12 +685,31 @@ def bench_c2(ctx):
            "h2d_bytes_per_step": world * 8 * B * (n * n + n_polys), "d2h_bytes_per_step": world * 8 * B * (n * n + n_polys),
            "api": "hermipy_b200.core.transform_batch (hb_transform_batch: host buffers, copies inside)",
            "cpu_affinity": numa_note}
+    # the same forward transforms through the OBJECT API a user of the reference calls -- Quad.transform_batch on
+    # pageable NumPy arrays (rank 0 only; forward only: the reference has no batched eval)
+    obj = None
+    if rank == 0:
+        import hermipy_b200 as hm
+        quad = hm.Quad([x, x], [w, w])
+        F_page = np.array(F_host.reshape(B, -1))          # ordinary (pageable) memory
+        quad.transform_batch(F_page, C2["degree"], index_set=C2["index_set"])
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            series = quad.transform_batch(F_page, C2["degree"], index_set=C2["index_set"])
+        dt = (time.perf_counter() - t0) / reps
+        err = float(np.linalg.norm(series[0].coeffs - Ch[0]) / np.linalg.norm(Ch[0]))
+        obj = {"value": B * n * n / dt * 1e-9, "unit": "Gpts/s (forward only)", "ms_per_call": dt * 1e3,
+               "h2d_bytes_per_call": 8 * B * n * n, "d2h_bytes_per_call": 8 * B * n_polys,
+               "api": "hermipy_b200.Quad.transform_batch (pageable NumPy input; factor evaluated and divided on the "
+                      "device: hb_transform_weighted), list of Series out",
+               "rel_diff_vs_core_transform_batch": err}
     os.sched_setaffinity(0, old_affinity)
     out = {"workload": "2-D forward+inverse, degree %d per axis (%s set), %d x %d grid, batch of %d functions per GPU"
                        % (C2["degree"], C2["index_set"], n, n, B),
            "scaling": "weak (replicas: a single 2-D transform does not shard)", "launch": how,
            "ms": total_ms / K, "gpts": value, "launches_per_step": launches_per_step, "roofline": roofline,
-           "e2e": e2e, "roundtrip_rel_err": rt}
+           "e2e": e2e, "e2e_object_api": obj, "roundtrip_rel_err": rt}
     if not args.skip_varf:
         out["varf"] = bench_c2_varf(ctx, plan, x, w, X, Y)
     if world == 1 and not args.skip_cpu:
@@ -824,12 +843,14 @@ def bench_c3(torch, Plan, world, rank, flush, barrier, max_over_ranks, peak):
     contraction) of a dense non-polynomial f.  One GPU: the triangle set (80 601^2 doubles = 52 GB).  N >= 2 GPUs:
     the cube set (160 801^2 = 207 GB), row-sharded, never gathered (each rank keeps its row block)."""
     from hermipy_b200.dist import split_range
-    x, w = gauss_hermite(C3["n_rule"])
-    keep = w > 0                                  # outer weights underflow in double precision
-    x, w = x[keep], w[keep]
+    # the nodes of the 801-point rule the degree-400 basis reaches (|x| <= 45.1: 717 of them).  80 of their weights
+    # underflow in double precision (w < 1e-308) while sqrt(w) phi_k is still O(1e-3) there: the plan gets sqrt(w) in
+    # extended range, without which the rows above degree ~290 come out wrong (DESIGN.md 4.3)
+    from hermipy_b200.lib import gram_rule
+    x, w, sw = gram_rule(C3["n_rule"], C3["degree"])
     n = len(x)
     set_name = "triangle" if world == 1 else "cube"
-    plan = Plan(C3["degree"], [x, x], [w, w], index_set=set_name)
+    plan = Plan(C3["degree"], [x, x], [w, w], index_set=set_name, sqrt_weights=[sw, sw])
     npol = plan.n_polys
     lo, hi = split_range(npol, world, rank)
     X, Y = np.meshgrid(x, x, indexing="ij")
@@ -855,7 +876,7 @@ def bench_c3(torch, Plan, world, rank, flush, barrier, max_over_ranks, peak):
         k = 4096
         sym = float((out[:k, :k] - out[:k, :k].T).abs().max().item())
     res = {"workload": "2-D Galerkin varf assembly, degree %d per axis, %s set: %d x %d dense (%.0f GB)%s, Gram form of a "
-                       "dense f on %d x %d nodes (w > 0 subset of the %d-point rule)"
+                       "dense f on %d x %d nodes (the part of the %d-point rule the basis reaches; sqrt(w) in extended range)"
                        % (C3["degree"], set_name, npol, npol, 8e-9 * npol ** 2,
                           "" if world == 1 else ", row-sharded over %d GPUs" % world, n, n, C3["n_rule"]),
            "scaling": "strong", "assembly_ms": ms, "algorithmic_tflop": survey_flops * 1e-12,

@@ -86,6 +86,7 @@ SIGNATURES = {
                                        C.c_char_p, c_llp, c_llp]),
     "hb_project_mat_sp": (C.c_int, [c_llp, c_ip, c_dp, C.c_size_t, C.c_int, c_ip, C.c_int, C.c_char_p, c_llp, c_llp]),
     "hb_varfd_sp": (C.c_int, [C.c_int, C.c_int, C.c_int, c_llp, c_ip, c_dp, C.c_size_t, C.c_int, C.c_char_p, c_llp]),
+    "hb_plan_set_sqrt_weights": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "hb_plan_varf_sp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, c_llp, C.c_void_p]),
     "hb_varfd": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, C.c_size_t, C.c_int, C.c_char_p, c_dp]),
     "hb_tensorize_vecs": (C.c_int, [C.c_int, C.POINTER(c_dp), c_ip, c_ip, c_ip, C.c_char_p, c_dp, C.c_size_t]),

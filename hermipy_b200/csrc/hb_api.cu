@@ -1170,6 +1170,11 @@ int hb_plan_discretize(hb_plan* plan, const char* body, const double* translatio
                        double* d_f, void* stream) {
     return plan_discretize(plan, body, translation, dilation, d_f, static_cast<cudaStream_t>(stream));
 }
+int hb_plan_set_sqrt_weights(hb_plan* plan, int axis, const double* sqrt_w) {
+    if (!plan) return HB_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    return plan_set_sqrt_weights(plan, axis, sqrt_w);
+}
 int hb_plan_set_timing(hb_plan* plan, int on) { plan->timing = on != 0; plan->n_timed = 0; return HB_OK; }
 int hb_plan_timing_count(const hb_plan* plan) { return plan->n_timed; }
 int hb_plan_timing_get(hb_plan* plan, int i, int* tag, double* ms, double* padded_flops) {

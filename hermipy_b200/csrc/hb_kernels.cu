@@ -72,11 +72,14 @@ int launch_basis_tables(const double* x, const double* w, int n, int P, int four
 // rule) where phi alone reaches 1e159 at degree 400 and overflows beyond degree ~780, and the pair products
 // psi_m psi_n = w phi_m phi_n never leave the double range (SURVEY.md findings 4 and 7).  Nodes whose weight
 // underflowed to 0 contribute 0, as in the weighted table of the transform.
-__global__ void psi_table_kernel(const double* __restrict__ x, const double* __restrict__ w, int n, int P, int fourier,
-                                 double* __restrict__ psi, long long ld) {
+// `sw` != nullptr: sqrt(w_i) supplied by the caller in extended range (a weight below 1e-308 underflows to 0 in double
+// precision although its square root -- all the table needs -- is representable while w > 1e-616 and psi_k is O(1) there:
+// at degree 400 the functions live out to |x| ~ 40, where w ~ 1e-348).
+__global__ void psi_table_kernel(const double* __restrict__ x, const double* __restrict__ w, const double* __restrict__ sw,
+                                 int n, int P, int fourier, double* __restrict__ psi, long long ld) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double xi = x[i], s = sqrt(w[i]);
+    const double xi = x[i], s = sw ? sw[i] : sqrt(w[i]);
     double* row = psi + (long long)i * ld;
     if (fourier) {
         row[0] = s / sqrt(2 * M_PI);
@@ -99,9 +102,9 @@ __global__ void psi_table_kernel(const double* __restrict__ x, const double* __r
     }
 }
 
-int launch_psi_table(const double* x, const double* w, int n, int P, int fourier, double* psi, long long ld,
-                     cudaStream_t s) {
-    psi_table_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, n, P, fourier, psi, ld);
+int launch_psi_table(const double* x, const double* w, const double* sw, int n, int P, int fourier, double* psi,
+                     long long ld, cudaStream_t s) {
+    psi_table_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, sw, n, P, fourier, psi, ld);
     return launch_status();
 }
 

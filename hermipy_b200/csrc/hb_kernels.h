@@ -9,8 +9,8 @@ namespace hb {
 
 int launch_basis_tables(const double* x, const double* w, int n, int P, int fourier, double* plain, double* wgt,
                         long long ld_ik, double* plainT, double* wgtT, long long ld_ki, cudaStream_t s);
-int launch_psi_table(const double* x, const double* w, int n, int P, int fourier, double* psi, long long ld,
-                     cudaStream_t s);
+int launch_psi_table(const double* x, const double* w, const double* sqrt_w, int n, int P, int fourier, double* psi,
+                     long long ld, cudaStream_t s);
 int launch_pair_table(const double* plain, long long ld_ik, const double* w, int n, int P, int Pp, double* out,
                       cudaStream_t s);
 int launch_triple_products(int N, int Pp, double* T, cudaStream_t s);

@@ -1041,7 +1041,7 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
             Axis& A = pl->ax[a];
             if (!A.psi.p) {
                 HB_TRY(A.psi.ensure_zero((size_t)A.n * A.Pp * 8, st));
-                HB_TRY(launch_psi_table(A.x.d(), A.w.d(), A.n, A.P, A.fourier, A.psi.d(), A.Pp, st));
+                HB_TRY(launch_psi_table(A.x.d(), A.w.d(), A.sw.p ? A.sw.d() : nullptr, A.n, A.P, A.fourier, A.psi.d(), A.Pp, st));
             }
             if (!pl->pairN[a].p) {
                 HB_TRY(pl->pairN[a].ensure((size_t)A.n * A.P * A.Pp * 8));
@@ -1055,7 +1055,7 @@ static int varf_gram(hb_plan* pl, const double* d_f, double* d_out, long long ld
     for (Axis& A : pl->ax) {
         if (A.psi.p) continue;
         HB_TRY(A.psi.ensure_zero((size_t)A.n * A.Pp * 8, st));
-        HB_TRY(launch_psi_table(A.x.d(), A.w.d(), A.n, A.P, A.fourier, A.psi.d(), A.Pp, st));
+        HB_TRY(launch_psi_table(A.x.d(), A.w.d(), A.sw.p ? A.sw.d() : nullptr, A.n, A.P, A.fourier, A.psi.d(), A.Pp, st));
     }
     if (pl->dim == 1) {
         const Axis& A = pl->ax[0];
@@ -1293,6 +1293,28 @@ static int varf_reference(hb_plan* pl, const double* d_f, double* d_out, long lo
     }
     if (csr) return HB_OK;   // no narrow band: dense assembly + compaction
     return launch_varf_sparse(a, d_out, st);
+}
+
+// Extended-range square roots of the weights of one axis for the Gram-form varf (see psi_table_kernel).  The tables
+// built from the weights so far are dropped.
+int plan_set_sqrt_weights(hb_plan* pl, int axis, const double* sqrt_w) {
+    if (axis < 0 || axis >= pl->dim || !sqrt_w) return HB_ERR_INVALID;
+    Axis& A = pl->ax[axis];
+    for (int i = 0; i < A.n; i++) {
+        if (!(sqrt_w[i] >= 0.0)) { set_error("sqrt_weights: entry %d is negative or NaN", i); return HB_ERR_INVALID; }
+        if (A.symmetric_nodes && sqrt_w[i] != sqrt_w[A.n - 1 - i]) {
+            set_error("sqrt_weights: the axis is bit-symmetric (x_i = -x_{n-1-i}, w_i = w_{n-1-i}); its square roots must be too");
+            return HB_ERR_INVALID;
+        }
+    }
+    HB_TRY(A.sw.ensure((size_t)A.n * 8));
+    HB_CUDA(cudaMemcpy(A.sw.p, sqrt_w, (size_t)A.n * 8, cudaMemcpyHostToDevice));
+    A.psi.release();
+    pl->pairB_ok[0] = pl->pairB_ok[1] = false;
+    pl->pair[0].release();
+    pl->pair[1].release();
+    pl->pairN.clear();
+    return HB_OK;
 }
 
 int plan_varf_csr(hb_plan* pl, const double* d_f, long long row_begin, long long row_end, CsrResult& out, cudaStream_t st) {

@@ -55,6 +55,7 @@ struct Axis {
     DevBuf plain, wgt;    // [n][Pp]   phi_k(x_i), w_i*phi_k(x_i)
     DevBuf plainT, wgtT;  // [P][np]
     DevBuf psi;           // [n][Pp]   sqrt(w_i)*phi_k(x_i), built on first Gram-form varf
+    DevBuf sw;            // optional: sqrt(w_i) supplied in extended range (plan_set_sqrt_weights)
     // dense 2-D varf: slots of the 8x8-blocked pair tables (slot -> basis index, -1 padding).  Hermite axes list
     // the even indices first and start the odd ones on a block boundary: `nb_even` blocks of even indices.
     std::vector<int> slots;
@@ -153,6 +154,7 @@ int plan_backward(hb_plan* pl, const double* d_coef, long long coef_stride, int 
                   long long f_stride, cudaStream_t st);
 // reference-algebra varf as CSR without a dense matrix when the retained alpha leave a narrow band (polynomial f);
 // out.rows = -1 when they do not (nothing assembled: use plan_varf + a compaction)
+int plan_set_sqrt_weights(hb_plan* pl, int axis, const double* sqrt_w);
 int plan_varf_csr(hb_plan* pl, const double* d_f, long long row_begin, long long row_end, CsrResult& out, cudaStream_t st);
 int plan_varf(hb_plan* pl, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
               long long row_end, cudaStream_t st);

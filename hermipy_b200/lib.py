@@ -26,13 +26,15 @@ def _scaled_recurrence(x, n):
     return pm, p, logs
 
 
-def hermegauss(n):
-    """n-point rule: nodes (ascending) and weights normalised to sum 1."""
+def hermegauss(n, sqrt_weights=False):
+    """n-point rule: nodes (ascending) and weights normalised to sum 1.  sqrt_weights=True also returns sqrt(w_i)
+    formed in the log domain: representable while w_i > 1e-616, where w_i itself underflows below 1e-308 (the Gram-form
+    varf at high degree needs it: Plan(..., sqrt_weights=...))."""
     n = int(n)
     if n < 1:
         raise ValueError("n must be positive")
     if n == 1:
-        return np.zeros(1), np.ones(1)
+        return (np.zeros(1), np.ones(1), np.ones(1)) if sqrt_weights else (np.zeros(1), np.ones(1))
     x = sl.eigvalsh_tridiagonal(np.zeros(n), np.sqrt(np.arange(1.0, n)))
     x = (x - x[::-1]) / 2                      # enforce the exact symmetry of the rule
     for _ in range(3):                         # Newton: phi_n' = sqrt(n) phi_{n-1}
@@ -44,7 +46,28 @@ def hermegauss(n):
         logw = -np.log(float(n)) - 2 * (np.log(np.abs(pm)) + logs)
         w = np.exp(logw)
     w = (w + w[::-1]) / 2
-    return x, w / w.sum()
+    total = w.sum()
+    if not sqrt_weights:
+        return x, w / total
+    with np.errstate(under="ignore"):
+        sw = np.exp(0.5 * logw)
+    sw = (sw + sw[::-1]) / 2
+    return x, w / total, sw / np.sqrt(total)
+
+
+def gram_rule(n, degree, tol=1e-17):
+    """The part of the n-point rule a degree-`degree` Gram-form varf needs: (nodes, weights, sqrt_weights) restricted
+    to the nodes where some psi_k = sqrt(w) phi_k, k <= degree, exceeds `tol` (the functions decay like Gaussians beyond
+    their turning point 2 sqrt(k)), symmetric bit for bit.  Setup code on the host."""
+    x, w, sw = hermegauss(n, sqrt_weights=True)
+    pm, p = sw.copy(), x * sw
+    amp = np.maximum(np.abs(pm), np.abs(p))
+    for k in range(1, int(degree)):
+        pm, p = p, (x * p - np.sqrt(float(k)) * pm) / np.sqrt(k + 1.0)
+        amp = np.maximum(amp, np.abs(p))
+    keep = amp > tol
+    keep &= keep[::-1]
+    return x[keep], w[keep], sw[keep]
 
 
 def hermegauss_nd(n_points):

@@ -42,7 +42,10 @@ def varfd_device(dim, degree, direction, var, do_fourier=0, index_set="triangle"
 
 
 class Plan:
-    def __init__(self, degree, nodes, weights, do_fourier=None, index_set="triangle"):
+    def __init__(self, degree, nodes, weights, do_fourier=None, index_set="triangle", sqrt_weights=None):
+        """sqrt_weights: optional list (one entry per axis, None to skip an axis) of sqrt(w_i) in extended range for
+        the Gram-form varf at high degree (hermipy_b200.lib.hermegauss(n, sqrt_weights=True) supplies them): weights
+        below 1e-308 underflow to 0 in double precision while sqrt(w) phi_k is still O(1) there."""
         nodes = [np.ascontiguousarray(n, dtype=np.float64).ravel() for n in nodes]
         weights = [np.ascontiguousarray(w, dtype=np.float64).ravel() for w in weights]
         self.dim = len(nodes)
@@ -61,6 +64,12 @@ class Plan:
         self.grid_pitch = int(lib().hb_plan_grid_pitch(self._h))
         self.grid_size = int(lib().hb_plan_grid_size(self._h))
         self.coef_stride = (self.n_polys + 1) & ~1
+        for a, sw in enumerate(sqrt_weights or []):
+            if sw is not None:
+                sw = np.ascontiguousarray(sw, dtype=np.float64).ravel()
+                if len(sw) != self.n_pts[a]:
+                    raise ValueError("sqrt_weights[%d] has %d entries, the axis has %d nodes" % (a, len(sw), self.n_pts[a]))
+                check(lib().hb_plan_set_sqrt_weights(self._h, a, sw.ctypes.data_as(c_dp)))
 
     def __del__(self):
         # at interpreter shutdown the module globals may already be gone: then the process-exit cleanup of the

@@ -181,6 +181,11 @@ int hb_plan_discretize(hb_plan* plan, const char* body, const double* translatio
  * (row-major, pitch ldo >= n_polys); row sharding across GPUs = one call per rank with its own range. */
 int hb_plan_varf(hb_plan* plan, const double* d_f, int mode, double* d_out, long long ldo, long long row_begin,
                  long long row_end, void* cuda_stream);
+/* Gram-form varf at high degree: sqrt(w_i) of one axis in extended range (host array of n entries).  A weight below
+ * 1e-308 is 0 in double precision, but the Gram tables only need psi_k = sqrt(w) phi_k, and sqrt(w) is representable
+ * while w > 1e-616: at degree 400 the basis functions reach |x| ~ 40, where w ~ 1e-348 -- with plain double weights the
+ * quadrature silently loses the rows above degree ~290.  Drops the tables built from the weights so far. */
+int hb_plan_set_sqrt_weights(hb_plan* plan, int axis, const double* sqrt_w);
 /* the owned rows [row_begin,row_end) of the reference-algebra varf as CSR (rows relative to row_begin), for
  * polynomial-like f only (HB_ERR_INVALID otherwise); result fetched with hb_sparse_fetch.  Row sharding of a
  * sparse matrix across GPUs = one call per rank with its own range. */

@@ -27,16 +27,14 @@ def bistable(X, Y):
 def test_c3_varf_degree_400_leading_rows(ref):
     import torch
     from hermipy_b200.plan import Plan
-    x, w = sp.roots_hermitenorm(801)
-    w = w / np.sqrt(2 * np.pi)
-    keep = w > 0                      # 635 nodes: the outer weights underflow in double precision
-    x, w = x[keep], w[keep]
+    from hermipy_b200.lib import gram_rule
+    x, w, sw = gram_rule(801, 400)    # 717 nodes; sqrt(w) in extended range (80 of the weights underflow in double)
     X, Y = np.meshgrid(x, x, indexing="ij")
     V = bistable(X, Y)
     sub = 40
     n_sub = (sub + 1) * (sub + 2) // 2
     want = ref.varf(sub, V, [x, x], [w, w], index_set="triangle")
-    plan = Plan(400, [x, x], [w, w], index_set="triangle")
+    plan = Plan(400, [x, x], [w, w], index_set="triangle", sqrt_weights=[sw, sw])
     assert plan.n_polys == 80601
     fV = plan.pack_grid(V[None])[0]
     rows_p = plan.varf(fV, "reference", row_begin=0, row_end=n_sub)
@@ -56,9 +54,11 @@ def test_c3_varf_degree_400_leading_rows(ref):
     rows_e = plan.varf(plan.pack_grid(E[None])[0], "gram", row_begin=0, row_end=n_sub).cpu().numpy()
     assert np.isfinite(rows_e).all()
     assert np.abs(rows_e[:, :n_sub] - rows_e[:, :n_sub].T).max() <= 1e-13 * np.abs(rows_e).max()
-    xl, wl = x.astype(np.longdouble), w.astype(np.longdouble)
+    # 80-bit psi_k = sqrt(w) phi_k (the recurrence seeded with sqrt(w): bounded, no overflow)
+    xl = x.astype(np.longdouble)
     phi = np.zeros((len(x), 401), dtype=np.longdouble)
-    phi[:, 0], phi[:, 1] = 1, xl
+    phi[:, 0] = sw.astype(np.longdouble)
+    phi[:, 1] = xl * phi[:, 0]
     for k in range(1, 400):
         phi[:, k + 1] = (xl * phi[:, k] - np.sqrt(np.longdouble(k)) * phi[:, k - 1]) / np.sqrt(np.longdouble(k + 1))
     idx = np.array([(m0, g - m0) for g in range(401) for m0 in range(g + 1)])     # triangle order: graded, m0 ascending
@@ -67,8 +67,8 @@ def test_c3_varf_degree_400_leading_rows(ref):
     for r in rng.integers(0, n_sub, 6):
         for c in rng.integers(0, 80601, 6):
             (m0, m1), (n0, n1) = idx[r], idx[c]
-            a0 = wl * phi[:, m0] * phi[:, n0]
-            a1 = wl * phi[:, m1] * phi[:, n1]
+            a0 = phi[:, m0] * phi[:, n0]
+            a1 = phi[:, m1] * phi[:, n1]
             exact = float(a0 @ El @ a1)
             assert abs(rows_e[r, c] - exact) <= 1e-11 * max(1.0, np.abs(rows_e[r]).max()), (r, c)
 
@@ -110,21 +110,24 @@ def test_c3_varf_degree_400_whole_matrix(ref):
     free = torch.cuda.mem_get_info()[0]
     if free < 70e9:
         pytest.skip("needs ~60 GB of free device memory (%.0f GB free)" % (free * 1e-9))
-    x, w = sp.roots_hermitenorm(801)
-    w = w / np.sqrt(2 * np.pi)
-    keep = w > 0
-    x, w = x[keep], w[keep]
+    # the nodes of the 801-point rule the degree-400 basis reaches, with sqrt(w) in extended range: 80 of the 717
+    # weights underflow in double precision while sqrt(w) phi_400 is still O(1e-3) there
+    from hermipy_b200.lib import gram_rule
+    x, w, sw = gram_rule(801, 400)
+    assert (w == 0).sum() > 20 and (sw > 0).all()
     X, Y = np.meshgrid(x, x, indexing="ij")
     V = bistable(X, Y)
     E = np.exp(-3 * V / 10)
-    plan = Plan(400, [x, x], [w, w], index_set="triangle")
+    plan = Plan(400, [x, x], [w, w], index_set="triangle", sqrt_weights=[sw, sw])
     npol = plan.n_polys
     A = torch.empty((npol, npol), dtype=torch.float64, device="cuda")
     plan.varf(plan.pack_grid(E[None])[0], "gram", A)
     torch.cuda.synchronize()
-    xl, wl = x.astype(np.longdouble), w.astype(np.longdouble)
+    # 80-bit psi_k = sqrt(w) phi_k (the recurrence seeded with sqrt(w): bounded, no overflow)
+    xl = x.astype(np.longdouble)
     phi = np.zeros((len(x), 401), dtype=np.longdouble)
-    phi[:, 0], phi[:, 1] = 1, xl
+    phi[:, 0] = sw.astype(np.longdouble)
+    phi[:, 1] = xl * phi[:, 0]
     for k in range(1, 400):
         phi[:, k + 1] = (xl * phi[:, k] - np.sqrt(np.longdouble(k)) * phi[:, k - 1]) / np.sqrt(np.longdouble(k + 1))
     idx = np.array([(m0, g - m0) for g in range(401) for m0 in range(g + 1)])     # triangle order: graded, m0 ascending
@@ -137,7 +140,7 @@ def test_c3_varf_degree_400_whole_matrix(ref):
     scale = float(A[:4096, :4096].abs().max().item())
     for r, c, v in zip(rows, cols, got):
         (m0, m1), (n0, n1) = idx[r], idx[c]
-        exact = float((wl * phi[:, m0] * phi[:, n0]) @ El @ (wl * phi[:, m1] * phi[:, n1]))
+        exact = float((phi[:, m0] * phi[:, n0]) @ El @ (phi[:, m1] * phi[:, n1]))
         assert abs(v - exact) <= 1e-11 * max(1.0, scale), (r, c, v, exact)
     # symmetric to the last bit, everywhere (checked on strided samples of the whole matrix)
     probe = torch.arange(0, npol, 97, device="cuda")
@@ -162,12 +165,9 @@ def test_c3_varf_degree_400_whole_matrix(ref):
     # (the closed form is exact; the reference's algebra -- a thresholded sum of Hf[alpha] T[alpha] whose Hf come from a
     # degree-800 transform -- carries its own rounding at this degree: measured 1.1e-12 here)
     assert rel_err(P, exact) <= 5e-12
-    # the Gram form is a quadrature on the nodes whose weight is representable in double precision (|x| < 38.4):
-    # exact for the basis functions that are negligible beyond them, i.e. up to degree ~280 per axis
-    # (tools/trunc_probe in DESIGN.md 4.3); compare there
-    low_r, low_c = idx[lo:].max(axis=1) <= 280, idx.max(axis=1) <= 280
-    assert low_r.sum() > 50
-    assert rel_err(Q[low_r][:, low_c], P[low_r][:, low_c]) <= 1e-12
+    # with sqrt(w) in extended range the Gram form is the exact quadrature it should be, up to the last row
+    assert rel_err(Q, exact) <= 1e-12
+    assert rel_err(Q, P) <= 5e-12
     # zero pattern of the reference algebra: a degree-4 polynomial couples |m - n|_1 <= 4 only
     nz = np.argwhere(P != 0)
     assert np.abs(idx[lo + nz[:, 0]] - idx[nz[:, 1]]).sum(axis=1).max() <= 4

@@ -544,3 +544,27 @@ def test_varf_3d_dense_gram_and_many_alpha(core, ref):
     finally:
         os.environ.pop("HB_VARF_ND_GEMM")
     assert rel_err(A, B) <= 1e-12
+
+
+def test_sqrt_weights_hook_of_the_gram_varf(core):
+    """Plan(sqrt_weights=...): sqrt(w) supplied by the caller replaces the library's sqrt(w) in the psi tables -- the same
+    bits when it is the same number; rejected when it breaks the bit-symmetry of the axis; hermegauss(n, True) returns
+    square roots consistent with the weights where those are representable."""
+    import torch
+    from hermipy_b200.lib import gram_rule, hermegauss
+    from hermipy_b200.plan import Plan
+    from hermipy_b200._lib import HermiteB200Error
+    x, w, sw = hermegauss(64, sqrt_weights=True)
+    assert np.abs(sw * sw / w - 1).max() < 1e-14
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    f = np.exp(-(X ** 2 + Y ** 2) / 6) * (1 + X * Y)
+    p0 = Plan(12, [x, x], [w, w], index_set="cube")
+    p1 = Plan(12, [x, x], [w, w], index_set="cube", sqrt_weights=[np.sqrt(w), None])
+    fd = p0.pack_grid(f[None])[0]
+    assert torch.equal(p0.varf(fd, "gram"), p1.varf(fd, "gram"))
+    bad = np.sqrt(w).copy()
+    bad[0] *= 1.5
+    with pytest.raises(HermiteB200Error):
+        Plan(12, [x, x], [w, w], index_set="cube", sqrt_weights=[bad, None])
+    xg, wg, swg = gram_rule(201, 60)
+    assert len(xg) < 201 and np.array_equal(xg, -xg[::-1]) and np.array_equal(swg, swg[::-1])
