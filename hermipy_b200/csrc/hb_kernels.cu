@@ -24,9 +24,10 @@ static const int kMaxGridY = 65535;
 // and their transposes [k][i].  One thread per node; the k-recurrence runs in registers in exactly the
 // reference's operation order ((A*x)*v_k - B*v_{k-1}); rows are written coalesced for the [k][i]
 // copies.  w_i == 0 gives wgt = 0 even where phi overflowed (the reference would produce 0*inf = NaN).
-__global__ void basis_tables_kernel(const double* __restrict__ x, const double* __restrict__ w, int n, int P,
-                                    int fourier, double* plain, double* wgt, long long ld_ik, double* plainT,
-                                    double* wgtT, long long ld_ki) {
+// Fourier axes (no recurrence): one thread per node.
+__global__ void fourier_tables_kernel(const double* __restrict__ x, const double* __restrict__ w, int n, int P,
+                                      double* plain, double* wgt, long long ld_ik, double* plainT, double* wgtT,
+                                      long long ld_ki, double seed_scale_unused) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double xi = x[i];
@@ -38,33 +39,99 @@ __global__ void basis_tables_kernel(const double* __restrict__ x, const double* 
         if (plainT) plainT[(long long)k * ld_ki + i] = v;
         if (wgtT) wgtT[(long long)k * ld_ki + i] = vw;
     };
-    if (fourier) {
-        // transform.cpp:98-109 ; COS(k)=2k, SIN(k)=2k-1 (transform.hpp:55-56)
-        put(0, 1.0 / sqrt(2 * M_PI));
-        for (int k = 1; 2 * k < P; k++) {
-            put(2 * k, cos(k * xi) / sqrt(M_PI));
-            put(2 * k - 1, sin(k * xi) / sqrt(M_PI));
-        }
-        return;
+    // transform.cpp:98-109 ; COS(k)=2k, SIN(k)=2k-1 (transform.hpp:55-56)
+    put(0, 1.0 / sqrt(2 * M_PI));
+    for (int k = 1; 2 * k < P; k++) {
+        put(2 * k, cos(k * xi) / sqrt(M_PI));
+        put(2 * k - 1, sin(k * xi) / sqrt(M_PI));
     }
-    double vm = 1.0, v = xi;
-    put(0, vm);
-    if (P > 1) put(1, v);
-    for (int k = 1; k + 1 < P; k++) {
+}
+
+// Hermite axes: ONE WARP per 32 nodes, lane = node.  The recurrence coefficients REC_A(k) = 1/sqrt(k+1),
+// REC_B(k) = sqrt(k)/sqrt(k+1) are formed once per warp in shared memory (not a square root and two divisions per step
+// per node); every lane runs the recurrence for its node in registers -- in exactly the reference's operation order,
+// ((A*x)*v_k) - (B*v_{k-1}), no FMA contraction, so the tables are bit-identical to hermite_eval -- 32 degrees at a
+// time into a 32 x 33 shared-memory tile, from which BOTH layouts leave coalesced: the [k][i] tables row by row (32
+// consecutive nodes), the [i][k] tables node by node (32 consecutive degrees, read transposed from the tile).
+// seed_mode 1: the recurrence starts from sqrt(w_i) (or the caller's extended-range sw[i]) instead of 1:
+// psi_k = sqrt(w) phi_k of the Gram-form varf, bounded where phi alone overflows.
+// HBM-write-bound: 8 n P bytes per table, once per plan.
+__global__ void __launch_bounds__(32)
+    hermite_tables_kernel(const double* __restrict__ x, const double* __restrict__ w, const double* __restrict__ sw,
+                          int seed_mode, int n, int P, double* plain, double* wgt, long long ld_ik, double* plainT,
+                          double* wgtT, long long ld_ki) {
+    extern __shared__ double sh[];
+    double* ra = sh;                 // [P]
+    double* rb = sh + P;             // [P]
+    double* tile = sh + 2 * P;       // [32][33]
+    const int lane = threadIdx.x, i0 = blockIdx.x * 32, i = i0 + lane;
+    for (int k = lane; k < P; k += 32) {
         const double sk1 = sqrt((double)(k + 1));
-        const double a = __ddiv_rn(1.0, sk1);               // REC_A(k) = 1/sqrt(k+1)
-        const double b = __ddiv_rn(sqrt((double)k), sk1);   // REC_B(k) = sqrt(k)/sqrt(k+1)
-        const double nv = __dsub_rn(__dmul_rn(__dmul_rn(a, xi), v), __dmul_rn(b, vm));
-        vm = v;
-        v = nv;
-        put(k + 1, v);
+        ra[k] = __ddiv_rn(1.0, sk1);
+        rb[k] = __ddiv_rn(sqrt((double)k), sk1);
     }
+    __syncwarp();
+    const bool live = i < n;
+    const double xi = live ? x[i] : 0.0;
+    const double wi = (live && w && !seed_mode) ? w[i] : 1.0;
+    const double s0 = !seed_mode ? 1.0 : (!live ? 0.0 : (sw ? sw[i] : sqrt(w[i])));
+    double vm = 0.0, v = 0.0;       // phi_{k-1}, phi_k at the start of a chunk
+    for (int k0 = 0; k0 < P; k0 += 32) {
+        const int kn = min(32, P - k0);
+        for (int kk = 0; kk < kn; kk++) {
+            const int k = k0 + kk;
+            double nv;
+            if (k == 0) nv = s0;
+            else if (k == 1) nv = seed_mode ? __dmul_rn(xi, v) : xi;
+            else nv = __dsub_rn(__dmul_rn(__dmul_rn(ra[k - 1], xi), v), __dmul_rn(rb[k - 1], vm));
+            vm = v;
+            v = nv;
+            tile[kk * 33 + lane] = nv;
+        }
+        __syncwarp();
+        // [k][i] layouts: row k, 32 consecutive nodes
+        if (live) {
+            for (int kk = 0; kk < kn; kk++) {
+                const double val = tile[kk * 33 + lane];
+                if (plainT) plainT[(long long)(k0 + kk) * ld_ki + i] = val;
+                if (wgtT) wgtT[(long long)(k0 + kk) * ld_ki + i] = (wi == 0.0) ? 0.0 : __dmul_rn(wi, val);
+            }
+        }
+        // [i][k] layouts: node i0 + ii, 32 consecutive degrees
+        if (lane < kn) {
+            for (int ii = 0; ii < 32 && i0 + ii < n; ii++) {
+                const double val = tile[lane * 33 + ii];
+                if (plain) plain[(long long)(i0 + ii) * ld_ik + k0 + lane] = val;
+                if (wgt) {
+                    const double wn = (w && !seed_mode) ? w[i0 + ii] : 1.0;
+                    wgt[(long long)(i0 + ii) * ld_ik + k0 + lane] = (wn == 0.0) ? 0.0 : __dmul_rn(wn, val);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int launch_hermite_tables(const double* x, const double* w, const double* sw, int seed_mode, int n, int P,
+                                 double* plain, double* wgt, long long ld_ik, double* plainT, double* wgtT,
+                                 long long ld_ki, cudaStream_t s) {
+    const size_t smem = ((size_t)2 * P + 32 * 33) * 8;
+    if (smem > 48 * 1024) {   // degree > ~2 500: opt in to more dynamic shared memory (cheap, per device: set every time)
+        if (smem > 200 * 1024) { set_error("basis tables: degree %d is beyond the shared-memory coefficient table", P - 1); return HB_ERR_INVALID; }
+        if (cudaFuncSetAttribute(hermite_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return HB_ERR_CUDA;
+    }
+    hermite_tables_kernel<<<cdiv(n, 32), 32, smem, s>>>(x, w, sw, seed_mode, n, P, plain, wgt, ld_ik, plainT, wgtT, ld_ki);
+    return launch_status();
 }
 
 int launch_basis_tables(const double* x, const double* w, int n, int P, int fourier, double* plain, double* wgt,
                         long long ld_ik, double* plainT, double* wgtT, long long ld_ki, cudaStream_t s) {
-    basis_tables_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, n, P, fourier, plain, wgt, ld_ik, plainT, wgtT, ld_ki);
-    return launch_status();
+    if (fourier) {
+        fourier_tables_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, n, P, plain, wgt, ld_ik, plainT, wgtT, ld_ki, 0.0);
+        return launch_status();
+    }
+    return launch_hermite_tables(x, w, nullptr, 0, n, P, plain, wgt, ld_ik, plainT, wgtT, ld_ki, s);
 }
 
 // Weighted basis psi_k(x_i) = sqrt(w_i) * phi_k(x_i), the operand of the Gram-form varf.  The recurrence is
@@ -104,8 +171,11 @@ __global__ void psi_table_kernel(const double* __restrict__ x, const double* __r
 
 int launch_psi_table(const double* x, const double* w, const double* sw, int n, int P, int fourier, double* psi,
                      long long ld, cudaStream_t s) {
-    psi_table_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, sw, n, P, fourier, psi, ld);
-    return launch_status();
+    if (fourier) {
+        psi_table_kernel<<<cdiv(n, 64), 64, 0, s>>>(x, w, sw, n, P, fourier, psi, ld);
+        return launch_status();
+    }
+    return launch_hermite_tables(x, w, sw, 1, n, P, psi, nullptr, ld, nullptr, nullptr, 0, s);
 }
 
 // Products of pairs of basis functions on the nodes, the operand of the Gram-form varf:

@@ -5,9 +5,9 @@ matrix is a NumPy / SciPy object; at the sizes this library assembles (C2 cube: 
 row-sharded over 8 GPUs) a host copy costs more than the assembly, so `Quad.varf(..., resident=True)`,
 `Quad.varfd(..., resident=True)` and `Quad.discretize_op(..., resident=True)` return a `ResidentVarf`: the
 same object surface (`__call__`, `+ - *`, `solve`, `eigs`, `multi_indices`), with the matrix a row block per
-rank on the device.  The Krylov drivers are SciPy's (ARPACK, GMRES), as in the reference; their only contact
-with the matrix -- the product A x -- is `hb_dev_matvec` (csrc/hb_matvec.cu, HBM-bound), and only vectors
-cross PCIe.  Dense direct solves run on the device through torch.linalg (cuSOLVER), which is library code
+rank on the device.  `solve` runs a device-side restarted GMRES (`device_gmres`: matrix, Krylov basis and vectors in
+HBM, the product A x is `hb_dev_matvec`, csrc/hb_matvec.cu, HBM-bound; per step one Hessenberg column crosses PCIe);
+`eigs` is SciPy's ARPACK, as in the reference, driving the same device product (one vector each way per product).  Dense direct solves run on the device through torch.linalg (cuSOLVER), which is library code
 beside the path, not part of it.
 """
 import ctypes as C
@@ -42,6 +42,59 @@ def device_matvec(A, x, out=None):
     check(lib().hb_dev_matvec(A.shape[0], A.shape[1], A.data_ptr(), A.stride(0), x.data_ptr(), out.data_ptr(),
                               _stream()))
     return out
+
+
+def device_gmres(matvec, b, x0=None, rtol=1e-5, atol=0.0, restart=20, maxiter=None):
+    """Restarted GMRES with every vector resident in HBM (same stopping rule and defaults as
+    scipy.sparse.linalg.gmres: ||b - A x|| <= max(rtol ||b||, atol), restart 20, at most `maxiter` restart cycles).
+    `matvec`: device vector -> device vector (hb_dev_matvec for a resident matrix).  The Krylov basis lives in one
+    device array; orthogonalisation is classical Gram-Schmidt applied twice (two matrix-vector products with the basis
+    per step, no loop over the basis vectors); per step only the j + 2 Hessenberg entries cross PCIe -- the small
+    least-squares problem is solved on the host.  Returns (x on the device, info): info = 0 converged, > 0 the number
+    of inner iterations spent without reaching the tolerance."""
+    n = b.numel()
+    dev, dt = b.device, b.dtype
+    x = torch.zeros(n, dtype=dt, device=dev) if x0 is None else x0.clone()
+    maxiter = 10 * n if maxiter is None else int(maxiter)
+    m = max(1, min(int(restart), n))
+    target = max(float(rtol) * float(torch.linalg.vector_norm(b)), float(atol))
+    V = torch.empty((m + 1, n), dtype=dt, device=dev)
+    spent = 0
+    for _ in range(maxiter):
+        r = b - matvec(x) if (x0 is not None or spent) else b.clone()
+        beta = float(torch.linalg.vector_norm(r))
+        if beta <= target:
+            return x, 0
+        V[0] = r / beta
+        H = np.zeros((m + 1, m))
+        g = np.zeros(m + 1)
+        g[0] = beta
+        k_used, y = 0, None
+        for j in range(m):
+            w = matvec(V[j])
+            Vj = V[:j + 1]
+            h = Vj @ w                         # classical Gram-Schmidt, twice
+            w = w - Vj.t() @ h
+            h2 = Vj @ w
+            w = w - Vj.t() @ h2
+            hn = torch.linalg.vector_norm(w)
+            col = torch.cat((h + h2, hn.reshape(1))).cpu().numpy()
+            H[:j + 2, j] = col
+            spent += 1
+            k_used = j + 1
+            # least squares of the small Hessenberg system (host, (j+2) x (j+1))
+            y, _, _, _ = np.linalg.lstsq(H[:j + 2, :j + 1], g[:j + 2], rcond=None)
+            res = float(np.linalg.norm(g[:j + 2] - H[:j + 2, :j + 1] @ y))
+            if col[-1] > 0:
+                V[j + 1] = w / hn
+            if res <= target or col[-1] == 0:
+                break
+        x = x + V[:k_used].t() @ torch.from_numpy(y).to(dev)
+        if res <= target:
+            # the recurrence residual can drift from the true one: confirm it
+            if float(torch.linalg.vector_norm(b - matvec(x))) <= target * (1 + 1e-8) + 1e-300:
+                return x, 0
+    return x, spent
 
 
 class ResidentMatrix:
@@ -227,8 +280,30 @@ class ResidentVarf:
         vector = np.append(series.coeffs, 0) if bordered else np.asarray(series.coeffs, dtype=np.float64)
 
         if use_gmres:
-            op = self._bordered_operator(border) if bordered else self.matrix.linear_operator()
-            solution, info = spla.gmres(op, vector, **kwargs)
+            # device-side GMRES: the matrix, the Krylov basis and every vector stay in HBM; per step only the
+            # Hessenberg column crosses PCIe (the reference hands the host matrix to SciPy's GMRES, varf.py:212-219)
+            dev = self.matrix.block.device
+            n = self.matrix.n
+            rhs = torch.from_numpy(np.ascontiguousarray(vector, dtype=np.float64)).to(dev)
+            if bordered:
+                bd = torch.from_numpy(border).to(dev)
+
+                def product(v):
+                    top = self.matrix.matvec_device(v[:n].contiguous()) + bd * v[n]
+                    return torch.cat((top, (bd @ v[:n]).reshape(1)))
+            else:
+                def product(v):
+                    return self.matrix.matvec_device(v.contiguous())
+            known = {k: kwargs.pop(k) for k in ("rtol", "atol", "restart", "maxiter") if k in kwargs}
+            if "tol" in kwargs:                       # older SciPy spelling
+                known.setdefault("rtol", kwargs.pop("tol"))
+            x0 = kwargs.pop("x0", None)
+            if x0 is not None:
+                x0 = torch.from_numpy(np.ascontiguousarray(x0, dtype=np.float64)).to(dev)
+            if kwargs:
+                raise ValueError("ResidentVarf.solve: unsupported GMRES options %s" % sorted(kwargs))
+            sol_dev, info = device_gmres(product, rhs, x0=x0, **known)
+            solution = sol_dev.cpu().numpy()
             if info != 0 and not quiet:
                 print("[Hermipy:varf:solve warning] GMRES returned info = {}".format(info))
         else:

@@ -92,3 +92,37 @@ def test_eigs_regular_and_shift_invert(operator):
     values, _ = varf.eigs(k=2, sigma=sigma, v0=np.ones(28))
     nearest = true[np.argsort(np.abs(true - sigma))[:2]]
     assert all(np.min(np.abs(nearest - lam)) < 1e-8 for lam in values)
+
+
+def test_device_gmres_matches_a_direct_solve_and_scipy_semantics():
+    """hermipy_b200.resident.device_gmres (the Krylov driver of ResidentVarf.solve) on CPU tensors with a torch.mv
+    stand-in for the device product: converges to the direct solution, honours rtol / restart / maxiter like
+    scipy.sparse.linalg.gmres (info = 0 on success, > 0 otherwise), exact for a rank-one update of the identity."""
+    import scipy.sparse.linalg as spla
+    import torch
+    from hermipy_b200.resident import device_gmres
+    rng = np.random.default_rng(4)
+    n = 120
+    A = np.eye(n) * 4 + rng.standard_normal((n, n)) / np.sqrt(n)
+    b = rng.standard_normal(n)
+    At, bt = torch.from_numpy(A), torch.from_numpy(b)
+    want = np.linalg.solve(A, b)
+    x, info = device_gmres(lambda v: torch.mv(At, v), bt, rtol=1e-12, restart=40, maxiter=20)
+    assert info == 0 and np.linalg.norm(x.numpy() - want) <= 1e-10 * np.linalg.norm(want)
+    # same tolerance semantics as SciPy: residual <= rtol * ||b||
+    xs, info_s = spla.gmres(A, b, rtol=1e-6, restart=20)
+    xd, info_d = device_gmres(lambda v: torch.mv(At, v), bt, rtol=1e-6, restart=20)
+    assert info_s == 0 and info_d == 0
+    assert np.linalg.norm(A @ xd.numpy() - b) <= 1e-6 * np.linalg.norm(b) * (1 + 1e-6)
+    assert np.linalg.norm(xd.numpy() - xs) <= 1e-4 * np.linalg.norm(xs)
+    # too few iterations: reported, not hidden
+    _, info_short = device_gmres(lambda v: torch.mv(At, v), bt, rtol=1e-14, restart=3, maxiter=1)
+    assert info_short > 0
+    # happy breakdown: A = I + u u^T has a two-dimensional Krylov space
+    u = torch.from_numpy(rng.standard_normal(n))
+    x2, info2 = device_gmres(lambda v: v + u * (u @ v), bt, rtol=1e-13)
+    assert info2 == 0
+    assert np.linalg.norm((x2 + u * (u @ x2) - bt).numpy()) <= 1e-12 * np.linalg.norm(b)
+    # start vector
+    x3, info3 = device_gmres(lambda v: torch.mv(At, v), bt, x0=torch.from_numpy(want + 1e-3), rtol=1e-12, restart=40)
+    assert info3 == 0 and np.linalg.norm(x3.numpy() - want) <= 1e-10 * np.linalg.norm(want)

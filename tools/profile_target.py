@@ -4,6 +4,7 @@
     python tools/profile_target.py varf      # C2 cube varf: polynomial f (banded assembly) + dense f (Gram GEMM)
     python tools/profile_target.py c5        # one C5 forward+inverse over 8192 rows
     python tools/profile_target.py c4        # 2 x (forward + inverse) 256^3 transform
+    python tools/profile_target.py tables    # recurrence kernel: basis tables of the C5 rule, psi table of the C3 rule
     python tools/profile_target.py matvec    # y = A x on a 40401 x 40401 resident matrix (the C2 cube varf size)
     python tools/profile_target.py gemm M N K CFG   # three launches of one plain GEMM with tile configuration CFG
 """
@@ -70,6 +71,16 @@ elif which == "gemm":
         dgemm(M, N, K, A, ev(K), Bm, ev(N), Cm, ev(N))
     torch.cuda.synchronize()
     print("max err vs torch", float((Cm[:, :N] - A[:, :K] @ Bm[:, :N]).abs().max()))
+elif which == "tables":
+    # basis tables of the C5 rule (n = 1397 nodes, degree 1000) and the psi table of the C3 rule (717 nodes, degree 400)
+    x, w = gh(2001)
+    keep = (w > 0) & (np.abs(x) <= 50)
+    for _ in range(2):
+        pl = Plan(1000, [x[keep]], [w[keep]])
+    from hermipy_b200.lib import gram_rule
+    xg, wg, swg = gram_rule(801, 400)
+    pl2 = Plan(400, [xg], [wg], sqrt_weights=[swg])
+    pl2.varf(torch.ones(pl2.grid_size, dtype=torch.float64, device="cuda"), "gram")
 elif which == "matvec":
     from hermipy_b200.resident import device_matvec
     n = 40401
