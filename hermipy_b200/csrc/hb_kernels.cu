@@ -47,81 +47,91 @@ __global__ void fourier_tables_kernel(const double* __restrict__ x, const double
     }
 }
 
-// Hermite axes: ONE WARP per 32 nodes, lane = node.  The recurrence coefficients REC_A(k) = 1/sqrt(k+1),
-// REC_B(k) = sqrt(k)/sqrt(k+1) are formed once per warp in shared memory (not a square root and two divisions per step
-// per node); every lane runs the recurrence for its node in registers -- in exactly the reference's operation order,
+// Hermite axes: one CTA of 4 warps per 32 nodes.  The recurrence coefficients REC_A(k) = 1/sqrt(k+1),
+// REC_B(k) = sqrt(k)/sqrt(k+1) are formed once per CTA in shared memory (not a square root and two divisions per step
+// per node).  Warp 0 runs the recurrence, lane = node, in registers -- in exactly the reference's operation order,
 // ((A*x)*v_k) - (B*v_{k-1}), no FMA contraction, so the tables are bit-identical to hermite_eval -- 32 degrees at a
-// time into a 32 x 33 shared-memory tile, from which BOTH layouts leave coalesced: the [k][i] tables row by row (32
-// consecutive nodes), the [i][k] tables node by node (32 consecutive degrees, read transposed from the tile).
+// time into one of two 32 x 33 shared-memory tiles; warps 1-3 write the previous tile out while warp 0 is already on
+// the next 32 degrees.  BOTH layouts leave coalesced: the [k][i] tables row by row (32 consecutive nodes), the [i][k]
+// tables node by node (32 consecutive degrees, read transposed from the tile).
 // seed_mode 1: the recurrence starts from sqrt(w_i) (or the caller's extended-range sw[i]) instead of 1:
 // psi_k = sqrt(w) phi_k of the Gram-form varf, bounded where phi alone overflows.
-// HBM-write-bound: 8 n P bytes per table, once per plan.
-__global__ void __launch_bounds__(32)
+// HBM-write-bound in principle (8 n P bytes per table, once per plan); in practice the serial chain of P steps per
+// node sets the time (see profiles/r02_tables_full_summary.txt).
+__global__ void __launch_bounds__(128)
     hermite_tables_kernel(const double* __restrict__ x, const double* __restrict__ w, const double* __restrict__ sw,
                           int seed_mode, int n, int P, double* plain, double* wgt, long long ld_ik, double* plainT,
                           double* wgtT, long long ld_ki) {
     extern __shared__ double sh[];
     double* ra = sh;                 // [P]
     double* rb = sh + P;             // [P]
-    double* tile = sh + 2 * P;       // [32][33]
-    const int lane = threadIdx.x, i0 = blockIdx.x * 32, i = i0 + lane;
-    for (int k = lane; k < P; k += 32) {
+    double* tiles = sh + 2 * P;      // [2][32][33]
+    double* wsh = tiles + 2 * 32 * 33;   // [32] weights of this CTA's nodes
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, i0 = blockIdx.x * 32;
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
         const double sk1 = sqrt((double)(k + 1));
         ra[k] = __ddiv_rn(1.0, sk1);
         rb[k] = __ddiv_rn(sqrt((double)k), sk1);
     }
-    __syncwarp();
+    if (threadIdx.x < 32) wsh[lane] = (i0 + lane < n && w && !seed_mode) ? w[i0 + lane] : 1.0;
+    __syncthreads();
+    const int i = i0 + lane;
     const bool live = i < n;
     const double xi = live ? x[i] : 0.0;
-    const double wi = (live && w && !seed_mode) ? w[i] : 1.0;
     const double s0 = !seed_mode ? 1.0 : (!live ? 0.0 : (sw ? sw[i] : sqrt(w[i])));
-    double vm = 0.0, v = 0.0;       // phi_{k-1}, phi_k at the start of a chunk
-    for (int k0 = 0; k0 < P; k0 += 32) {
-        const int kn = min(32, P - k0);
-        for (int kk = 0; kk < kn; kk++) {
-            const int k = k0 + kk;
-            double nv;
-            if (k == 0) nv = s0;
-            else if (k == 1) nv = seed_mode ? __dmul_rn(xi, v) : xi;
-            else nv = __dsub_rn(__dmul_rn(__dmul_rn(ra[k - 1], xi), v), __dmul_rn(rb[k - 1], vm));
-            vm = v;
-            v = nv;
-            tile[kk * 33 + lane] = nv;
-        }
-        __syncwarp();
-        // [k][i] layouts: row k, 32 consecutive nodes
-        if (live) {
+    double vm = 0.0, v = 0.0;       // phi_{k-1}, phi_k (warp 0)
+    const int n_chunks = (P + 31) / 32;
+    for (int c = 0; c <= n_chunks; c++) {
+        if (warp == 0 && c < n_chunks) {
+            double* tile = tiles + (c & 1) * 32 * 33;
+            const int k0 = c * 32, kn = min(32, P - k0);
             for (int kk = 0; kk < kn; kk++) {
-                const double val = tile[kk * 33 + lane];
-                if (plainT) plainT[(long long)(k0 + kk) * ld_ki + i] = val;
-                if (wgtT) wgtT[(long long)(k0 + kk) * ld_ki + i] = (wi == 0.0) ? 0.0 : __dmul_rn(wi, val);
+                const int k = k0 + kk;
+                double nv;
+                if (k == 0) nv = s0;
+                else if (k == 1) nv = seed_mode ? __dmul_rn(xi, v) : xi;
+                else nv = __dsub_rn(__dmul_rn(__dmul_rn(ra[k - 1], xi), v), __dmul_rn(rb[k - 1], vm));
+                vm = v;
+                v = nv;
+                tile[kk * 33 + lane] = nv;
             }
-        }
-        // [i][k] layouts: node i0 + ii, 32 consecutive degrees
-        if (lane < kn) {
-            for (int ii = 0; ii < 32 && i0 + ii < n; ii++) {
-                const double val = tile[lane * 33 + ii];
-                if (plain) plain[(long long)(i0 + ii) * ld_ik + k0 + lane] = val;
-                if (wgt) {
-                    const double wn = (w && !seed_mode) ? w[i0 + ii] : 1.0;
-                    wgt[(long long)(i0 + ii) * ld_ik + k0 + lane] = (wn == 0.0) ? 0.0 : __dmul_rn(wn, val);
+        } else if (warp > 0 && c > 0) {
+            // write out chunk c - 1: rows kk = warp - 1, warp + 2, ... of the tile for the [k][i] layouts,
+            // nodes ii = warp - 1, warp + 2, ... for the [i][k] layouts
+            const double* tile = tiles + ((c - 1) & 1) * 32 * 33;
+            const int k0 = (c - 1) * 32, kn = min(32, P - k0);
+            if (plainT || wgtT) {
+                for (int kk = warp - 1; kk < kn; kk += 3) {
+                    if (!live) break;
+                    const double val = tile[kk * 33 + lane];
+                    const double wi = wsh[lane];
+                    if (plainT) plainT[(long long)(k0 + kk) * ld_ki + i] = val;
+                    if (wgtT) wgtT[(long long)(k0 + kk) * ld_ki + i] = (wi == 0.0) ? 0.0 : __dmul_rn(wi, val);
+                }
+            }
+            if ((plain || wgt) && lane < kn) {
+                for (int ii = warp - 1; ii < 32 && i0 + ii < n; ii += 3) {
+                    const double val = tile[lane * 33 + ii];
+                    const double wn = wsh[ii];
+                    if (plain) plain[(long long)(i0 + ii) * ld_ik + k0 + lane] = val;
+                    if (wgt) wgt[(long long)(i0 + ii) * ld_ik + k0 + lane] = (wn == 0.0) ? 0.0 : __dmul_rn(wn, val);
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
 static int launch_hermite_tables(const double* x, const double* w, const double* sw, int seed_mode, int n, int P,
                                  double* plain, double* wgt, long long ld_ik, double* plainT, double* wgtT,
                                  long long ld_ki, cudaStream_t s) {
-    const size_t smem = ((size_t)2 * P + 32 * 33) * 8;
+    const size_t smem = ((size_t)2 * P + 2 * 32 * 33 + 32) * 8;
     if (smem > 48 * 1024) {   // degree > ~2 500: opt in to more dynamic shared memory (cheap, per device: set every time)
         if (smem > 200 * 1024) { set_error("basis tables: degree %d is beyond the shared-memory coefficient table", P - 1); return HB_ERR_INVALID; }
         if (cudaFuncSetAttribute(hermite_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return HB_ERR_CUDA;
     }
-    hermite_tables_kernel<<<cdiv(n, 32), 32, smem, s>>>(x, w, sw, seed_mode, n, P, plain, wgt, ld_ik, plainT, wgtT, ld_ki);
+    hermite_tables_kernel<<<cdiv(n, 32), 128, smem, s>>>(x, w, sw, seed_mode, n, P, plain, wgt, ld_ik, plainT, wgtT, ld_ki);
     return launch_status();
 }
 
