@@ -466,12 +466,15 @@ struct ParityNDWork {          // host-derived addressing of the work index (las
     int sq_axis[3];             // the split axes, outermost first
 };
 
-template <int M, bool MERGE>
+// I: type of the work-index arithmetic (unsigned when the index fits 32 bits: the decomposition costs several
+// divisions per thread, and 64-bit ones are emulated)
+template <int M, bool MERGE, typename I>
 __global__ void nd_parity_kernel(ParityNDArgs a, ParityNDWork wk, const double* __restrict__ in,
                                  double* __restrict__ out, long long total) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const long long b = idx / wk.per_batch;
+    const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx64 >= total) return;
+    const I idx = (I)idx64;
+    const long long b = (long long)(idx / (I)wk.per_batch);
     long long nat = b * a.nat_bstride, srt = b * a.srt_bstride;
     // natural / sorted offsets of the point, and per split axis: the two natural positions and the parity offset
     long long pos_p[M], pos_m[M], par[M];
@@ -479,7 +482,7 @@ __global__ void nd_parity_kernel(ParityNDArgs a, ParityNDWork wk, const double* 
 #pragma unroll
     for (int q = 0; q < M; q++) {
         const int ax = wk.sq_axis[q];
-        const int c = (int)((idx / wk.div[ax]) % a.nh[ax]);
+        const int c = (int)((idx / (I)wk.div[ax]) % (I)a.nh[ax]);
         const int xp = a.n[ax] - a.nh[ax] + c, xm = a.n[ax] - 1 - xp;
         pos_p[q] = xp * a.nat_stride[ax];
         pos_m[q] = xm * a.nat_stride[ax];
@@ -490,7 +493,7 @@ __global__ void nd_parity_kernel(ParityNDArgs a, ParityNDWork wk, const double* 
 #pragma unroll 1
     for (int ax = 0; ax < a.d; ax++) {
         if (a.split[ax]) continue;
-        const int c = (int)((idx / wk.div[ax]) % a.n[ax]);
+        const int c = (int)((idx / (I)wk.div[ax]) % (I)a.n[ax]);
         nat += c * a.nat_stride[ax];
         srt += c * a.srt_stride[ax];
     }
@@ -544,7 +547,7 @@ __global__ void nd_parity_kernel(ParityNDArgs a, ParityNDWork wk, const double* 
                     v[s | (1 << q)] = e - o;
                 }
         // the thread at work coordinate 0 of the last axis also zero-fills the pad columns of the rows it touches
-        const bool pads = a.nat_pad_last > a.n[last] && (idx % (last_split ? a.nh[last] : a.n[last])) == 0;
+        const bool pads = a.nat_pad_last > a.n[last] && (idx % (I)(last_split ? a.nh[last] : a.n[last])) == 0;
 #pragma unroll
         for (int s = 0; s < (1 << M); s++) {
             long long off = nat, row = nat;   // row: the same point with the last axis at its origin
@@ -586,9 +589,15 @@ static int launch_nd_parity(const ParityNDArgs& a, const double* in, double* out
     if (m < 1 || m > 3) { set_error("nd parity pass: 1..3 split axes supported (got %d)", m); return HB_ERR_INVALID; }
     const long long blocks = (total + 255) / 256;
     if (blocks > 0x7fffffffLL) { set_error("nd parity pass: grid too large"); return HB_ERR_INVALID; }
-    if (m == 1) nd_parity_kernel<1, MERGE><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
-    else if (m == 2) nd_parity_kernel<2, MERGE><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
-    else nd_parity_kernel<3, MERGE><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+    if (total < 0x7fffffffLL) {
+        if (m == 1) nd_parity_kernel<1, MERGE, unsigned><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+        else if (m == 2) nd_parity_kernel<2, MERGE, unsigned><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+        else nd_parity_kernel<3, MERGE, unsigned><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+    } else {
+        if (m == 1) nd_parity_kernel<1, MERGE, long long><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+        else if (m == 2) nd_parity_kernel<2, MERGE, long long><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+        else nd_parity_kernel<3, MERGE, long long><<<(unsigned)blocks, 256, 0, s>>>(a, wk, in, out, total);
+    }
     return launch_status();
 }
 int launch_nd_parity_split(const ParityNDArgs& a, const double* natural, double* sorted, cudaStream_t s) {
