@@ -7,7 +7,9 @@ row-sharded over 8 GPUs) a host copy costs more than the assembly, so `Quad.varf
 same object surface (`__call__`, `+ - *`, `solve`, `eigs`, `multi_indices`), with the matrix a row block per
 rank on the device.  `solve` runs a device-side restarted GMRES (`device_gmres`: matrix, Krylov basis and vectors in
 HBM, the product A x is `hb_dev_matvec`, csrc/hb_matvec.cu, HBM-bound; per step one Hessenberg column crosses PCIe);
-`eigs` is SciPy's ARPACK, as in the reference, driving the same device product (one vector each way per product).  Dense direct solves run on the device through torch.linalg (cuSOLVER), which is library code
+`eigs` without shift runs a device-side Krylov-Schur iteration (`device_eigs`: thick-restarted Arnoldi, basis and
+products in HBM, the ncv x ncv projected problem on the host with LAPACK); with `sigma` (shift-invert) it is SciPy's
+ARPACK, as in the reference, on a device LU.  Dense direct solves run on the device through torch.linalg (cuSOLVER), which is library code
 beside the path, not part of it.
 """
 import ctypes as C
@@ -95,6 +97,123 @@ def device_gmres(matvec, b, x0=None, rtol=1e-5, atol=0.0, restart=20, maxiter=No
             if float(torch.linalg.vector_norm(b - matvec(x))) <= target * (1 + 1e-8) + 1e-300:
                 return x, 0
     return x, spent
+
+
+def _wanted_order(theta, which):
+    """indices of Ritz values, most wanted first, for ARPACK's `which` codes (general, non-symmetric problem)"""
+    key = {"LM": -np.abs(theta), "SM": np.abs(theta), "LR": -theta.real, "SR": theta.real,
+           "LI": -np.abs(theta.imag), "SI": np.abs(theta.imag)}
+    if which not in key:
+        raise ValueError("eigs: which must be one of %s" % sorted(key))
+    return np.argsort(key[which], kind="stable")
+
+
+def device_eigs(matvec, n, k=6, which="LM", ncv=None, tol=0.0, maxiter=None, v0=None, device=None, dtype=torch.float64):
+    """k eigenpairs of a real non-symmetric operator by the Krylov-Schur method (Stewart 2001: Arnoldi with thick
+    restarts through a reordered real Schur form) -- the algorithm family ARPACK's implicitly restarted Arnoldi belongs
+    to, with the same meaning of k / which / ncv / tol / maxiter / v0 as scipy.sparse.linalg.eigs (standard problem, no
+    shift).  The Krylov basis (ncv + 1 vectors) and every operator product stay in HBM; the small projected matrix
+    (ncv x ncv) is handled on the host with LAPACK, and per Arnoldi step one column of it crosses PCIe.
+    Returns (eigenvalues (k,), eigenvectors as a device tensor (n, k) -- complex when a conjugate pair is among them)."""
+    import scipy.linalg as sla
+    if not 0 < k < n - 1:
+        raise ValueError("eigs: need 0 < k < n - 1")
+    m = min(n, max(2 * k + 1, 20)) if ncv is None else int(ncv)
+    if not k + 1 < m <= n:
+        raise ValueError("eigs: need k + 1 < ncv <= n")
+    maxiter = 10 * n if maxiter is None else int(maxiter)
+    eps = float(np.finfo(np.float64).eps)
+    tol = eps if not tol else float(tol)
+    dev = device if device is not None else (v0.device if torch.is_tensor(v0) else "cpu")
+    V = torch.zeros((m + 1, n), dtype=dtype, device=dev)
+    if v0 is None:
+        g = torch.Generator(device="cpu").manual_seed(0)
+        v = torch.rand(n, generator=g, dtype=dtype).to(dev) - 0.5
+    else:
+        v = (v0 if torch.is_tensor(v0) else torch.from_numpy(np.ascontiguousarray(v0, dtype=np.float64))).to(dev)
+    V[0] = v / torch.linalg.vector_norm(v)
+    H = np.zeros((m + 1, m))
+    p = 0                      # columns of the current decomposition that are in (reordered) Schur form
+
+    def expand(j0):
+        """Arnoldi steps j0 .. m-1: A V_m = V_m H_m + H[m, m-1] v_m e^T (classical Gram-Schmidt, twice)"""
+        for j in range(j0, m):
+            w = matvec(V[j])
+            Vj = V[:j + 1]
+            h = Vj @ w
+            w = w - Vj.t() @ h
+            h2 = Vj @ w
+            w = w - Vj.t() @ h2
+            hn = torch.linalg.vector_norm(w)
+            col = torch.cat((h + h2, hn.reshape(1))).cpu().numpy()
+            H[:j + 2, j] = col
+            if col[-1] <= eps * max(1.0, np.abs(col[:-1]).max()):      # invariant subspace: restart direction
+                g2 = torch.Generator(device="cpu").manual_seed(j + 1)
+                w = torch.rand(n, generator=g2, dtype=dtype).to(dev) - 0.5
+                w = w - Vj.t() @ (Vj @ w)
+                hn = torch.linalg.vector_norm(w)
+                H[j + 1, j] = 0.0
+            V[j + 1] = w / hn
+
+    expand(0)
+    theta, order, Q, T = None, None, None, None
+    for _ in range(maxiter):
+        Hm = H[:m, :m]
+        beta_row = H[m, :m].copy()             # the residual row: zero except the last entry right after expand()
+        T, Q = sla.schur(Hm, output="real")
+        # eigenvalue of every diagonal position of the quasi-triangular T (2 x 2 blocks: a conjugate pair)
+        theta = np.zeros(m, dtype=complex)
+        i = 0
+        while i < m:
+            if i + 1 < m and T[i + 1, i] != 0.0:
+                pair = np.linalg.eigvals(T[i:i + 2, i:i + 2])
+                theta[i], theta[i + 1] = pair[0], pair[1]
+                i += 2
+            else:
+                theta[i] = T[i, i]
+                i += 1
+        order = _wanted_order(theta, which)
+        # keep the k wanted values plus a share of the rest (thick restart), never cutting a conjugate pair
+        keep = min(m - 2, k + max(1, (m - k) // 2))
+        sel = np.zeros(m, dtype=bool)
+        sel[order[:keep]] = True
+        for i in range(m - 1):
+            if T[i + 1, i] != 0.0 and (sel[i] or sel[i + 1]):
+                sel[i] = sel[i + 1] = True
+        # move the selected eigenvalues to the leading block (LAPACK dtrsen: orthogonal reordering of the Schur form)
+        T, Q, _wr, _wi, pk, _s, _sep, info = sla.lapack.dtrsen(sel.astype(np.int32), T, Q, job="N")
+        if info != 0:
+            raise RuntimeError("device_eigs: reordering of the Schur form failed (dtrsen info = %d)" % info)
+        pk = int(pk)
+        b = beta_row @ Q                        # residual row in the Schur basis
+        # Ritz residuals of the wanted pairs: |b . y| for the eigenvectors y of the leading block
+        wv, Y = np.linalg.eig(T[:pk, :pk])
+        resid = np.abs(b[:pk] @ Y)
+        idx = _wanted_order(wv, which)[:k]
+        # ARPACK's test, |residual| <= tol max(eps^(2/3), |theta|), with a floor at the rounding level of the projected
+        # problem (residuals of converged pairs stagnate at ~eps ||A||: a pair cannot be resolved below that)
+        floor = 20.0 * eps * max(1.0, float(np.abs(theta).max()))
+        done = np.all(resid[idx] <= np.maximum(tol * np.maximum(eps ** (2.0 / 3.0), np.abs(wv[idx])), floor))
+        if done:
+            Qk = torch.from_numpy(np.ascontiguousarray(Q[:, :pk])).to(dev)
+            basis = V[:m].t() @ Qk              # (n, pk) Schur vectors
+            vals, Yk = wv[idx], Y[:, idx]
+            if np.all(np.abs(vals.imag) <= 0) and np.all(np.abs(Yk.imag) <= 0):
+                vecs = basis @ torch.from_numpy(np.ascontiguousarray(Yk.real)).to(dev)
+                return vals.real.astype(np.float64), vecs
+            Yc = torch.from_numpy(np.ascontiguousarray(Yk)).to(dev)
+            return vals, basis.to(Yc.dtype) @ Yc
+        # thick restart: V <- [V Q[:, :pk], v_{m+1}], H <- [[T_pk], [b_pk]]
+        Qk = torch.from_numpy(np.ascontiguousarray(Q[:, :pk])).to(dev)
+        Vnew = (V[:m].t() @ Qk).t().contiguous()
+        V[pk] = V[m]
+        V[:pk] = Vnew
+        H[:] = 0.0
+        H[:pk, :pk] = T[:pk, :pk]
+        H[pk, :pk] = b[:pk]
+        p = pk
+        expand(p)
+    raise RuntimeError("device_eigs: no convergence in %d restarts (k = %d, ncv = %d)" % (maxiter, k, m))
 
 
 class ResidentMatrix:
@@ -323,9 +442,32 @@ class ResidentVarf:
 
     @stats.log_stats()
     def eigs(self, **kwargs):
-        """scipy.sparse.linalg.eigs (ARPACK) on the resident matrix (varf.py:228-237).  With `sigma`
-        (shift-invert) the factorisation of A - sigma I is a device LU (torch.linalg.lu_factor)."""
+        """Eigenpairs of the resident matrix with the arguments of scipy.sparse.linalg.eigs (varf.py:228-237).
+        Standard problem without shift: the device-side Krylov-Schur driver (`driver='arpack'` forces SciPy's ARPACK on
+        the device product).  With `sigma` (shift-invert): ARPACK on a device LU of A - sigma I
+        (torch.linalg.lu_factor)."""
         sigma = kwargs.get('sigma')
+        driver = kwargs.pop('driver', None)
+        plain = sigma is None and not (set(kwargs) - {'k', 'which', 'ncv', 'tol', 'maxiter', 'v0'})
+        if driver not in (None, 'device', 'arpack'):
+            raise ValueError("ResidentVarf.eigs: driver must be 'device' or 'arpack'")
+        if driver == 'device' and not plain:
+            raise ValueError("ResidentVarf.eigs: the device driver handles the standard problem without shift")
+        if plain and driver != 'arpack':
+            # device-side Krylov-Schur: basis and products in HBM, the projected ncv x ncv problem on the host
+            dev = self.matrix.block.device
+            v0 = kwargs.get('v0')
+            values, vectors = device_eigs(lambda v: self.matrix.matvec_device(v.contiguous()), self.matrix.n,
+                                          k=kwargs.get('k', 6), which=kwargs.get('which', 'LM'), ncv=kwargs.get('ncv'),
+                                          tol=kwargs.get('tol', 0.0), maxiter=kwargs.get('maxiter'),
+                                          v0=None if v0 is None else torch.from_numpy(np.ascontiguousarray(v0, dtype=np.float64)).to(dev),
+                                          device=dev)
+            vectors = vectors.cpu().numpy()
+            series = []
+            for v in vectors.T:
+                v = v if la.norm(np.imag(v)) > 1e-15 else np.real(v)
+                series.append(hs.Series(v, self.position, factor=self.factor, index_set=self.index_set))
+            return values, series
         if sigma is not None and 'OPinv' not in kwargs:
             if self.matrix.sharded or np.iscomplex(sigma):
                 raise ValueError("ResidentVarf.eigs: shift-invert needs a real shift and the whole matrix on one device")

@@ -135,3 +135,38 @@ def test_resident_operator_call_solve_eigs():
     want_b = host.solve(rhs, remove_vec=null, quiet=True).coeffs
     got_b = res.solve(rhs, use_gmres=False, remove_vec=null, quiet=True).coeffs
     np.testing.assert_allclose(got_b, want_b, rtol=0, atol=1e-8 * np.abs(want_b).max())
+
+
+def test_resident_operator_against_the_reference_package_golden():
+    """The resident consumers against the ORACLE: the matrix of the McKean-Vlasov-type generator of tests/api_cases.py
+    (case_2d, '2d/operator') as the reference's unmodified Python package produced it (tests/golden/api.npz).  The
+    resident matrix, its product, the device-side GMRES, the device LU and the leading eigenvalues are compared with
+    NumPy on that golden matrix."""
+    import os
+    import torch
+    import hermipy_b200 as hm
+    import api_cases
+    from hermipy_b200.resident import ResidentVarf
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api.npz"))["2d/operator"]
+    x, y, f = sym.symbols('x y', real=True) + (sym.Function('f'),)
+    quad = api_cases.quad_gh(hm, [44, 44], mean=[.2, -.1], cov=[[.8, 0], [0, 1.3]])
+    op = sym.diff(f(x, y), x, x) / 2 + sym.diff((x ** 3 - x + y / 2) * f(x, y), x) \
+        + sym.diff(f(x, y), y, y) + sym.diff(y * f(x, y), y)
+    res = quad.discretize_op(op, 10, index_set="triangle", resident=True)
+    A = res.matrix.to_host()
+    assert A.shape == golden.shape
+    assert np.linalg.norm(A - golden) <= 1e-12 * np.linalg.norm(golden)
+    rng = np.random.default_rng(12)
+    n = golden.shape[0]
+    u = hm.Series(rng.standard_normal(n), quad.position, factor=quad.factor)
+    np.testing.assert_allclose(res(u).coeffs, golden @ u.coeffs, rtol=0, atol=1e-12 * np.abs(golden).max() * np.abs(u.coeffs).sum())
+    shift = 3.0
+    shifted = res - ResidentVarf(shift * torch.eye(n, dtype=torch.float64, device="cuda"), quad.position, factor=quad.factor)
+    want = np.linalg.solve(golden - shift * np.eye(n), u.coeffs)
+    got_gm = shifted.solve(u, rtol=1e-13, restart=n, maxiter=5, quiet=True).coeffs
+    got_lu = shifted.solve(u, use_gmres=False).coeffs
+    assert np.linalg.norm(got_gm - want) <= 1e-9 * np.linalg.norm(want)
+    assert np.linalg.norm(got_lu - want) <= 1e-10 * np.linalg.norm(want)
+    lead = np.sort(np.linalg.eigvals(golden).real)[-3:]
+    vals, _ = res.eigs(k=3, which='LR', ncv=min(n - 1, 50), v0=rng.standard_normal(n))
+    np.testing.assert_allclose(np.sort(vals.real), lead, atol=1e-8 * max(1.0, np.abs(lead).max()))
