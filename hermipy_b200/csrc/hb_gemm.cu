@@ -77,9 +77,10 @@ int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint
 // modelled time: small or oddly shaped problems (P = 201, n = 401, batch 17 ...) otherwise lose most of
 // their time to tile quantisation and partial waves over the 148 SMs.
 struct TileCfg { int bm, bn, ctas; };
-static const int kNumCfgs = 10;
+static const int kNumCfgs = 12;
 static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 208, 1}, {32, 208, 2},
-                                {48, 208, 1},  {96, 128, 1}, {32, 128, 2}, {48, 208, 1}, {32, 208, 1}};
+                                {48, 208, 1},  {96, 128, 1}, {32, 128, 2}, {48, 208, 1}, {32, 208, 1},
+                                {112, 128, 1}, {128, 112, 1}};
 
 // Modelled time (microseconds) of configuration i on the problem `a` (used to rank candidates; fitted before the
 // CTAs became persistent, so the per-wave fixed cost is now pessimistic for multi-wave problems -- the first-call
@@ -89,8 +90,8 @@ static const TileCfg kCfgs[] = {{128, 128, 1}, {64, 64, 2}, {64, 128, 2}, {64, 2
 // least-squares fit to tools/cfg_sweep.py on B200 (nine shapes from 0.5 GFLOP to 1.3 TFLOP, fit error <= 10 %
 // except for partial second waves of the two-CTA configurations).
 static double model_us(const GemmArgs& a, int i) {
-    static const double kEff[kNumCfgs] = {1.005, 1.036, 0.956, 0.957, 0.926, 0.881, 0.994, 0.979, 0.96, 0.90};
-    static const double kFixedUs[kNumCfgs] = {7.8, 11.7, 10.0, 6.9, 12.0, 7.9, 5.8, 10.8, 7.9, 7.0};
+    static const double kEff[kNumCfgs] = {1.005, 1.036, 0.956, 0.957, 0.926, 0.881, 0.994, 0.979, 0.96, 0.90, 1.0, 1.0};
+    static const double kFixedUs[kNumCfgs] = {7.8, 11.7, 10.0, 6.9, 12.0, 7.9, 5.8, 10.8, 7.9, 7.0, 7.8, 7.8};
     const double sms = 148.0, clk_per_us = 1920.0;
     const double ksteps = (a.K + 15) / 16;
     const TileCfg& c = kCfgs[i];
@@ -244,7 +245,7 @@ int gemm_launch(const GemmArgs& a, cudaStream_t stream) {
         for (int i = 0; i < GEMM_MAX_BLOCKS && aligned; i++)
             aligned = (reinterpret_cast<uintptr_t>(a.blocks[i]) & 15) == 0;
         if (aligned) {
-            static const int kBulkOf[kNumCfgs] = {6, 1, 2, 2, 7, 2, 6, 7, 2, 7};
+            static const int kBulkOf[kNumCfgs] = {6, 1, 2, 2, 7, 2, 6, 7, 2, 7, 6, 6};
             const char* pick = getenv("HB_GEMM_BULK_CFG");
             int bc = (cfg >= 0 && cfg < kNumCfgs) ? kBulkOf[cfg] : 1;
             if (cfg < 0 && pick && pick[0]) bc = kBulkOf[std::max(0, std::min(kNumCfgs - 1, atoi(pick)))];

@@ -40,6 +40,8 @@ int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint
 // of configuration 5: 83 %), two can (96 % for configuration 1): configuration 8 is configuration 5's tile on
 // 2 x 4 consumer warps, the 26 column slots dealt 7,7,6,6 so that each sub-partition owns 39 of the 156 MMAs;
 // configuration 9 does the same for the 32 x 208 tile when its tiles fit one wave at one CTA per SM.
+// Configurations 10 / 11 (112 x 128, 128 x 112) exist for the per-rank GEMMs of the 8-GPU sharded transform, whose
+// 8192 rows (or columns) x 2 parities make 128 tiles of 128 x 128 -- 20 of the 148 SMs idle -- but 148 tiles of 112.
 #define HB_GEMM_CONFIGS(X, AM, EPI)   \
     X(0, 128, 128, 4, 2, 4, AM, 1, EPI) \
     X(1, 64, 64, 2, 2, 6, AM, 2, EPI)   \
@@ -50,7 +52,9 @@ int make_map4(CUtensorMap* m, const double* base, uint64_t d0, uint64_t d1, uint
     X(6, 96, 128, 4, 2, 4, AM, 1, EPI)  \
     X(7, 32, 128, 2, 2, 4, AM, 2, EPI)  \
     X(8, 48, 208, 2, 4, 4, AM, 1, EPI)  \
-    X(9, 32, 208, 2, 4, 4, AM, 1, EPI)
+    X(9, 32, 208, 2, 4, 4, AM, 1, EPI)  \
+    X(10, 112, 128, 2, 4, 4, AM, 1, EPI) \
+    X(11, 128, 112, 4, 2, 4, AM, 1, EPI)
 
 // The bulk-store epilogue (EPI_BULK) carries a staging sub-tile per consumer warp in shared memory: same tiles, fewer
 // pipeline stages / resident CTAs where the two would not fit 227 KB.  Configuration ids as above (the others map to

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-N_CFGS = 10
+N_CFGS = 12
 
 
 def _run(torch, M, N, K, batch, a_mmajor, shared_a, cfg):

@@ -13,7 +13,7 @@ def run(M,N,K,batch,am,shared_a=False,reps=10):
     Cc=torch.empty(batch*M*ldB, dtype=torch.float64, device="cuda")
     st=C.c_void_p(torch.cuda.current_stream().cuda_stream)
     res={}
-    for cfg in (-1,0,1,2,3,4,5,6,7,8,9):
+    for cfg in (-1,0,1,2,3,4,5,6,7,8,9,10,11):
         os.environ["HB_GEMM_CFG"]=str(cfg)
         def go():
             rc=lib.hb_dev_dgemm(M,N,K,batch,A.data_ptr(),ldA,0 if shared_a else rowsA*ldA,int(am),B.data_ptr(),ldB,K*ldB,Cc.data_ptr(),ldB,M*ldB,st)
