@@ -103,11 +103,13 @@ static int launch_cfg(const GemmArgs& a, const GemmParams& p_in, cudaStream_t st
             return HB_ERR_CUDA;
         attr_set.fetch_or(1ull << dev.index, std::memory_order_relaxed);
     }
-    // Programmatic dependent launch (opt-in, HB_GEMM_PDL=1): the CTA launch and barrier setup of this kernel overlap
-    // the tail of its predecessor in the stream (every warp blocks in griddepcontrol.wait before touching operands;
-    // the predecessor triggers after the main loop of its last tile).  Measured on B200: C4 1.45 -> 1.42 ms, but the
-    // C2 step of four 30-55 us GEMMs replayed from a CUDA graph gets SLOWER (163 -> 185 us), so it is off by default.
-    static const bool pdl = [] { const char* e = getenv("HB_GEMM_PDL"); return e && e[0] == '1'; }();
+    // Programmatic dependent launch (HB_GEMM_PDL=0 turns it off): the CTA launch and barrier setup of this kernel overlap
+    // the tail of its predecessor in the stream (every warp blocks in griddepcontrol.wait before touching operands; the
+    // predecessor triggers after the main loop of its last tile; a predecessor that never triggers -- any non-GEMM
+    // kernel -- releases its dependents when it completes, i.e. the launch is an ordinary one).  Measured on B200 with
+    // the persistent CTAs of round 2, graph replay: C2 step 159.5 -> 156.2 us, C4 1.1385 -> 1.1368 ms, C5 and the
+    // 8-GPU sharded C4 unchanged (round 1, before the CTAs were persistent, it made the C2 step slower).
+    static const bool pdl = [] { const char* e = getenv("HB_GEMM_PDL"); return !(e && e[0] == '0'); }();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_cta);
     cfg.blockDim = dim3((WMc * WNc + 4) * 32);
