@@ -636,8 +636,9 @@ def bench_c2(ctx):
     for _ in range(max(K, 3)):
         flush()
         plan.forward(F, Cf)
-        for tag, ms, _ in plan.timings():
+        for tag, ms, fl in plan.timings():
             acc.setdefault(("fwd", tag), []).append(ms)
+            executed[("fwd", tag)] = fl
         plan.backward(Cf, G)
         for tag, ms, fl in plan.timings():
             acc.setdefault(("bwd", tag), []).append(ms)
@@ -650,7 +651,13 @@ def bench_c2(ctx):
     alg = {("fwd", 2): big, ("fwd", 1): small}
     first_is_big = executed.get(("bwd", 11), 1.0) >= executed.get(("bwd", 12), 0.0)
     alg[("bwd", 11)], alg[("bwd", 12)] = (big, small) if first_is_big else (small, big)
-    launches_info = {"%s_tag%d" % k: {"ms": float(np.mean(v)), "tflops_algorithmic": alg[k] / np.mean(v) * 1e-9}
+    # On the bit-symmetric Gauss-Hermite rule every axis contraction is halved by the parity of the Hermite functions
+    # (round 2: at every size): the flops EXECUTED are half the SURVEY's count, and the roofline fraction is computed on
+    # those (as for the headline); "tflops_algorithmic" is the survey-equivalent rate.
+    parity = sum(executed.get(k, alg[k]) for k in alg) < 0.75 * sum(alg.values())
+    exe = {k: (alg[k] / 2 if parity else alg[k]) for k in alg}
+    launches_info = {"%s_tag%d" % k: {"ms": float(np.mean(v)), "tflops_algorithmic": alg[k] / np.mean(v) * 1e-9,
+                                      "tflops_executed": exe[k] / np.mean(v) * 1e-9}
                      for k, v in acc.items() if k in alg}
     dom = max((k for k in acc if k in alg), key=lambda k: np.mean(acc[k]))
     traffic = None
@@ -659,10 +666,13 @@ def bench_c2(ctx):
         tj = json.load(open(tpath))
         traffic = tj.get("c2_transform_bytes_per_launch", {}).get("%s_tag%d" % dom, tj.get("c2_transform_dominant_bytes_per_launch"))
     roofline = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (%s stage, tag %d)" % dom,
-                "achieved": alg[dom] / np.mean(acc[dom]) * 1e-9, "peak": dgemm_burst, "unit": "TFLOP/s",
-                "frac": alg[dom] / np.mean(acc[dom]) * 1e-9 / dgemm_burst, "traffic": traffic,
+                "achieved": exe[dom] / np.mean(acc[dom]) * 1e-9, "peak": dgemm_burst, "unit": "TFLOP/s",
+                "frac": exe[dom] / np.mean(acc[dom]) * 1e-9 / dgemm_burst, "traffic": traffic,
+                "parity_halved_contraction": bool(parity),
+                "step_tflops_executed": sum(exe.values()) * K / (total_ms * 1e-3) * 1e-12,
+                "step_frac": sum(exe.values()) * K / (total_ms * 1e-3) * 1e-12 / dgemm_burst,
                 "step_tflops_algorithmic": sum(alg.values()) * K / (total_ms * 1e-3) * 1e-12,
-                "step_frac": sum(alg.values()) * K / (total_ms * 1e-3) * 1e-12 / dgemm_burst,
+                "step_frac_survey_equivalent": sum(alg.values()) * K / (total_ms * 1e-3) * 1e-12 / dgemm_burst,
                 "launches": launches_info}
 
     # round-trip property at full size, in the quadrature-weighted L2 norm: un-weighted values at the outer nodes

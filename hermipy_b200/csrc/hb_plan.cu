@@ -408,7 +408,10 @@ static int parity_mask(const hb_plan* pl, int batch) {
         flops += 2.0 * prefix * A.n * A.P * cols;
         cols *= A.P;
     }
-    static const double min_gflop = [] { const char* e = getenv("HB_TRANSFORM_PARITY_GFLOP"); return e && e[0] ? atof(e) : 4.0; }();
+    // With the one-pass split of round 2 the split pays at every size measured (tools/parity_threshold.py: 401 x 401,
+    // degree 200: 1 function 74 -> 55 us per round trip, 17 functions 158 -> 135 us; 201 x 201, degree 100: 49 -> 45 us),
+    // so the default threshold is 0; HB_TRANSFORM_PARITY_GFLOP restores one.
+    static const double min_gflop = [] { const char* e = getenv("HB_TRANSFORM_PARITY_GFLOP"); return e && e[0] ? atof(e) : 0.0; }();
     if (mode != 2 && flops < min_gflop * 1e9) return 0;
     int mask = 0, count = 0;
     for (int a = d - 1; a >= 0 && count < 3; a--) {
