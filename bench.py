@@ -445,6 +445,7 @@ def bench_c4(ctx):
                     "achieved": stage_flops / store_ms * 1e-9, "peak": peak, "unit": "TFLOP/s",
                     "frac": stage_flops / store_ms * 1e-9 / peak, "traffic": traffic,
                     "flops_per_launch": stage_flops,
+                    "frac_survey_equivalent": (2.0 if parity else 1.0) * stage_flops / store_ms * 1e-9 / peak,
                     "other_instantiation": {"kernel": "dgemm_dmma_tma_kernel<...,EPI_LUT> (last forward stage: scatter into the "
                                                       "reference's shell order)", "ms": lut_ms,
                                             "frac": None if lut_ms is None else stage_flops / lut_ms * 1e-9 / peak,
