@@ -62,14 +62,14 @@ int cached_plan(hb_plan** out, int dim, const int* n_pts, int degree, const doub
     HB_TRY(check_device());
     const int set = index_set_from_name(index_set);
     if (set < 0) { set_error("Invalid index set!"); return HB_ERR_INDEX_SET; }
-    if (dim < 1 || dim > HB_MAX_DIM || !n_pts) return HB_ERR_INVALID;
+    if (dim < 1 || dim > HB_MAX_DIM || !n_pts) return invalid(__func__);
     PlanKey key;
     key.dim = dim; key.degree = degree; key.set = set;
     key.n_pts.assign(n_pts, n_pts + dim);
     key.fourier.assign(dim, 0);
     if (do_fourier) key.fourier.assign(do_fourier, do_fourier + dim);
     size_t tot = 0;
-    for (int a = 0; a < dim; a++) { if (n_pts[a] < 1) return HB_ERR_INVALID; tot += n_pts[a]; }
+    for (int a = 0; a < dim; a++) { if (n_pts[a] < 1) return invalid(__func__); tot += n_pts[a]; }
     key.nodes.assign(nodes, nodes + tot);
     key.weights.assign(weights, weights + tot);
     uint64_t h = 1469598103934665603ull;
@@ -210,12 +210,12 @@ int hb_index_list(const char* index_set, int dim, int degree, uint32_t* out, siz
 }
 
 int hb_triangle_index(const uint32_t* m, int dim, uint32_t* index) {
-    if (!m || dim < 1) return HB_ERR_INVALID;
+    if (!m || dim < 1) return invalid(__func__);
     *index = triangle_index(m, dim);
     return HB_OK;
 }
 int hb_cube_index(const uint32_t* m, int dim, uint32_t* index) {
-    if (!m || dim < 1) return HB_ERR_INVALID;
+    if (!m || dim < 1) return invalid(__func__);
     *index = cube_index(m, dim);
     return HB_OK;
 }
@@ -236,7 +236,7 @@ int hb_index_positions(const char* index_set, int dim, int degree, const uint32_
 // ---------------------------------------------------------------------------------------------
 int hb_hermite_eval(const double* x, int n, int degree, double* out) {
     HB_TRY(check_device());
-    if (n < 0 || degree < 0) return HB_ERR_INVALID;
+    if (n < 0 || degree < 0) return invalid(__func__);
     if (n == 0) return HB_OK;
     std::lock_guard<std::mutex> lock(g_call_mutex);
     const int P = degree + 1;
@@ -602,9 +602,9 @@ int hb_integrate(int dim, const int* n_pts, const double* f, const double* nodes
 int hb_discretize(const char* body, int dim, const int* n_pts, const double* nodes, const double* translation,
                   const double* dilation, double* out, size_t out_len) {
     HB_TRY(check_device());
-    if (!body || dim < 1 || dim > HB_MAX_DIM || !n_pts || !nodes) return HB_ERR_INVALID;
+    if (!body || dim < 1 || dim > HB_MAX_DIM || !n_pts || !nodes) return invalid(__func__);
     size_t tot = 0, total = 1;
-    for (int a = 0; a < dim; a++) { if (n_pts[a] < 1) return HB_ERR_INVALID; tot += n_pts[a]; total *= n_pts[a]; }
+    for (int a = 0; a < dim; a++) { if (n_pts[a] < 1) return invalid(__func__); tot += n_pts[a]; total *= n_pts[a]; }
     if (out_len != total) { set_error("discretize: out_len %zu != grid size %zu", out_len, total); return HB_ERR_INVALID; }
     std::lock_guard<std::mutex> lock(g_call_mutex);
     HB_TRY(g_in.ensure(tot * 8));
@@ -619,7 +619,7 @@ int hb_discretize(const char* body, int dim, const int* n_pts, const double* nod
 // ---------------------------------------------------------------------------------------------
 static int triple_products_impl(int degree, bool fourier, double* out) {
     HB_TRY(check_device());
-    if (degree < 0) return HB_ERR_INVALID;
+    if (degree < 0) return invalid(__func__);
     if (fourier && (degree % 2 == 1)) { set_error("Use even degree for Fourier"); return HB_ERR_FOURIER_DEGREE; }
     const int P = degree + 1, Pp = (int)even_up(P), K = 2 * degree + 1;
     std::lock_guard<std::mutex> lock(g_call_mutex);
@@ -703,7 +703,7 @@ int hb_varf_sp(int dim, const int* n_pts, int degree, const double* f, const dou
 int hb_varf_function(int dim, const int* n_pts, int degree, const char* f_body, const double* translation,
                      const double* dilation, const double* nodes, const double* weights, const int* do_fourier,
                      const char* index_set, int mode, double* out, size_t n_polys) {
-    if (!f_body) return HB_ERR_INVALID;
+    if (!f_body) return invalid(__func__);
     std::lock_guard<std::mutex> lock(g_call_mutex);
     hb_plan* pl = nullptr;
     HB_TRY(varf_to_device(&pl, dim, n_pts, degree, nullptr, nodes, weights, do_fourier, index_set, mode, f_body, translation, dilation));
@@ -715,7 +715,7 @@ int hb_varf_function(int dim, const int* n_pts, int degree, const char* f_body, 
 int hb_varf_function_sp(int dim, const int* n_pts, int degree, const char* f_body, const double* translation,
                         const double* dilation, const double* nodes, const double* weights, const int* do_fourier,
                         const char* index_set, int mode, long long* nnz) {
-    if (!f_body) return HB_ERR_INVALID;
+    if (!f_body) return invalid(__func__);
     return varf_sp_impl(dim, n_pts, degree, nullptr, f_body, translation, dilation, nodes, weights, do_fourier, index_set, mode, nnz);
 }
 
@@ -740,7 +740,7 @@ static int varf_sp_impl(int dim, const int* n_pts, int degree, const double* f, 
 
 int hb_plan_varf_sp(hb_plan* plan, const double* d_f, int mode, long long row_begin, long long row_end, long long* nnz,
                     void* stream) {
-    if (!plan || !nnz) return HB_ERR_INVALID;
+    if (!plan || !nnz) return invalid(__func__);
     std::lock_guard<std::mutex> lock(g_call_mutex);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (row_begin < 0) row_begin = 0;
@@ -773,7 +773,7 @@ static int varfd_column_map(int dim, int degree, int direction, size_t n_polys, 
     const int set = set_or_err(index_set);
     if (set < 0) return HB_ERR_INDEX_SET;
     auto s = get_index_set(set, dim, degree);
-    if (!s || direction < 0 || direction >= dim) return HB_ERR_INVALID;
+    if (!s || direction < 0 || direction >= dim) return invalid(__func__);
     if (n_polys != s->size) { set_error("varfd: matrix size %zu != n_polys %u", n_polys, s->size); return HB_ERR_INVALID; }
     const int n = (int)n_polys;
     src.assign(n, -1);
@@ -845,7 +845,7 @@ static int tensorize_impl(int k, const double* const* inputs, const int* lens, c
         return HB_ERR_DEGREE;
     }
     auto full = get_index_set(set, dim, degree);
-    if (!full) return HB_ERR_INVALID;
+    if (!full) return invalid(__func__);
     if (out_n != full->size) { set_error("tensorize: output size %zu != %u", out_n, full->size); return HB_ERR_INVALID; }
     std::lock_guard<std::mutex> lock(g_call_mutex);
     TensorizeArgs a;
@@ -890,7 +890,7 @@ static int project_impl(const double* input, size_t n_in, int dim, const int* di
     HB_TRY(check_device());
     const int set = set_or_err(index_set);
     if (set < 0) return HB_ERR_INDEX_SET;
-    if (n_dirs < 1 || n_dirs > dim) return HB_ERR_INVALID;
+    if (n_dirs < 1 || n_dirs > dim) return invalid(__func__);
     int degree = 0;
     if (index_get_degree(set, dim, (long long)n_in, &degree)) {
         set_error("Can't find a degree with %zu polynomials in dimension %d", n_in, dim);
@@ -898,7 +898,7 @@ static int project_impl(const double* input, size_t n_in, int dim, const int* di
     }
     auto full = get_index_set(set, dim, degree);
     auto sub = get_index_set(set, n_dirs, degree);
-    if (!full || !sub) return HB_ERR_INVALID;
+    if (!full || !sub) return invalid(__func__);
     if (n_out != sub->size) { set_error("project: output size %zu != %u", n_out, sub->size); return HB_ERR_INVALID; }
     // sel[i] = position in the full set of sub-index i embedded on dirs (zeros elsewhere); project.cpp:48-56
     // scans the full set and writes aligned entries, which visits each sub-index at most once.
@@ -907,7 +907,7 @@ static int project_impl(const double* input, size_t n_in, int dim, const int* di
     for (uint32_t i = 0; i < sub->size; i++) {
         std::fill(m.begin(), m.end(), 0u);
         for (int j = 0; j < n_dirs; j++) {
-            if (dirs[j] < 0 || dirs[j] >= dim) return HB_ERR_INVALID;
+            if (dirs[j] < 0 || dirs[j] >= dim) return invalid(__func__);
             m[dirs[j]] = sub->list[(size_t)i * n_dirs + j];
         }
         sel[i] = full->position(m.data());
@@ -975,7 +975,7 @@ int hb_tensorize_mats_sp(int k, const long long* const* indptr, const int* const
         return HB_ERR_DEGREE;
     }
     auto full = get_index_set(set, dim, degree);
-    if (!full) return HB_ERR_INVALID;
+    if (!full) return invalid(__func__);
     // strides of the lexicographic box of the full set (axis 0 slowest)
     std::vector<long long> stride(dim, 1);
     for (int a = dim - 2; a >= 0; a--) stride[a] = stride[a + 1] * full->extent[a + 1];
@@ -1024,7 +1024,7 @@ int hb_project_mat_sp(const long long* indptr, const int* indices, const double*
     HB_TRY(check_device());
     const int set = set_or_err(index_set);
     if (set < 0) return HB_ERR_INDEX_SET;
-    if (n_dirs < 1 || n_dirs > dim) return HB_ERR_INVALID;
+    if (n_dirs < 1 || n_dirs > dim) return invalid(__func__);
     int degree = 0;
     if (index_get_degree(set, dim, (long long)n_in, &degree)) {
         set_error("Can't find a degree with %zu polynomials in dimension %d", n_in, dim);
@@ -1032,14 +1032,14 @@ int hb_project_mat_sp(const long long* indptr, const int* indices, const double*
     }
     auto full = get_index_set(set, dim, degree);
     auto sub = get_index_set(set, n_dirs, degree);
-    if (!full || !sub) return HB_ERR_INVALID;
+    if (!full || !sub) return invalid(__func__);
     // position in the sub-set of every ALIGNED multi-index of the full set (zero outside dirs), -1 otherwise
     std::vector<int> to_sub(full->size, -1);
     std::vector<uint32_t> m(dim);
     for (uint32_t i = 0; i < sub->size; i++) {
         std::fill(m.begin(), m.end(), 0u);
         for (int j = 0; j < n_dirs; j++) {
-            if (dirs[j] < 0 || dirs[j] >= dim) return HB_ERR_INVALID;
+            if (dirs[j] < 0 || dirs[j] >= dim) return invalid(__func__);
             m[dirs[j]] = sub->list[(size_t)i * n_dirs + j];
         }
         const int p = full->position(m.data());
@@ -1085,7 +1085,7 @@ int hb_inner(const double* s1, size_t n1, const double* s2, size_t n2, const int
     HB_TRY(check_device());
     const int set = set_or_err(index_set);
     if (set < 0) return HB_ERR_INDEX_SET;
-    if (nd1 < 1 || nd2 < 1) return HB_ERR_INVALID;
+    if (nd1 < 1 || nd2 < 1) return invalid(__func__);
     // merge the (increasing) direction lists: shared directions are contracted, the others survive
     // in increasing order (inner.cpp:61-84)
     std::vector<int> from1, slot, inner1, inner2;   // for every result axis: comes from s1? which axis there
@@ -1105,7 +1105,7 @@ int hb_inner(const double* s1, size_t n1, const double* s2, size_t n2, const int
     auto it1 = get_index_set(set, nd1, degree), it2 = get_index_set(set, nd2, degree);
     std::shared_ptr<const IndexSet> it_res = dim_res ? get_index_set(set, dim_res, degree) : nullptr;
     std::shared_ptr<const IndexSet> it_in = dim_in ? get_index_set(set, dim_in, degree) : nullptr;
-    if (!it1 || !it2 || (dim_res && !it_res) || (dim_in && !it_in)) return HB_ERR_INVALID;
+    if (!it1 || !it2 || (dim_res && !it_res) || (dim_in && !it_in)) return invalid(__func__);
     const int n_res = dim_res ? (int)it_res->size : 1, n_in = dim_in ? (int)it_in->size : 1;
     if (out_len != (size_t)n_res) { set_error("inner: output size %zu != %d", out_len, n_res); return HB_ERR_INVALID; }
     std::vector<int> ind1((size_t)n_res * n_in), ind2((size_t)n_res * n_in);
@@ -1171,14 +1171,14 @@ int hb_plan_discretize(hb_plan* plan, const char* body, const double* translatio
     return plan_discretize(plan, body, translation, dilation, d_f, static_cast<cudaStream_t>(stream));
 }
 int hb_plan_set_sqrt_weights(hb_plan* plan, int axis, const double* sqrt_w) {
-    if (!plan) return HB_ERR_INVALID;
+    if (!plan) return invalid(__func__);
     std::lock_guard<std::mutex> lock(g_call_mutex);
     return plan_set_sqrt_weights(plan, axis, sqrt_w);
 }
 int hb_plan_set_timing(hb_plan* plan, int on) { plan->timing = on != 0; plan->n_timed = 0; return HB_OK; }
 int hb_plan_timing_count(const hb_plan* plan) { return plan->n_timed; }
 int hb_plan_timing_get(hb_plan* plan, int i, int* tag, double* ms, double* padded_flops) {
-    if (i < 0 || i >= plan->n_timed) return HB_ERR_INVALID;
+    if (i < 0 || i >= plan->n_timed) return invalid(__func__);
     hb_plan::Timed& t = plan->timed[i];
     HB_CUDA(cudaEventSynchronize(t.e1));
     float el = 0;
@@ -1217,7 +1217,7 @@ int hb_dev_dgemm_scatter(int M, int N, int K, int batch, const double* A, long l
     return gemm_launch(g, static_cast<cudaStream_t>(stream));
 }
 int hb_dev_dgemm_ex(const hb_gemm_desc* q, void* stream) {
-    if (!q) return HB_ERR_INVALID;
+    if (!q) return invalid(__func__);
     GemmArgs g;
     g.M = q->M; g.N = q->N; g.K = q->K; g.batch = q->batch; g.batch_lo = q->batch_lo > 0 ? q->batch_lo : 1;
     g.A = q->A; g.lda = q->lda; g.strideA = q->strideA; g.strideA_lo = q->strideA_lo; g.a_mmajor = q->a_mmajor != 0;
@@ -1252,7 +1252,7 @@ int hb_dev_parity_pass(int merge, int d, const int* n, const int* split, const l
                        const long long* srt_stride, const long long* srt_par, long long batch, long long nat_bstride,
                        long long srt_bstride, int nat_pad_last, const double* in, double* out, void* stream) {
     HB_TRY(check_device());
-    if (d < 1 || d > HB_MAX_DIM || !n || !split || !nat_stride || !srt_stride || !srt_par) return HB_ERR_INVALID;
+    if (d < 1 || d > HB_MAX_DIM || !n || !split || !nat_stride || !srt_stride || !srt_par) return invalid(__func__);
     ParityNDArgs a;
     a.d = d;
     for (int k = 0; k < d; k++) {
@@ -1265,7 +1265,7 @@ int hb_dev_parity_pass(int merge, int d, const int* n, const int* split, const l
 }
 int hb_plan_parity_table(hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
                          long long* ld, long long* stride, void* stream) {
-    if (axis < 0 || axis >= plan->dim) return HB_ERR_INVALID;
+    if (axis < 0 || axis >= plan->dim) return invalid(__func__);
     Axis& A = plan->ax[axis];
     if (!A.symmetric_nodes) { set_error("hb_plan_parity_table: axis %d is not a bit-symmetric Hermite axis", axis); return HB_ERR_INVALID; }
     HB_TRY(ensure_combined_parity_tables(A, static_cast<cudaStream_t>(stream)));
@@ -1276,7 +1276,7 @@ int hb_plan_parity_table(hb_plan* plan, int axis, int kind, const double** ptr, 
         case 1: *ptr = A.cWT.d(); *rows = Pe; *cols = nh; *ld = nhp; *stride = Pe * nhp; break;
         case 2: *ptr = A.cPhi.d(); *rows = nh; *cols = Pe; *ld = Pep; *stride = nh * Pep; break;
         case 3: *ptr = A.cPhiT.d(); *rows = Pe; *cols = nh; *ld = nhp; *stride = Pe * nhp; break;
-        default: return HB_ERR_INVALID;
+        default: return invalid(__func__);
     }
     return HB_OK;
 }
@@ -1309,14 +1309,14 @@ int hb_dev_varfd(int dim, int degree, int direction, const double* var, long lon
 }
 int hb_plan_table(const hb_plan* plan, int axis, int kind, const double** ptr, long long* rows, long long* cols,
                   long long* ld) {
-    if (axis < 0 || axis >= plan->dim) return HB_ERR_INVALID;
+    if (axis < 0 || axis >= plan->dim) return invalid(__func__);
     const Axis& A = plan->ax[axis];
     switch (kind) {
         case 0: *ptr = A.plain.d(); *rows = A.n; *cols = A.P; *ld = A.Pp; break;   // phi_k(x_i)        [i][k]
         case 1: *ptr = A.wgt.d(); *rows = A.n; *cols = A.P; *ld = A.Pp; break;     // w_i phi_k(x_i)    [i][k]
         case 2: *ptr = A.plainT.d(); *rows = A.P; *cols = A.n; *ld = A.np; break;  // phi_k(x_i)        [k][i]
         case 3: *ptr = A.wgtT.d(); *rows = A.P; *cols = A.n; *ld = A.np; break;    // w_i phi_k(x_i)    [k][i]
-        default: return HB_ERR_INVALID;
+        default: return invalid(__func__);
     }
     return HB_OK;
 }

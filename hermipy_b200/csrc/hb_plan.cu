@@ -35,6 +35,10 @@ const char* last_error() {
     g_err[0] = 0;
     return g_err_out;
 }
+int invalid(const char* where) {
+    set_error("%s: invalid arguments", where);
+    return HB_ERR_INVALID;
+}
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error '%s' in %s", cudaGetErrorString(e), what);
     return HB_ERR_CUDA;

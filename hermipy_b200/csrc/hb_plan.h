@@ -13,6 +13,7 @@ namespace hb {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+int invalid(const char* where);   // sets "<where>: invalid arguments" and returns HB_ERR_INVALID
 void note_launch(int n = 1);
 int launch_status();  // counts one launch and maps cudaGetLastError() to a status
 

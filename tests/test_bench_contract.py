@@ -33,3 +33,16 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                           "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_both_arms_print_the_same_config():
+    """the driver compares `config` of the two arms byte for byte: both come from bench.workload_config(world)"""
+    sys.path.insert(0, ROOT)
+    import bench
+    import inspect
+    src = inspect.getsource(bench)
+    assert src.count("workload_config(") >= 3          # definition + one use per arm
+    for world in (1, 2, 8):
+        cfg = bench.workload_config(world)
+        assert set(cfg) == {"workload", "baseline_config", "l2", "parallelism"} and "c4" in cfg["workload"]
+        assert json.dumps(cfg) == json.dumps(bench.workload_config(world))

@@ -197,3 +197,48 @@ def test_row_sharded_resident_matrix_world2(n):
         assert sum(counts) == n
         np.testing.assert_allclose(y, A @ x, rtol=0, atol=1e-14 * np.abs(A).sum())
         assert np.array_equal(shifted, A - 0.25 * np.eye(n))
+
+
+def _gather_worker(rank, world, port_no, f_all, want, result):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dist_cpu_ops import CpuOps
+        from hermipy_b200.dist import ShardedParityTransform, parity_tables
+        n_pts, P = [8, 6, 6], [4, 4, 4]
+        tables = []
+        for n in n_pts:
+            x, w = gauss_hermite(n)
+            x, w = (x - x[::-1]) / 2, (w + w[::-1]) / 2
+            phi = port.hermite_eval(x, P[0] - 1)
+            tables.append(parity_tables(torch.from_numpy(phi.copy()), torch.from_numpy(phi * w[:, None])))
+        T = ShardedParityTransform(n_pts, P, tables, ops=CpuOps())
+        f = np.zeros(T.local_grid_shape())
+        f[..., :n_pts[2]] = f_all[T.local_x0()]
+        c = T.forward(torch.from_numpy(f).reshape(-1))
+        valid, pos = T.set_positions(P[0] - 1, "cube")
+        full = T.gather_coefficients(c, P[0] - 1, "cube")
+        result[rank] = (float(np.abs(full.numpy() - want).max()), int(valid.sum()), float(c[~valid].abs().sum()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_coefficients_into_the_reference_enumeration_world2():
+    """The sharded coefficient blocks assembled into ONE vector in the reference's enumeration order (the only
+    collective of the transform path besides the exchange) equal the naive-loop restatement of the transform."""
+    rng = np.random.default_rng(11)
+    n_pts, deg = [8, 6, 6], 3
+    f = rng.standard_normal(n_pts)
+    rules = [gauss_hermite(n) for n in n_pts]
+    nodes = [(r[0] - r[0][::-1]) / 2 for r in rules]
+    weights = [(r[1] + r[1][::-1]) / 2 for r in rules]
+    want = port.transform(deg, f, nodes, weights, True, index_set="cube")
+    result = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_gather_worker, args=(2, _free_port(), f, want, result), nprocs=2, join=True)
+    total_valid = 0
+    for rank in range(2):
+        err, n_valid, pad = result[rank]
+        assert err < 1e-13 and pad == 0.0, (rank, result[rank])
+        total_valid += n_valid
+    assert total_valid == (deg + 1) ** 3
