@@ -335,6 +335,9 @@ class ShardedParityTransform:
     Ownership.  The parity split pairs node x with -x, so rank r owns a SYMMETRIC pair of half-slabs of axis 0:
     with nh0 = n0/2 and sh = nh0/g, the nodes n0/2 - (r+1) sh ... n0/2 - r sh - 1 and their mirror images
     n0/2 + r sh ... n0/2 + (r+1) sh - 1 (`local_x0()` lists them; local array [2 sh][n1][n2 padded to even]).
+    Index sets other than the cube are handled through the box: `gather_coefficients` / `scatter_coefficients` move
+    between a coefficient vector in the reference's enumeration of ANY set contained in the box (triangle, cross, ...)
+    and the sharded box, whose cells outside the set are computed and dropped / zero.
     Coefficients stay sharded: the parity-sorted box c[m0'][m1' in slice][m2'] where an index k' of a sorted axis
     runs over the even basis functions first, then the odd ones, both blocks padded to the same size (`coef_index()`
     maps the local block to basis indices; pad cells are -1 and hold zeros); the slice of rank r is rows
@@ -614,6 +617,15 @@ class ShardedParityTransform:
         if self.world > 1:
             dist.all_reduce(full, group=self.group)
         return full
+
+    def scatter_coefficients(self, full, degree, index_set="cube"):
+        """Inverse of `gather_coefficients`: this rank's block of the parity-sorted coefficient box from a coefficient
+        vector in the reference's enumeration order (any index set contained in the box: cells outside the set are
+        zero), ready for `backward`.  No communication: every rank picks its own cells."""
+        valid, pos = self.set_positions(degree, index_set)
+        c = torch.zeros(self.local_coef_shape(), dtype=self.dtype, device=self.dev)
+        c[valid] = full[pos]
+        return c
 
 
 def plan_tables_as_tensors(plan):

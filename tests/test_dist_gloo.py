@@ -199,7 +199,7 @@ def test_row_sharded_resident_matrix_world2(n):
         assert np.array_equal(shifted, A - 0.25 * np.eye(n))
 
 
-def _gather_worker(rank, world, port_no, f_all, want, result):
+def _gather_worker(rank, world, port_no, f_all, want, want_tri, g_tri_ref, result):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -219,7 +219,16 @@ def _gather_worker(rank, world, port_no, f_all, want, result):
         c = T.forward(torch.from_numpy(f).reshape(-1))
         valid, pos = T.set_positions(P[0] - 1, "cube")
         full = T.gather_coefficients(c, P[0] - 1, "cube")
-        result[rank] = (float(np.abs(full.numpy() - want).max()), int(valid.sum()), float(c[~valid].abs().sum()))
+        # a set smaller than the box: gathered from the same block; scattered back it reproduces the projection
+        tri = T.gather_coefficients(c, P[0] - 1, "triangle")
+        err_tri = float(np.abs(tri.numpy() - want_tri).max())
+        c_tri = T.scatter_coefficients(tri, P[0] - 1, "triangle")
+        v_tri, _ = T.set_positions(P[0] - 1, "triangle")
+        ok_scatter = bool(torch.equal(c_tri[v_tri], c[v_tri]) and float(c_tri[~v_tri].abs().sum()) == 0.0)
+        g_tri = T.backward(c_tri).numpy()
+        err_back = float(np.abs(g_tri[..., :n_pts[2]] - g_tri_ref[T.local_x0()]).max())
+        result[rank] = (float(np.abs(full.numpy() - want).max()), int(valid.sum()), float(c[~valid].abs().sum()),
+                        err_tri, ok_scatter, err_back)
     finally:
         dist.destroy_process_group()
 
@@ -234,11 +243,13 @@ def test_gather_coefficients_into_the_reference_enumeration_world2():
     nodes = [(r[0] - r[0][::-1]) / 2 for r in rules]
     weights = [(r[1] + r[1][::-1]) / 2 for r in rules]
     want = port.transform(deg, f, nodes, weights, True, index_set="cube")
+    want_tri = port.transform(deg, f, nodes, weights, True, index_set="triangle")
+    g_tri_ref = port.transform(deg, want_tri, nodes, weights, False, index_set="triangle").reshape(n_pts)
     result = mp.get_context("spawn").Manager().dict()
-    mp.spawn(_gather_worker, args=(2, _free_port(), f, want, result), nprocs=2, join=True)
+    mp.spawn(_gather_worker, args=(2, _free_port(), f, want, want_tri, g_tri_ref, result), nprocs=2, join=True)
     total_valid = 0
     for rank in range(2):
-        err, n_valid, pad = result[rank]
-        assert err < 1e-13 and pad == 0.0, (rank, result[rank])
+        err, n_valid, pad, err_tri, ok_scatter, err_back = result[rank]
+        assert err < 1e-13 and pad == 0.0 and err_tri < 1e-13 and ok_scatter and err_back < 1e-12, (rank, result[rank])
         total_valid += n_valid
     assert total_valid == (deg + 1) ** 3
