@@ -40,8 +40,10 @@ sq = torch.stack([(((g - f) * sw) ** 2).sum(), ((f * sw) ** 2).sum()])
 if world > 1:
     dist.all_reduce(sq)
 full = T.gather_coefficients(c, degree, "cube")                     # whole vector, reference order, on every rank
+assert torch.equal(T.scatter_coefficients(full, degree, "cube"), c)   # ... and back to this rank's block
+tri = T.gather_coefficients(c, degree, "triangle")                 # any index set contained in the box
 if rank == 0:
-    print("%d GPU(s), %d^3 grid, degree %d: round trip error %.2e (weighted L2); |c_000| = %.6f; %d coefficients gathered"
-          % (world, n, degree, float((sq[0] / sq[1]).sqrt()), abs(float(full[0])), full.numel()))
+    print("%d GPU(s), %d^3 grid, degree %d: round trip error %.2e (weighted L2); |c_000| = %.6f; %d coefficients gathered "
+          "(cube), %d (triangle)" % (world, n, degree, float((sq[0] / sq[1]).sqrt()), abs(float(full[0])), full.numel(), tri.numel()))
 if world > 1:
     dist.destroy_process_group()
